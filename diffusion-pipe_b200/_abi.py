@@ -1,0 +1,19 @@
+"""ctypes signatures for the C-ABI entry points beyond the GEMM (kept in one place so that the CPU-side
+test can check every symbol of include/dpipe.h is both exported and declared)."""
+import ctypes
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_int64 = ctypes.c_int64
+c_float = ctypes.c_float
+
+SIGNATURES = {}
+
+
+def declare(l):
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(l, name, None)
+        if fn is None:
+            continue
+        fn.restype = restype
+        fn.argtypes = argtypes
