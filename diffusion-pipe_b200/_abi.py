@@ -17,3 +17,16 @@ def declare(l):
             continue
         fn.restype = restype
         fn.argtypes = argtypes
+
+
+class AttnArgs(ctypes.Structure):
+    _fields_ = [
+        ('q', c_void_p), ('k', c_void_p), ('v', c_void_p),
+        ('o', c_void_p), ('ldo', c_int64),
+        ('lse', c_void_p),
+        ('batch', c_int), ('heads', c_int), ('seq_q', c_int), ('seq_k', c_int),
+        ('scale', c_float),
+    ]
+
+
+SIGNATURES['dpipe_attn_fwd'] = (c_int, [ctypes.POINTER(AttnArgs), c_void_p])

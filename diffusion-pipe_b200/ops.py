@@ -89,3 +89,27 @@ def make_qkv_epilogue(q, k, v, q_norm_w, k_norm_w, rope_cos, rope_sin, heads, se
     e.n_qkv = 3 * heads * 128
     e.eps = eps
     return e
+
+
+def attn_fwd(q, k, v, out=None, lse=None, scale=None):
+    """softmax(q k^T * scale) v.  q: [B,H,Lq,128], k/v: [B,H,Lk,128] (bf16, contiguous).
+    Returns (o [B*Lq, >=H*128] token-major, lse [B,H,Lq] fp32 in the log2 domain)."""
+    from ._abi import AttnArgs
+    for t, n in ((q, 'q'), (k, 'k'), (v, 'v')):
+        _req_bf16(t, n)
+        if not t.is_contiguous() or t.shape[-1] != 128:
+            raise ValueError(f'{n} must be contiguous [B,H,L,128]')
+    B, H, Lq, _ = q.shape
+    Lk = k.shape[2]
+    if out is None:
+        out = torch.empty((B * Lq, H * 128), dtype=torch.bfloat16, device=q.device)
+    if lse is None:
+        lse = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device)
+    a = AttnArgs()
+    a.q, a.k, a.v = _ptr(q), _ptr(k), _ptr(v)
+    a.o, a.ldo = _ptr(out), out.stride(0)
+    a.lse = _ptr(lse)
+    a.batch, a.heads, a.seq_q, a.seq_k = B, H, Lq, Lk
+    a.scale = float(scale if scale is not None else 128 ** -0.5)
+    check(lib().dpipe_attn_fwd(ctypes.byref(a), _stream()), 'dpipe_attn_fwd')
+    return out, lse

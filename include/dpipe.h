@@ -87,6 +87,24 @@ typedef struct dpipe_gemm_args {
 
 int dpipe_gemm_bf16(const dpipe_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Fused attention (FlashAttention-style, head_dim 128, non-causal) on tcgen05 + TMEM.           */
+/* replaces: torch SDPA dispatched by the diffusers Flux attention processor invoked from        */
+/*           models/flux.py:502,525; flash_attn_varlen_func at models/wan/attention.py:108-122.  */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct dpipe_attn_args {
+  const void* q;   /* bf16 [batch, heads, seq_q, 128] contiguous */
+  const void* k;   /* bf16 [batch, heads, seq_k, 128] */
+  const void* v;   /* bf16 [batch, heads, seq_k, 128] */
+  void* o;         /* bf16 token-major [batch*seq_q, ldo]; head h occupies columns [128h, 128h+128) */
+  int64_t ldo;
+  float* lse;      /* fp32 [batch, heads, seq_q]: log2-domain logsumexp = max*scale*log2(e) + log2(sum); may be NULL (fwd) */
+  int batch, heads, seq_q, seq_k;
+  float scale;     /* softmax scale, 1/sqrt(128) for Flux */
+} dpipe_attn_args;
+
+int dpipe_attn_fwd(const dpipe_attn_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
