@@ -30,3 +30,18 @@ class AttnArgs(ctypes.Structure):
 
 
 SIGNATURES['dpipe_attn_fwd'] = (c_int, [ctypes.POINTER(AttnArgs), c_void_p])
+
+
+class AttnBwdArgs(ctypes.Structure):
+    _fields_ = [
+        ('q', c_void_p), ('k', c_void_p), ('v', c_void_p),
+        ('o', c_void_p), ('ldo', c_int64),
+        ('d_o', c_void_p), ('lddo', c_int64),
+        ('lse', c_void_p), ('delta', c_void_p),
+        ('dq', c_void_p), ('dk', c_void_p), ('dv', c_void_p),
+        ('batch', c_int), ('heads', c_int), ('seq_q', c_int), ('seq_k', c_int),
+        ('scale', c_float),
+    ]
+
+
+SIGNATURES['dpipe_attn_bwd'] = (c_int, [ctypes.POINTER(AttnBwdArgs), c_void_p])

@@ -1,0 +1,542 @@
+// Fused attention backward for sm_100a (head_dim 128, non-causal), three kernels:
+//
+//   attn_bwd_delta    D[b,h,q] = sum_d O*dO                       (HBM-bound, one warp per (token, head))
+//   attn_bwd_dkv      one CTA per 128-key tile, loops over query tiles:
+//                        St  = K Q^T          (SS)     -> TMEM            Pt  = exp2(St*c - LSE[q])
+//                        dPt = V dO^T         (SS)     -> TMEM            dSt = Pt * (dPt - D[q])
+//                        dV += Pt  dO         (TS: Pt / dSt are read from TMEM, dO / Q tiles re-used MN-major)
+//                        dK += dSt Q
+//   attn_bwd_dq       one CTA per 128-query tile, loops over key tiles:
+//                        S = Q K^T, dP = dO V^T (SS) ; dS = P*(dP - D) ; dQ += dS K (TS, K tile re-used MN-major)
+//
+// Splitting dQ from dK/dV recomputes S and dP once more (7 instead of 5 tile GEMMs) but needs no atomics and no fp32
+// dQ staging buffer.  The transposed formulation in dkv makes P^T / dS^T land row-per-thread in TMEM so they can feed
+// tcgen05.mma as the A operand without touching shared memory.
+//
+// In both kernels 8 softmax warps share a tile: warp w owns TMEM lane quarter (w & 3) and column half (w-4)/4.
+// bf16 P / dS for columns [64h, 64h+64) are written over columns [64h, 64h+32) of the fp32 tile they came from, so each
+// warp only overwrites columns it has already read.
+//
+// LSE is the log2-domain logsumexp written by attn_fwd.  Outputs dQ/dK/dV are head-major [B,H,L,128] bf16.
+// Replaces flash-attn / SDPA backward reached through autograd from models/flux.py:502,525.
+#include "host_util.h"
+#include "sm100_common.cuh"
+
+namespace dpipe {
+
+constexpr int AB_THREADS = 384;
+constexpr int BT = 128;  // tile edge (queries and keys)
+constexpr int BHALF = 128 * 64 * 2;
+constexpr int BTILE = 2 * BHALF;  // 32 KiB
+constexpr int AB_SMEM_BYTES = 6 * BTILE + 4 * 512 /*lse,D x 2 stages*/ + 1024 + 256;
+
+struct AttnBwdParams {
+  const float* lse;    // [B,H,Lq] log2 domain
+  const float* delta;  // [B,H,Lq]
+  __nv_bfloat16* dq;   // [B,H,Lq,128]
+  __nv_bfloat16* dk;   // [B,H,Lk,128]
+  __nv_bfloat16* dv;   // [B,H,Lk,128]
+  int batch, heads, seq_q, seq_k;
+  float scale_log2, scale;
+};
+
+// K-major operand tile [128 rows][128 d] as two 64-wide halves: byte offset of k-step `k` (16 d per step)
+__device__ __forceinline__ uint32_t kmajor_off(int k) { return (k >> 2) * BHALF + (k & 3) * 32; }
+// TMEM column of the packed bf16 pair for logical column c (see header comment)
+__device__ __forceinline__ uint32_t packed_col(int kstep) { return (kstep < 4) ? kstep * 8 : 64 + (kstep - 4) * 8; }
+
+// ---------------------------------------------------------------------------------------------
+__global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ o, int64_t ldo,
+                                      const __nv_bfloat16* __restrict__ d_o, int64_t lddo, float* __restrict__ delta,
+                                      int batch, int heads, int seq) {
+  const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int64_t total = (int64_t)batch * seq * heads;
+  if (gw >= total) return;
+  const int h = gw % heads;
+  const int64_t tok = gw / heads;  // b*seq + q
+  const uint2 a = *reinterpret_cast<const uint2*>(o + tok * ldo + h * 128 + lane * 4);
+  const uint2 b = *reinterpret_cast<const uint2*>(d_o + tok * lddo + h * 128 + lane * 4);
+  float s = bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) +
+            bf16_hi(a.y) * bf16_hi(b.y);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) {
+    const int bb = tok / seq, q = tok % seq;
+    delta[((int64_t)bb * heads + h) * seq + q] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dK / dV
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                    const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do,
+                    const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* k_smem = smem;
+  uint8_t* v_smem = smem + BTILE;
+  uint8_t* q_smem = smem + 2 * BTILE;   // 2 stages
+  uint8_t* do_smem = smem + 4 * BTILE;  // 2 stages
+  float* lse_smem = reinterpret_cast<float*>(smem + 6 * BTILE);  // [2][128]
+  float* dl_smem = lse_smem + 256;                               // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * BTILE + 4 * 512);
+  uint64_t* kv_full = bars;        // [1]
+  uint64_t* q_full = bars + 1;     // [2]
+  uint64_t* q_empty = bars + 3;    // [2]
+  uint64_t* do_full = bars + 5;    // [2]
+  uint64_t* do_empty = bars + 7;   // [2]
+  uint64_t* st_full = bars + 9;    // MMA -> softmax
+  uint64_t* dpt_full = bars + 10;  // MMA -> softmax
+  uint64_t* p_ready = bars + 11;   // softmax -> MMA (8 warps)
+  uint64_t* ds_ready = bars + 12;  // softmax -> MMA (8 warps)
+  uint64_t* acc_done = bars + 13;  // MMA -> epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const uint32_t warp = warp_id_uniform();
+  const uint32_t lane = lane_id();
+  const int kv0 = blockIdx.x * BT;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int bh = b * p.heads + head;
+  const int nq = (p.seq_q + BT - 1) / BT;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tma_q); tma_prefetch_desc(&tma_k); tma_prefetch_desc(&tma_v); tma_prefetch_desc(&tma_do);
+  }
+  if (warp == 1 && elect_one()) {
+    mbar_init(smem_u32(kv_full), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&q_full[s]), 1); mbar_init(smem_u32(&q_empty[s]), 1);
+      mbar_init(smem_u32(&do_full[s]), 1); mbar_init(smem_u32(&do_empty[s]), 1);
+    }
+    mbar_init(smem_u32(st_full), 1); mbar_init(smem_u32(dpt_full), 1);
+    mbar_init(smem_u32(p_ready), 8); mbar_init(smem_u32(ds_ready), 8);
+    mbar_init(smem_u32(acc_done), 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<1>(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // TMEM: St [0,128)  dPt [128,256)  dV [256,384)  dK [384,512)
+  const uint32_t T_ST = tmem_base, T_DPT = tmem_base + 128, T_DV = tmem_base + 256, T_DK = tmem_base + 384;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t kvb = smem_u32(kv_full);
+      mbar_expect_tx(kvb, 2 * BTILE);
+      for (int h = 0; h < 2; ++h) {
+        tma_load_3d(&tma_k, kvb, smem_u32(k_smem + h * BHALF), h * 64, kv0, bh, kEvictFirst);
+        tma_load_3d(&tma_v, kvb, smem_u32(v_smem + h * BHALF), h * 64, kv0, bh, kEvictFirst);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nq; ++j) {
+        const int q0 = j * BT;
+        mbar_wait(smem_u32(&q_empty[stage]), phase ^ 1);
+        const uint32_t qb = smem_u32(&q_full[stage]);
+        mbar_expect_tx(qb, BTILE);
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(&tma_q, qb, smem_u32(q_smem + stage * BTILE + h * BHALF), h * 64, q0, bh, kEvictLast);
+        mbar_wait(smem_u32(&do_empty[stage]), phase ^ 1);
+        const uint32_t db = smem_u32(&do_full[stage]);
+        mbar_expect_tx(db, BTILE);
+        for (int h = 0; h < 2; ++h)
+          tma_load_4d(&tma_do, db, smem_u32(do_smem + stage * BTILE + h * BHALF), h * 64, q0, head, b, kEvictLast);
+        if (++stage == 2) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_ss = make_idesc_bf16(BT, BT, false, false);
+      constexpr uint32_t idesc_ts = make_idesc_bf16(BT, 128, false, true);
+      mbar_wait(smem_u32(kv_full), 0);
+      const uint32_t kb = smem_u32(k_smem), vb = smem_u32(v_smem);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nq; ++j) {
+        const uint32_t qb = smem_u32(q_smem + stage * BTILE), dob = smem_u32(do_smem + stage * BTILE);
+        mbar_wait(smem_u32(&q_full[stage]), phase);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // St[kv, q] = K Q^T
+          umma_ss<1>(T_ST, make_smem_desc(kb + kmajor_off(k), 16, 1024), make_smem_desc(qb + kmajor_off(k), 16, 1024),
+                     idesc_ss, k != 0);
+        umma_commit<1>(smem_u32(st_full));
+        mbar_wait(smem_u32(&do_full[stage]), phase);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dPt[kv, q] = V dO^T
+          umma_ss<1>(T_DPT, make_smem_desc(vb + kmajor_off(k), 16, 1024), make_smem_desc(dob + kmajor_off(k), 16, 1024),
+                     idesc_ss, k != 0);
+        umma_commit<1>(smem_u32(dpt_full));
+        mbar_wait(smem_u32(p_ready), j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dV[kv, d] += Pt[kv, q] dO[q, d]   (dO tile read MN-major: 16 queries per step)
+          umma_ts(T_DV, T_ST + packed_col(k), make_smem_desc(dob + k * 2048, BHALF, 1024), idesc_ts, (j | k) != 0);
+        umma_commit<1>(smem_u32(&do_empty[stage]));
+        mbar_wait(smem_u32(ds_ready), j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dK[kv, d] += dSt[kv, q] Q[q, d]
+          umma_ts(T_DK, T_DPT + packed_col(k), make_smem_desc(qb + k * 2048, BHALF, 1024), idesc_ts, (j | k) != 0);
+        umma_commit<1>(smem_u32(&q_empty[stage]));
+        if (++stage == 2) { stage = 0; phase ^= 1; }
+      }
+      umma_commit<1>(smem_u32(acc_done));
+    }
+  } else if (warp >= 4) {
+    const uint32_t quad = warp & 3;
+    const int half = (warp - 4) >> 2;          // column half of the tile this warp handles
+    const int sm_tid = (warp - 4) * 32 + lane;  // 0..255 among softmax threads
+    const uint32_t lane_base = (quad * 32u) << 16;
+    const float c = p.scale_log2;
+    for (int j = 0; j < nq; ++j) {
+      const int q0 = j * BT;
+      const int st = j & 1;
+      // stage LSE / D of this query tile (invalid queries get +inf so their probabilities vanish)
+      {
+        const int t = sm_tid & 127;
+        const int q = q0 + t;
+        if (sm_tid < 128) lse_smem[st * 128 + t] = (q < p.seq_q) ? p.lse[(int64_t)bh * p.seq_q + q] : INFINITY;
+        else dl_smem[st * 128 + t] = (q < p.seq_q) ? p.delta[(int64_t)bh * p.seq_q + q] : 0.f;
+      }
+      named_bar_sync(1, 256);
+      const float* lse_s = lse_smem + st * 128 + half * 64;
+      const float* dl_s = dl_smem + st * 128 + half * 64;
+      float pv[64];
+      mbar_wait(smem_u32(st_full), j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t r[32], pk[16];
+        tmem_ld_x32(T_ST + lane_base + half * 64 + cc * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int x = 0; x < 32; x += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(r[x]), c, -lse_s[cc * 32 + x]));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(r[x + 1]), c, -lse_s[cc * 32 + x + 1]));
+          pv[cc * 32 + x] = p0; pv[cc * 32 + x + 1] = p1;
+          pk[x >> 1] = pack_bf16(p0, p1);
+        }
+        tmem_st_x16(T_ST + lane_base + half * 64 + cc * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(p_ready));
+      mbar_wait(smem_u32(dpt_full), j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t r[32], pk[16];
+        tmem_ld_x32(T_DPT + lane_base + half * 64 + cc * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int x = 0; x < 32; x += 2) {
+          const float d0 = pv[cc * 32 + x] * (__uint_as_float(r[x]) - dl_s[cc * 32 + x]);
+          const float d1 = pv[cc * 32 + x + 1] * (__uint_as_float(r[x + 1]) - dl_s[cc * 32 + x + 1]);
+          pk[x >> 1] = pack_bf16(d0, d1);
+        }
+        tmem_st_x16(T_DPT + lane_base + half * 64 + cc * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(ds_ready));
+    }
+    // epilogue: each thread stores 64 columns of its key row of dV and dK
+    mbar_wait(smem_u32(acc_done), 0);
+    tc_fence_after();
+    const int kv = kv0 + quad * 32 + lane;
+    const bool ok = kv < p.seq_k;
+    const int64_t o = ((int64_t)bh * p.seq_k + kv) * 128 + half * 64;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t t = (which == 0 ? T_DV : T_DK) + lane_base + half * 64;
+      __nv_bfloat16* dst = (which == 0 ? p.dv : p.dk) + o;
+      const float mul = which == 0 ? 1.0f : p.scale;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t r[32];
+        tmem_ld_x32(t + cc * 32, r);
+        tmem_ld_wait();
+        if (ok) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + cc * 32);
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            uint4 qv;
+            qv.x = pack_bf16(__uint_as_float(r[x * 8 + 0]) * mul, __uint_as_float(r[x * 8 + 1]) * mul);
+            qv.y = pack_bf16(__uint_as_float(r[x * 8 + 2]) * mul, __uint_as_float(r[x * 8 + 3]) * mul);
+            qv.z = pack_bf16(__uint_as_float(r[x * 8 + 4]) * mul, __uint_as_float(r[x * 8 + 5]) * mul);
+            qv.w = pack_bf16(__uint_as_float(r[x * 8 + 6]) * mul, __uint_as_float(r[x * 8 + 7]) * mul);
+            d4[x] = qv;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dQ
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                   const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do,
+                   const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* q_smem = smem;
+  uint8_t* do_smem = smem + BTILE;
+  uint8_t* k_smem = smem + 2 * BTILE;  // 2 stages
+  uint8_t* v_smem = smem + 4 * BTILE;  // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * BTILE + 4 * 512);
+  uint64_t* qdo_full = bars;       // [1]
+  uint64_t* k_full = bars + 1;     // [2]
+  uint64_t* k_empty = bars + 3;    // [2]
+  uint64_t* v_full = bars + 5;     // [2]
+  uint64_t* v_empty = bars + 7;    // [2]
+  uint64_t* s_full = bars + 9;     // [2] double-buffered S
+  uint64_t* dp_full = bars + 11;
+  uint64_t* ds_ready = bars + 12;  // 8 warps
+  uint64_t* acc_done = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const uint32_t warp = warp_id_uniform();
+  const uint32_t lane = lane_id();
+  const int q0 = blockIdx.x * BT;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int bh = b * p.heads + head;
+  const int nkv = (p.seq_k + BT - 1) / BT;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tma_q); tma_prefetch_desc(&tma_k); tma_prefetch_desc(&tma_v); tma_prefetch_desc(&tma_do);
+  }
+  if (warp == 1 && elect_one()) {
+    mbar_init(smem_u32(qdo_full), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&k_full[s]), 1); mbar_init(smem_u32(&k_empty[s]), 1);
+      mbar_init(smem_u32(&v_full[s]), 1); mbar_init(smem_u32(&v_empty[s]), 1);
+      mbar_init(smem_u32(&s_full[s]), 1);
+    }
+    mbar_init(smem_u32(dp_full), 1);
+    mbar_init(smem_u32(ds_ready), 8);
+    mbar_init(smem_u32(acc_done), 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<1>(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // TMEM: S0 [0,128) S1 [128,256) dP [256,384) dQ [384,512)
+  const uint32_t T_DP = tmem_base + 256, T_DQ = tmem_base + 384;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t qb = smem_u32(qdo_full);
+      mbar_expect_tx(qb, 2 * BTILE);
+      for (int h = 0; h < 2; ++h) {
+        tma_load_3d(&tma_q, qb, smem_u32(q_smem + h * BHALF), h * 64, q0, bh, kEvictFirst);
+        tma_load_4d(&tma_do, qb, smem_u32(do_smem + h * BHALF), h * 64, q0, head, b, kEvictFirst);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nkv; ++j) {
+        const int kv0 = j * BT;
+        mbar_wait(smem_u32(&k_empty[stage]), phase ^ 1);
+        const uint32_t kb = smem_u32(&k_full[stage]);
+        mbar_expect_tx(kb, BTILE);
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(&tma_k, kb, smem_u32(k_smem + stage * BTILE + h * BHALF), h * 64, kv0, bh, kEvictLast);
+        mbar_wait(smem_u32(&v_empty[stage]), phase ^ 1);
+        const uint32_t vb = smem_u32(&v_full[stage]);
+        mbar_expect_tx(vb, BTILE);
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(&tma_v, vb, smem_u32(v_smem + stage * BTILE + h * BHALF), h * 64, kv0, bh, kEvictLast);
+        if (++stage == 2) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_ss = make_idesc_bf16(BT, BT, false, false);
+      constexpr uint32_t idesc_ts = make_idesc_bf16(BT, 128, false, true);
+      const uint32_t qb = smem_u32(q_smem), dob = smem_u32(do_smem);
+      auto issue_s = [&](int jj, int stg) {   // S_{jj&1}[q, kv] = Q K^T
+        const uint32_t kb = smem_u32(k_smem + stg * BTILE);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss<1>(tmem_base + (jj & 1) * 128, make_smem_desc(qb + kmajor_off(k), 16, 1024),
+                     make_smem_desc(kb + kmajor_off(k), 16, 1024), idesc_ss, k != 0);
+        umma_commit<1>(smem_u32(&s_full[jj & 1]));
+      };
+      auto issue_dp = [&](int stg) {          // dP[q, kv] = dO V^T
+        const uint32_t vb = smem_u32(v_smem + stg * BTILE);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss<1>(T_DP, make_smem_desc(dob + kmajor_off(k), 16, 1024), make_smem_desc(vb + kmajor_off(k), 16, 1024),
+                     idesc_ss, k != 0);
+        umma_commit<1>(smem_u32(dp_full));
+      };
+      mbar_wait(smem_u32(qdo_full), 0);
+      mbar_wait(smem_u32(&k_full[0]), 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      mbar_wait(smem_u32(&v_full[0]), 0);
+      tc_fence_after();
+      issue_dp(0);
+      umma_commit<1>(smem_u32(&v_empty[0]));
+      for (int j = 0; j < nkv; ++j) {
+        const int stg = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const bool more = j + 1 < nkv;
+        const int nstg = (j + 1) & 1;
+        const uint32_t nph = ((j + 1) >> 1) & 1;
+        if (more) {   // S(j+1) into the other S buffer while the softmax warps work on tile j
+          mbar_wait(smem_u32(&k_full[nstg]), nph);
+          tc_fence_after();
+          issue_s(j + 1, nstg);
+        }
+        mbar_wait(smem_u32(ds_ready), j & 1);
+        tc_fence_after();
+        const uint32_t kb = smem_u32(k_smem + stg * BTILE);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dQ[q, d] += dS[q, kv] K[kv, d]   (K tile read MN-major)
+          umma_ts(T_DQ, T_DP + packed_col(k), make_smem_desc(kb + k * 2048, BHALF, 1024), idesc_ts, (j | k) != 0);
+        umma_commit<1>(smem_u32(&k_empty[stg]));
+        (void)ph;
+        if (more) {
+          mbar_wait(smem_u32(&v_full[nstg]), nph);
+          tc_fence_after();
+          issue_dp(nstg);
+          umma_commit<1>(smem_u32(&v_empty[nstg]));
+        }
+      }
+      umma_commit<1>(smem_u32(acc_done));
+    }
+  } else if (warp >= 4) {
+    const uint32_t quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const uint32_t lane_base = (quad * 32u) << 16;
+    const int q = q0 + quad * 32 + lane;
+    const bool ok = q < p.seq_q;
+    const float lse = ok ? p.lse[(int64_t)bh * p.seq_q + q] : INFINITY;
+    const float dl = ok ? p.delta[(int64_t)bh * p.seq_q + q] : 0.f;
+    const float c = p.scale_log2;
+    for (int j = 0; j < nkv; ++j) {
+      const int valid = min(BT, p.seq_k - j * BT) - half * 64;  // valid keys within this warp's 64 columns
+      float pv[64];
+      mbar_wait(smem_u32(&s_full[j & 1]), (j >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t r[32];
+        tmem_ld_x32(tmem_base + (j & 1) * 128 + lane_base + half * 64 + cc * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int x = 0; x < 32; ++x) {
+          float pp = fast_exp2(fmaf(__uint_as_float(r[x]), c, -lse));
+          pv[cc * 32 + x] = (cc * 32 + x < valid) ? pp : 0.f;
+        }
+      }
+      mbar_wait(smem_u32(dp_full), j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t r[32], pk[16];
+        tmem_ld_x32(T_DP + lane_base + half * 64 + cc * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int x = 0; x < 32; x += 2)
+          pk[x >> 1] = pack_bf16(pv[cc * 32 + x] * (__uint_as_float(r[x]) - dl),
+                                 pv[cc * 32 + x + 1] * (__uint_as_float(r[x + 1]) - dl));
+        tmem_st_x16(T_DP + lane_base + half * 64 + cc * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(ds_ready));
+    }
+    mbar_wait(smem_u32(acc_done), 0);
+    tc_fence_after();
+    __nv_bfloat16* dst = p.dq + ((int64_t)bh * p.seq_q + q) * 128 + half * 64;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      uint32_t r[32];
+      tmem_ld_x32(T_DQ + lane_base + half * 64 + cc * 32, r);
+      tmem_ld_wait();
+      if (ok) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + cc * 32);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          uint4 qv;
+          qv.x = pack_bf16(__uint_as_float(r[x * 8 + 0]) * p.scale, __uint_as_float(r[x * 8 + 1]) * p.scale);
+          qv.y = pack_bf16(__uint_as_float(r[x * 8 + 2]) * p.scale, __uint_as_float(r[x * 8 + 3]) * p.scale);
+          qv.z = pack_bf16(__uint_as_float(r[x * 8 + 4]) * p.scale, __uint_as_float(r[x * 8 + 5]) * p.scale);
+          qv.w = pack_bf16(__uint_as_float(r[x * 8 + 6]) * p.scale, __uint_as_float(r[x * 8 + 7]) * p.scale);
+          d4[x] = qv;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
+}  // namespace dpipe
+
+extern "C" int dpipe_attn_bwd(const dpipe_attn_bwd_args* a, void* stream) {
+  using namespace dpipe;
+  if (!a || !a->q || !a->k || !a->v || !a->o || !a->d_o || !a->lse || !a->delta || !a->dq || !a->dk || !a->dv)
+    return fail(DPIPE_EINVAL, "dpipe_attn_bwd: null argument");
+  if (a->batch <= 0 || a->heads <= 0 || a->seq_q <= 0 || a->seq_k <= 0) return fail(DPIPE_EINVAL, "dpipe_attn_bwd: empty problem");
+  if (a->ldo % 8 || a->lddo % 8) return fail(DPIPE_EINVAL, "dpipe_attn_bwd: ldo/lddo must be multiples of 8");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int B = a->batch, H = a->heads, Lq = a->seq_q, Lk = a->seq_k;
+  {
+    const int64_t warps = (int64_t)B * Lq * H;
+    const int wpb = 8;
+    attn_bwd_delta_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(a->o), a->ldo, reinterpret_cast<const __nv_bfloat16*>(a->d_o), a->lddo,
+        a->delta, B, H, Lq);
+  }
+  CUtensorMap tq, tk, tv, tdo;
+  const uint64_t bh = (uint64_t)B * H;
+  int rc;
+  if ((rc = make_tmap_3d_bf16(&tq, a->q, 128, Lq, bh, 128, (uint64_t)Lq * 128, 64, BT, 1))) return rc;
+  if ((rc = make_tmap_3d_bf16(&tk, a->k, 128, Lk, bh, 128, (uint64_t)Lk * 128, 64, BT, 1))) return rc;
+  if ((rc = make_tmap_3d_bf16(&tv, a->v, 128, Lk, bh, 128, (uint64_t)Lk * 128, 64, BT, 1))) return rc;
+  {
+    const uint64_t dims[4] = {128, (uint64_t)Lq, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)a->lddo, 128, (uint64_t)Lq * a->lddo};
+    const uint32_t box[4] = {64, BT, 1, 1};
+    if ((rc = make_tmap_4d_bf16(&tdo, a->d_o, dims, strides, box))) return rc;
+  }
+  static bool configured = false;
+  if (!configured) {
+    DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
+    DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
+    configured = true;
+  }
+  AttnBwdParams p;
+  p.lse = a->lse; p.delta = a->delta;
+  p.dq = reinterpret_cast<__nv_bfloat16*>(a->dq);
+  p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk);
+  p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv);
+  p.batch = B; p.heads = H; p.seq_q = Lq; p.seq_k = Lk;
+  p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
+  attn_bwd_dkv_kernel<<<dim3((Lk + BT - 1) / BT, H, B), AB_THREADS, AB_SMEM_BYTES, s>>>(tq, tk, tv, tdo, p);
+  DPIPE_CUDA_CHECK(cudaGetLastError());
+  attn_bwd_dq_kernel<<<dim3((Lq + BT - 1) / BT, H, B), AB_THREADS, AB_SMEM_BYTES, s>>>(tq, tk, tv, tdo, p);
+  DPIPE_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -30,12 +30,6 @@ constexpr int TILE_BYTES = 2 * HALF_TILE_BYTES; // 32 KiB
 constexpr int KV_STAGES = 2;
 constexpr int ATT_SMEM_BYTES = 2 * TILE_BYTES + 2 * KV_STAGES * TILE_BYTES + 1024 + 256;
 
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
 struct AttnFwdParams {
   __nv_bfloat16* o;
   int64_t ldo;

@@ -77,6 +77,25 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_
   return 0;
 }
 
+int make_tmap_4d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_elems[3],
+                      const uint32_t box[4]) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(DPIPE_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(DPIPE_EINVAL, "TMA operand must be 16B aligned");
+  cuuint64_t d[4], st[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i < 3; ++i) {
+    st[i] = strides_elems[i] * 2;
+    if (st[i] % 16 != 0) return fail(DPIPE_EINVAL, "TMA strides must be multiples of 16 bytes");
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), d, st, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DPIPE_ECUDA, "cuTensorMapEncodeTiled(4d) failed: %d", (int)r);
+  return 0;
+}
+
 int num_sms() {
   static int cached[64];
   static bool have[64];

@@ -29,6 +29,10 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_
                       uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box0, uint32_t box1,
                       uint32_t box2);
 
+// 4-D variant for token-major [batch, seq, heads, 128] activations viewed as {d, seq, head, batch}
+int make_tmap_4d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_elems[3],
+                      const uint32_t box[4]);
+
 int num_sms();  // SM count of the current device (cached per device)
 
 }  // namespace dpipe

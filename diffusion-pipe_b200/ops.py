@@ -113,3 +113,30 @@ def attn_fwd(q, k, v, out=None, lse=None, scale=None):
     a.scale = float(scale if scale is not None else 128 ** -0.5)
     check(lib().dpipe_attn_fwd(ctypes.byref(a), _stream()), 'dpipe_attn_fwd')
     return out, lse
+
+
+def attn_bwd(q, k, v, o, d_o, lse, scale=None, dq=None, dk=None, dv=None, delta=None):
+    """Backward of attn_fwd.  o / d_o are token-major [B*Lq, >=H*128]; returns head-major (dq, dk, dv)."""
+    from ._abi import AttnBwdArgs
+    B, H, Lq, _ = q.shape
+    Lk = k.shape[2]
+    for t, n in ((q, 'q'), (k, 'k'), (v, 'v')):
+        _req_bf16(t, n)
+        if not t.is_contiguous():
+            raise ValueError(f'{n} must be contiguous')
+    _req_bf16(o, 'o')
+    _req_bf16(d_o, 'd_o')
+    dq = torch.empty_like(q) if dq is None else dq
+    dk = torch.empty_like(k) if dk is None else dk
+    dv = torch.empty_like(v) if dv is None else dv
+    delta = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device) if delta is None else delta
+    a = AttnBwdArgs()
+    a.q, a.k, a.v = _ptr(q), _ptr(k), _ptr(v)
+    a.o, a.ldo = _ptr(o), o.stride(0)
+    a.d_o, a.lddo = _ptr(d_o), d_o.stride(0)
+    a.lse, a.delta = _ptr(lse), _ptr(delta)
+    a.dq, a.dk, a.dv = _ptr(dq), _ptr(dk), _ptr(dv)
+    a.batch, a.heads, a.seq_q, a.seq_k = B, H, Lq, Lk
+    a.scale = float(scale if scale is not None else 128 ** -0.5)
+    check(lib().dpipe_attn_bwd(ctypes.byref(a), _stream()), 'dpipe_attn_bwd')
+    return dq, dk, dv

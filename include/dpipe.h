@@ -105,6 +105,26 @@ typedef struct dpipe_attn_args {
 
 int dpipe_attn_fwd(const dpipe_attn_args* args, void* stream);
 
+typedef struct dpipe_attn_bwd_args {
+  const void* q;   /* bf16 [batch, heads, seq_q, 128] (as given to the forward) */
+  const void* k;   /* bf16 [batch, heads, seq_k, 128] */
+  const void* v;   /* bf16 [batch, heads, seq_k, 128] */
+  const void* o;   /* bf16 token-major forward output [batch*seq_q, ldo] */
+  int64_t ldo;
+  const void* d_o; /* bf16 token-major gradient of o [batch*seq_q, lddo] */
+  int64_t lddo;
+  const float* lse; /* fp32 [batch, heads, seq_q] from dpipe_attn_fwd (log2 domain) */
+  float* delta;     /* fp32 [batch, heads, seq_q] scratch: rowsum(o * d_o), written by this call */
+  void* dq;        /* bf16 [batch, heads, seq_q, 128] */
+  void* dk;        /* bf16 [batch, heads, seq_k, 128] */
+  void* dv;        /* bf16 [batch, heads, seq_k, 128] */
+  int batch, heads, seq_q, seq_k;
+  float scale;
+} dpipe_attn_bwd_args;
+
+/* backward of dpipe_attn_fwd; replaces flash-attn / SDPA backward reached via autograd from models/flux.py:502,525 */
+int dpipe_attn_bwd(const dpipe_attn_bwd_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

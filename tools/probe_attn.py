@@ -43,6 +43,59 @@ def run_case(name):
         oref, lseref, _ = ref_attn(q, k, v, scale)
         res['lse'] = _err(lse * math.log(2.0), lseref)
         res.update(_err(o.view(B, Lq, H, 128).permute(0, 2, 1, 3).reshape(-1, 128), oref.reshape(-1, 128)))
+    elif kind in ('bwd', 'perfbwd'):
+        q = torch.randn(B, H, Lq, 128, device=dev).bfloat16()
+        k = torch.randn(B, H, Lk, 128, device=dev).bfloat16()
+        v = torch.randn(B, H, Lk, 128, device=dev).bfloat16()
+        ld = H * 128 + (64 if kind == 'bwd' else 0)      # exercise a padded leading dimension
+        o = torch.zeros(B * Lq, ld, device=dev, dtype=torch.bfloat16)
+        d_o = (torch.randn(B * Lq, ld, device=dev) * 0.5).bfloat16()
+        _, lse = ops.attn_fwd(q, k, v, out=o)
+        dq, dk, dv = ops.attn_bwd(q, k, v, o, d_o, lse)
+        torch.cuda.synchronize()
+        if kind == 'bwd':
+            qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+            oref, _, _ = ref_attn(qf, kf, vf, scale)
+            g = d_o[:, :H * 128].float().view(B, Lq, H, 128).permute(0, 2, 1, 3)
+            oref.backward(g)
+            res['dq'] = _err(dq.reshape(-1, 128), qf.grad.reshape(-1, 128))
+            res['dk'] = _err(dk.reshape(-1, 128), kf.grad.reshape(-1, 128))
+            res.update(_err(dv.reshape(-1, 128), vf.grad.reshape(-1, 128)))
+            res['ok_all'] = all(res[x]['rel'] < 2e-2 and res[x]['bad_frac'] == 0 for x in ('dq', 'dk'))
+        else:
+            flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+            delta = torch.empty(B, H, Lq, device=dev)
+
+            def ours():
+                ops.attn_bwd(q, k, v, o, d_o, lse, dq=dq, dk=dk, dv=dv, delta=delta)
+            ts = []
+            for it in range(8):
+                flush.zero_()
+                s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+                s.record(); ours(); e.record(); torch.cuda.synchronize()
+                if it >= 3:
+                    ts.append(s.elapsed_time(e))
+            ts.sort()
+            t = ts[len(ts) // 2]
+            fl = 2.5 * 4.0 * B * H * Lq * Lk * 128    # algorithmic backward = 2.5x forward (5 tile GEMMs)
+            res['ours_ms'] = t; res['ours_tflops_algorithmic'] = fl / t / 1e9
+            try:
+                from flash_attn import flash_attn_func
+                qf, kf, vf = (x.transpose(1, 2).contiguous().requires_grad_(True) for x in (q, k, v))
+                of = flash_attn_func(qf, kf, vf)
+                gof = torch.randn_like(of)
+                ts = []
+                for it in range(8):
+                    flush.zero_()
+                    s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+                    s.record(); of.backward(gof, retain_graph=True); e.record(); torch.cuda.synchronize()
+                    if it >= 3:
+                        ts.append(s.elapsed_time(e))
+                ts.sort()
+                res['fa2_bwd_ms'] = ts[len(ts) // 2]; res['fa2_bwd_tflops'] = fl / ts[len(ts) // 2] / 1e9
+            except Exception as ex:  # noqa
+                res['fa2_err'] = repr(ex)[:200]
+            res['rel'] = 0.0; res['bad_frac'] = 0.0
     elif kind == 'perf':
         q = torch.randn(B, H, Lq, 128, device=dev).bfloat16()
         k = torch.randn(B, H, Lk, 128, device=dev).bfloat16()
@@ -89,6 +142,7 @@ def run_case(name):
 
 
 CASES = ['fwd:1x2x256x256', 'fwd:2x3x512x384', 'fwd:1x2x300x200', 'fwd:1x2x1024x1024:peaky', 'fwd:1x1x128x640',
+         'bwd:1x2x256x256', 'bwd:2x3x512x384', 'bwd:1x2x300x200', 'bwd:1x1x128x640',
          'perf:1x24x4608x4608', 'perf:1x40x9216x9216']
 
 
