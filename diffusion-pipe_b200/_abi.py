@@ -1,5 +1,5 @@
-"""ctypes signatures for the C-ABI entry points beyond the GEMM (kept in one place so that the CPU-side
-test can check every symbol of include/dpipe.h is both exported and declared)."""
+"""ctypes structures and signatures for the C-ABI entry points beyond the GEMM (kept in one place so that the
+CPU-side test can check every symbol of include/dpipe.h is both exported and declared)."""
 import ctypes
 
 c_void_p = ctypes.c_void_p
@@ -29,9 +29,6 @@ class AttnArgs(ctypes.Structure):
     ]
 
 
-SIGNATURES['dpipe_attn_fwd'] = (c_int, [ctypes.POINTER(AttnArgs), c_void_p])
-
-
 class AttnBwdArgs(ctypes.Structure):
     _fields_ = [
         ('q', c_void_p), ('k', c_void_p), ('v', c_void_p),
@@ -44,4 +41,36 @@ class AttnBwdArgs(ctypes.Structure):
     ]
 
 
+class QkBwdArgs(ctypes.Structure):
+    _fields_ = [
+        ('dq', c_void_p), ('dk', c_void_p), ('dv', c_void_p),
+        ('qhat', c_void_p), ('khat', c_void_p),
+        ('q_rstd', c_void_p), ('k_rstd', c_void_p),
+        ('q_norm_w', c_void_p), ('k_norm_w', c_void_p),
+        ('rope_cos', c_void_p), ('rope_sin', c_void_p),
+        ('dqkv', c_void_p), ('ld', c_int64),
+        ('dbias', c_void_p), ('dw', c_void_p),
+        ('batch', c_int), ('heads', c_int), ('seq_total', c_int), ('seq_offset', c_int), ('rows_per_batch', c_int),
+    ]
+
+
+SIGNATURES['dpipe_attn_fwd'] = (c_int, [ctypes.POINTER(AttnArgs), c_void_p])
 SIGNATURES['dpipe_attn_bwd'] = (c_int, [ctypes.POINTER(AttnBwdArgs), c_void_p])
+SIGNATURES['dpipe_row_chunk'] = (c_int, [])
+SIGNATURES['dpipe_ln_modulate_fwd'] = (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                               c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p])
+SIGNATURES['dpipe_ln_modulate_bwd'] = (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                               c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int,
+                                               c_int, c_void_p])
+SIGNATURES['dpipe_gate_bwd'] = (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                                        c_void_p, c_int, c_int, c_int, c_void_p])
+SIGNATURES['dpipe_colreduce_finish'] = (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_void_p,
+                                                c_int64, c_void_p, c_void_p, c_void_p])
+SIGNATURES['dpipe_colsum_chunks'] = (c_int, [c_int])
+SIGNATURES['dpipe_colsum'] = (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p])
+SIGNATURES['dpipe_qknorm_rope_bwd'] = (c_int, [ctypes.POINTER(QkBwdArgs), c_void_p])
+SIGNATURES['dpipe_sched_num_pipe_buffers'] = (c_int, [c_int, c_int, c_int])
+SIGNATURES['dpipe_sched_train'] = (c_int, [c_int, c_int, c_int, c_void_p, c_int])
+SIGNATURES['dpipe_sched_infer'] = (c_int, [c_int, c_int, c_int, c_void_p, c_int])
+SIGNATURES['dpipe_partition_balanced'] = (c_int, [c_void_p, c_int, c_int, c_void_p])
+SIGNATURES['dpipe_mse_loss'] =(c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p])

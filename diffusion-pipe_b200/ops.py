@@ -1,11 +1,21 @@
-"""Tensor-level wrappers over the C ABI (include/dpipe.h).  torch is used only for device memory and
-streams; every compute call goes to libdpipe_b200.so."""
+"""Tensor-level wrappers over the C ABI (include/dpipe.h).  torch is used only for device memory and streams;
+every compute call goes to libdpipe_b200.so, and a missing library raises (no fallback)."""
 import ctypes
 
 import torch
 
 from . import _lib
+from ._abi import AttnArgs, AttnBwdArgs, QkBwdArgs
 from ._lib import GemmArgs, QkvEpilogue, check, lib
+
+EPI_STORE = _lib.EPI_STORE
+EPI_BIAS_GELU = _lib.EPI_BIAS_GELU
+EPI_GATE_RES = _lib.EPI_GATE_RES
+EPI_QKV_ROPE = _lib.EPI_QKV_ROPE
+EPI_MUL_GELU_GRAD = _lib.EPI_MUL_GELU_GRAD
+
+# kernel-launch counter (bench.py reports it as gpu_launches)
+LAUNCHES = 0
 
 
 def _stream():
@@ -23,13 +33,21 @@ def _req_bf16(t, name):
         raise ValueError(f'{name} must be contiguous in its last dimension')
 
 
-def gemm(a, b, *, a_mn=False, b_mn=False, out=None, epilogue=_lib.EPI_STORE, bias=None, out2=None,
-         aux=None, gate=None, rows_per_batch=None, accumulate=False, cta_group=2, qkv=None,
-         M=None, N=None, K=None):
+def _req_f32(t, name):
+    if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+        raise TypeError(f'{name} must be a contiguous CUDA fp32 tensor')
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GEMM
+# ---------------------------------------------------------------------------------------------------------------
+def gemm(a, b, *, a_mn=False, b_mn=False, out=None, epilogue=EPI_STORE, bias=None, out2=None, aux=None, gate=None,
+         rows_per_batch=None, accumulate=False, cta_group=2, qkv=None, M=None, N=None, K=None):
     """D[M,N] = Aop[M,K] @ Bop[N,K]^T with a fused epilogue (see include/dpipe.h).
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True); b: [N,K] (b_mn=False) or [K,N] (b_mn=True).
     """
+    global LAUNCHES
     _req_bf16(a, 'a')
     _req_bf16(b, 'b')
     assert a.dim() == 2 and b.dim() == 2
@@ -66,24 +84,24 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, epilogue=_lib.EPI_STORE, bia
     args.rows_per_batch = int(rows_per_batch) if rows_per_batch else M
     args.accumulate = int(bool(accumulate))
     args.cta_group = cta_group
-    keep = None
     if qkv is not None:
-        keep = qkv
         args.qkv = ctypes.pointer(qkv)
     check(lib().dpipe_gemm_bf16(ctypes.byref(args), _stream()), 'dpipe_gemm_bf16')
-    del keep
+    LAUNCHES += 1
     return out
 
 
-def make_qkv_epilogue(q, k, v, q_norm_w, k_norm_w, rope_cos, rope_sin, heads, seq_total, seq_offset,
-                      qhat=None, khat=None, q_rstd=None, k_rstd=None, eps=1e-6):
+def make_qkv_epilogue(q, k, v, q_norm_w, k_norm_w, rope_cos, rope_sin, heads, seq_total, seq_offset, qhat=None,
+                      khat=None, q_rstd=None, k_rstd=None, eps=1e-6):
     e = QkvEpilogue()
     e.q, e.k, e.v = _ptr(q), _ptr(k), _ptr(v)
     e.qhat, e.khat = _ptr(qhat), _ptr(khat)
     e.q_rstd, e.k_rstd = _ptr(q_rstd), _ptr(k_rstd)
+    _req_bf16(q_norm_w, 'q_norm_w')
+    _req_bf16(k_norm_w, 'k_norm_w')
     e.q_norm_w, e.k_norm_w = _ptr(q_norm_w), _ptr(k_norm_w)
-    assert rope_cos.dtype == torch.float32 and rope_sin.dtype == torch.float32
-    assert rope_cos.is_contiguous() and rope_sin.is_contiguous()
+    _req_f32(rope_cos, 'rope_cos')
+    _req_f32(rope_sin, 'rope_sin')
     e.rope_cos, e.rope_sin = _ptr(rope_cos), _ptr(rope_sin)
     e.heads, e.seq_total, e.seq_offset = heads, seq_total, seq_offset
     e.n_qkv = 3 * heads * 128
@@ -91,10 +109,13 @@ def make_qkv_epilogue(q, k, v, q_norm_w, k_norm_w, rope_cos, rope_sin, heads, se
     return e
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# attention
+# ---------------------------------------------------------------------------------------------------------------
 def attn_fwd(q, k, v, out=None, lse=None, scale=None):
     """softmax(q k^T * scale) v.  q: [B,H,Lq,128], k/v: [B,H,Lk,128] (bf16, contiguous).
     Returns (o [B*Lq, >=H*128] token-major, lse [B,H,Lq] fp32 in the log2 domain)."""
-    from ._abi import AttnArgs
+    global LAUNCHES
     for t, n in ((q, 'q'), (k, 'k'), (v, 'v')):
         _req_bf16(t, n)
         if not t.is_contiguous() or t.shape[-1] != 128:
@@ -112,12 +133,13 @@ def attn_fwd(q, k, v, out=None, lse=None, scale=None):
     a.batch, a.heads, a.seq_q, a.seq_k = B, H, Lq, Lk
     a.scale = float(scale if scale is not None else 128 ** -0.5)
     check(lib().dpipe_attn_fwd(ctypes.byref(a), _stream()), 'dpipe_attn_fwd')
+    LAUNCHES += 1
     return out, lse
 
 
 def attn_bwd(q, k, v, o, d_o, lse, scale=None, dq=None, dk=None, dv=None, delta=None):
     """Backward of attn_fwd.  o / d_o are token-major [B*Lq, >=H*128]; returns head-major (dq, dk, dv)."""
-    from ._abi import AttnBwdArgs
+    global LAUNCHES
     B, H, Lq, _ = q.shape
     Lk = k.shape[2]
     for t, n in ((q, 'q'), (k, 'k'), (v, 'v')):
@@ -139,4 +161,148 @@ def attn_bwd(q, k, v, o, d_o, lse, scale=None, dq=None, dk=None, dv=None, delta=
     a.batch, a.heads, a.seq_q, a.seq_k = B, H, Lq, Lk
     a.scale = float(scale if scale is not None else 128 ** -0.5)
     check(lib().dpipe_attn_bwd(ctypes.byref(a), _stream()), 'dpipe_attn_bwd')
+    LAUNCHES += 3
     return dq, dk, dv
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# LayerNorm + modulation, gated residual, reductions
+# ---------------------------------------------------------------------------------------------------------------
+_ROW_CHUNK = None
+
+
+def row_chunk():
+    global _ROW_CHUNK
+    if _ROW_CHUNK is None:
+        _ROW_CHUNK = lib().dpipe_row_chunk()
+    return _ROW_CHUNK
+
+
+def nchunks(rows_per_batch):
+    rc = row_chunk()
+    return (rows_per_batch + rc - 1) // rc
+
+
+def ln_modulate_fwd(x, scale, shift, batch, rows_per_batch, eps=1e-6, out=None, save_stats=True):
+    """out = LN(x) * bf16(1+scale[b]) + shift[b].  x: [batch*rows, D]; scale/shift: [batch, D] views (bf16)."""
+    global LAUNCHES
+    _req_bf16(x, 'x')
+    _req_bf16(scale, 'scale')
+    _req_bf16(shift, 'shift')
+    D = x.shape[1]
+    assert scale.stride(0) == shift.stride(0)
+    if out is None:
+        out = torch.empty((x.shape[0], D), dtype=torch.bfloat16, device=x.device)
+    mean = rstd = None
+    if save_stats:
+        mean = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        rstd = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    check(lib().dpipe_ln_modulate_fwd(_ptr(x), x.stride(0), _ptr(scale), _ptr(shift), scale.stride(0), _ptr(out),
+                                      out.stride(0), _ptr(mean), _ptr(rstd), batch, rows_per_batch, D, eps, _stream()),
+          'dpipe_ln_modulate_fwd')
+    LAUNCHES += 1
+    return out, mean, rstd
+
+
+def ln_modulate_bwd(dxn, x, scale, mean, rstd, batch, rows_per_batch, dres=None, dx=None, partials=None):
+    """Returns (dx, partials) with partials[batch][nchunk][2][D]: slot 0 = d scale, slot 1 = d shift."""
+    global LAUNCHES
+    _req_bf16(dxn, 'dxn')
+    _req_bf16(x, 'x')
+    _req_bf16(scale, 'scale')
+    D = x.shape[1]
+    nc = nchunks(rows_per_batch)
+    if dx is None:
+        dx = torch.empty((x.shape[0], D), dtype=torch.bfloat16, device=x.device)
+    if partials is None:
+        partials = torch.empty((batch, nc, 2, D), dtype=torch.float32, device=x.device)
+    if dres is not None:
+        _req_bf16(dres, 'dres')
+    check(lib().dpipe_ln_modulate_bwd(_ptr(dxn), dxn.stride(0), _ptr(x), x.stride(0), _ptr(scale), scale.stride(0),
+                                      _ptr(mean), _ptr(rstd), _ptr(dres), dres.stride(0) if dres is not None else 0,
+                                      _ptr(dx), dx.stride(0), _ptr(partials), batch, rows_per_batch, D, _stream()),
+          'dpipe_ln_modulate_bwd')
+    LAUNCHES += 1
+    return dx, partials
+
+
+def gate_bwd(dx, y, gate, batch, rows_per_batch, dy=None, partials=None):
+    """dy = bf16(gate*dx); partial slot 0 = sum dx*y (d gate per sample), slot 1 = sum dy (d bias)."""
+    global LAUNCHES
+    _req_bf16(dx, 'dx')
+    _req_bf16(y, 'y')
+    _req_bf16(gate, 'gate')
+    D = y.shape[1]
+    nc = nchunks(rows_per_batch)
+    if dy is None:
+        dy = torch.empty((y.shape[0], D), dtype=torch.bfloat16, device=y.device)
+    if partials is None:
+        partials = torch.empty((batch, nc, 2, D), dtype=torch.float32, device=y.device)
+    check(lib().dpipe_gate_bwd(_ptr(dx), dx.stride(0), _ptr(y), y.stride(0), _ptr(gate), gate.stride(0), _ptr(dy),
+                               dy.stride(0), _ptr(partials), batch, rows_per_batch, D, _stream()), 'dpipe_gate_bwd')
+    LAUNCHES += 1
+    return dy, partials
+
+
+def colreduce_finish(partials, per_sample0=None, per_sample1=None, summed0=None, summed1=None):
+    """partials [batch, nchunk, nslot, D] fp32.  per_sample*: fp32 [batch, D] views (row stride = stride(0));
+    summed*: fp32 [D]."""
+    global LAUNCHES
+    batch, nc, nslot, D = partials.shape
+    ld0 = per_sample0.stride(0) if per_sample0 is not None else 0
+    ld1 = per_sample1.stride(0) if per_sample1 is not None else 0
+    check(lib().dpipe_colreduce_finish(_ptr(partials), batch, nc, nslot, D, _ptr(per_sample0), ld0, _ptr(per_sample1),
+                                       ld1, _ptr(summed0), _ptr(summed1), _stream()), 'dpipe_colreduce_finish')
+    LAUNCHES += 1
+
+
+def colsum(x, out=None):
+    """fp32 column sums of a bf16 [rows, N] matrix."""
+    global LAUNCHES
+    _req_bf16(x, 'x')
+    rows, N = x.shape
+    nc = lib().dpipe_colsum_chunks(rows)
+    partials = torch.empty((nc, N), dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=x.device)
+    check(lib().dpipe_colsum(_ptr(x), x.stride(0), rows, N, _ptr(partials), _ptr(out), _stream()), 'dpipe_colsum')
+    LAUNCHES += 2
+    return out
+
+
+def qknorm_rope_bwd(dq, dk, dv, qhat, khat, q_rstd, k_rstd, q_norm_w, k_norm_w, rope_cos, rope_sin, dqkv, dbias, dw,
+                    batch, heads, seq_total, seq_offset, rows_per_batch):
+    """Backward of the QKV_ROPE epilogue for one stream: writes token-major dqkv [batch*rows, 3*H*128] and
+    accumulates dbias (fp32 [3*H*128]) and dw (fp32 [2,128]) — both must be zero-initialised by the caller."""
+    global LAUNCHES
+    a = QkBwdArgs()
+    a.dq, a.dk, a.dv = _ptr(dq), _ptr(dk), _ptr(dv)
+    a.qhat, a.khat = _ptr(qhat), _ptr(khat)
+    a.q_rstd, a.k_rstd = _ptr(q_rstd), _ptr(k_rstd)
+    a.q_norm_w, a.k_norm_w = _ptr(q_norm_w), _ptr(k_norm_w)
+    a.rope_cos, a.rope_sin = _ptr(rope_cos), _ptr(rope_sin)
+    _req_bf16(dqkv, 'dqkv')
+    a.dqkv, a.ld = _ptr(dqkv), dqkv.stride(0)
+    _req_f32(dbias, 'dbias')
+    _req_f32(dw, 'dw')
+    a.dbias, a.dw = _ptr(dbias), _ptr(dw)
+    a.batch, a.heads, a.seq_total, a.seq_offset, a.rows_per_batch = batch, heads, seq_total, seq_offset, rows_per_batch
+    check(lib().dpipe_qknorm_rope_bwd(ctypes.byref(a), _stream()), 'dpipe_qknorm_rope_bwd')
+    LAUNCHES += 1
+
+
+def mse_loss(out, target, mask=None, want_grad=True):
+    """(loss fp32 scalar tensor, dout bf16 or None) for loss = mean((out-target)^2 * mask)."""
+    global LAUNCHES
+    _req_bf16(out, 'out')
+    assert out.is_contiguous()
+    target = target.to(torch.float32).contiguous()
+    if mask is not None:
+        mask = mask.to(torch.float32).expand_as(target).contiguous()
+    ws = torch.empty(1024, dtype=torch.float32, device=out.device)
+    loss = torch.empty((), dtype=torch.float32, device=out.device)
+    dout = torch.empty_like(out) if want_grad else None
+    check(lib().dpipe_mse_loss(_ptr(out), _ptr(target), _ptr(mask), out.numel(), _ptr(ws), _ptr(loss), _ptr(dout),
+                               _stream()), 'dpipe_mse_loss')
+    LAUNCHES += 2
+    return loss, dout

@@ -1,0 +1,491 @@
+"""PipelineEngine: executes the 1F1B instruction stream over the local stage.
+
+Replaces `deepspeed.initialize(...)` -> PipelineEngine as used by the reference (train.py:623-631, 817-823, 915-918,
+181-183; utils/dataset.py:1387-1405; utils/saver.py:59-128).  Semantics restated from deepspeed==0.18.4
+runtime/pipe/engine.py as recorded in SURVEY.md section 8a rows E3-E11:
+
+  LoadMicroBatch   first stage: inputs = clone().detach().to(device), requires_grad = is_floating_point;
+                   last stage: labels -> device                                                     (E3)
+  ForwardPass      local layers in order; last stage loss = loss_fn(outputs, labels)                (E4)
+  BackwardPass     last stage (loss / GAS).backward(); else autograd.backward(float outputs, received grads)  (E5)
+  Send/Recv*       every tensor of the boundary tuple; grads for every floating-point tensor        (E6)
+  ReduceGrads      data-parallel mean of all trainable grads in `communication_data_type`           (E7)
+  OptimizerStep    global-norm clip (utils/patches.py:175-246) -> optimizer.step -> zero_grad -> lr_scheduler.step (E8, E9)
+  train_batch      returns mean micro-batch loss, averaged over DP and broadcast to every stage      (E10)
+
+Stage links: `DistLink` moves boundary tensors with torch.distributed p2p (gloo on CPU, NCCL on GPUs);
+`IpcLink` (pipe/ipc_link.py) is the B200 path — peer copies into pre-registered slots over NVLink with device-side
+flags, no NCCL on the boundary.  Selected by `config['stage_link']` ('auto' picks IpcLink on CUDA).
+"""
+import os
+import time
+
+import torch
+
+from . import dist
+from .module import PipelineModule
+from .schedule import (BackwardPass, ForwardPass, InferenceSchedule, LoadMicroBatch, OptimizerStep, RecvActivation, RecvGrad,
+                       ReduceGrads, ReduceTiedGrads, SendActivation, SendGrad, TrainSchedule)
+
+_DTYPES = [torch.float32, torch.float16, torch.bfloat16, torch.int64, torch.int32, torch.int16, torch.int8, torch.uint8,
+           torch.bool, torch.float64, torch.complex64]
+_DTYPE_ID = {d: i for i, d in enumerate(_DTYPES)}
+
+
+class DistLink:
+    """Boundary transport over torch.distributed point-to-point (same scheme as DeepSpeed: a metadata message when
+    shapes are unknown, then one message per tensor)."""
+
+    def __init__(self, engine):
+        self.engine = engine
+        self.device = engine.device
+        self.reset()
+
+    def reset(self):
+        self._send_meta_done = {}
+        self._recv_meta = {}
+
+    def _meta_device(self):
+        return self.device if self.device.type == 'cuda' else torch.device('cpu')
+
+    def send_tuple(self, tensors, dst, key):
+        if key not in self._send_meta_done:
+            meta = [len(tensors)]
+            for t in tensors:
+                meta += [_DTYPE_ID[t.dtype], t.dim()] + list(t.shape)
+            m = torch.tensor([len(meta)] + meta, dtype=torch.int64, device=self._meta_device())
+            dist.send(m[:1].clone(), dst)
+            dist.send(m[1:].contiguous(), dst)
+            self._send_meta_done[key] = True
+        for t in tensors:
+            dist.send(t.contiguous(), dst)
+
+    def recv_tuple(self, src, key):
+        if key not in self._recv_meta:
+            n = torch.zeros(1, dtype=torch.int64, device=self._meta_device())
+            dist.recv(n, src)
+            m = torch.zeros(int(n.item()), dtype=torch.int64, device=self._meta_device())
+            dist.recv(m, src)
+            m = m.tolist()
+            specs, pos = [], 1
+            for _ in range(m[0]):
+                dt, nd = _DTYPES[m[pos]], m[pos + 1]
+                specs.append((dt, tuple(m[pos + 2:pos + 2 + nd])))
+                pos += 2 + nd
+            self._recv_meta[key] = specs
+        out = []
+        for dt, shape in self._recv_meta[key]:
+            t = torch.empty(shape, dtype=dt, device=self.device)
+            dist.recv(t, src)
+            out.append(t)
+        return tuple(out)
+
+
+class PipelineEngine:
+    def __init__(self, model, config, args=None):
+        assert isinstance(model, PipelineModule), 'model must be a PipelineModule'
+        self.module = model
+        self.config = dict(config or {})
+        self.grid = model._grid
+        self.num_stages = self.grid.pipe_parallel_size
+        self.stage_id = self.grid.get_stage_id()
+        self.prev_stage = self.stage_id - 1
+        self.next_stage = self.stage_id + 1
+        self.global_rank = self.grid.global_rank
+        self.is_pipe_parallel = self.num_stages > 1
+        self.is_data_parallel = self.grid.data_parallel_size > 1
+        self.device = next((p.device for p in model.parameters()), None)
+        if self.device is None:
+            self.device = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu')
+        self._micro_batch_size = int(self.config.get('train_micro_batch_size_per_gpu', 1))
+        self.micro_batches = int(self.config.get('gradient_accumulation_steps', 1))
+        self._gradient_clipping = float(self.config.get('gradient_clipping', 0.0))
+        self.steps_per_print = int(self.config.get('steps_per_print', 10))
+        self.optimizer = None
+        self.lr_scheduler = None
+        self.communication_data_type = None
+        self.first_last_stage_group = None
+        self._support_torch_style_backward = True
+        self.global_steps = 0
+        self.global_samples = 0
+        self._grad_norm = None
+        self.loss_fn = model.loss_fn
+        self.pipe_buffers = {'inputs': [], 'labels': [], 'outputs': [], 'grads': []}
+        self.link = self._make_link()
+        self.total_loss = None
+        self.fwd_losses = []
+        self._data_iter = None
+        self._busy_ms = 0.0
+
+    # ------------------------------------------------------------------ DeepSpeed-compatible accessors
+    def is_first_stage(self):
+        return self.stage_id == 0
+
+    def is_last_stage(self):
+        return self.stage_id == self.num_stages - 1
+
+    def train_micro_batch_size_per_gpu(self):
+        return self._micro_batch_size
+
+    def gradient_accumulation_steps(self):
+        return self.micro_batches
+
+    def gradient_clipping(self):
+        return self._gradient_clipping
+
+    def train_batch_size(self):
+        return self._micro_batch_size * self.micro_batches * self.grid.data_parallel_size
+
+    def reset_activation_shape(self):
+        """train.py:916 — boundary shapes may change between steps (resolution buckets)."""
+        self.link.reset()
+
+    def _configure_optimizer(self, client_optimizer, model_parameters):
+        """train.py:817 — `client_optimizer` is a factory taking the trainable parameter list."""
+        self.optimizer = client_optimizer(model_parameters) if callable(client_optimizer) else client_optimizer
+        return self.optimizer
+
+    def _make_link(self):
+        kind = self.config.get('stage_link', 'auto')
+        if kind == 'auto':
+            kind = 'ipc' if (self.device.type == 'cuda' and self.is_pipe_parallel
+                             and os.environ.get('DPIPE_STAGE_LINK', 'ipc') == 'ipc') else 'dist'
+        if kind == 'ipc' and self.is_pipe_parallel:
+            from .ipc_link import IpcLink
+            return IpcLink(self)
+        return DistLink(self)
+
+    # ------------------------------------------------------------------ public API
+    def train_batch(self, data_iter=None):
+        self.module.train()
+        self.total_loss = None
+        self.fwd_losses = []
+        self._data_iter = data_iter
+        sched = TrainSchedule(self.micro_batches, self.num_stages, self.stage_id)
+        self._reserve_buffers(sched.num_pipe_buffers())
+        self._exec_schedule(sched, train=True)
+        self.global_steps += 1
+        self.global_samples += self.train_batch_size()
+        loss = self._aggregate_total_loss(self.micro_batches)
+        if self.steps_per_print and self.global_steps % self.steps_per_print == 0 and self.global_rank == 0:
+            lr = self.optimizer.param_groups[0]['lr'] if self.optimizer and self.optimizer.param_groups else float('nan')
+            print(f'steps: {self.global_steps} loss: {float(loss):.4f} lr: {lr:.3e}', flush=True)
+        return loss
+
+    def eval_batch(self, data_iter, num_micro_batches=None, return_logits=False, compute_loss=True, reduce_output='avg'):
+        self.module.eval()
+        n = num_micro_batches or self.micro_batches
+        self.total_loss = None
+        self.fwd_losses = []
+        self._data_iter = data_iter
+        sched = InferenceSchedule(n, self.num_stages, self.stage_id)
+        self._reserve_buffers(sched.num_pipe_buffers())
+        with torch.no_grad():
+            self._exec_schedule(sched, train=False)
+        return self._aggregate_total_loss(n)
+
+    # ------------------------------------------------------------------ schedule execution
+    def _reserve_buffers(self, n):
+        for k in self.pipe_buffers:
+            if len(self.pipe_buffers[k]) < n:
+                self.pipe_buffers[k].extend([None] * (n - len(self.pipe_buffers[k])))
+
+    def _exec_schedule(self, sched, train):
+        handlers = self._INSTRUCTION_MAP
+        for tick in sched.steps():
+            for cmd in tick:
+                handlers[type(cmd)](self, cmd, train)
+        self.link.flush() if hasattr(self.link, 'flush') else None
+
+    def _exec_load_micro_batch(self, cmd, train):
+        b = cmd.buffer_id
+        batch = next(self._data_iter)
+        if self.is_first_stage():
+            feats = batch[0]
+            if torch.is_tensor(feats):
+                feats = (feats,)
+            loaded = []
+            for x in feats:
+                assert torch.is_tensor(x)
+                y = x.clone().detach().to(self.device, non_blocking=True)
+                y.requires_grad = y.is_floating_point() and train
+                loaded.append(y)
+            self.pipe_buffers['inputs'][b] = tuple(loaded)
+        if self.is_last_stage():
+            labels = batch[1]
+            if torch.is_tensor(labels):
+                labels = labels.to(self.device, non_blocking=True)
+            else:
+                labels = tuple(x.to(self.device, non_blocking=True) for x in labels)
+            self.pipe_buffers['labels'][b] = labels
+
+    def _exec_forward_pass(self, cmd, train):
+        b = cmd.buffer_id
+        inputs = self.pipe_buffers['inputs'][b]
+        outputs = self.module(inputs if len(inputs) > 1 else inputs[0])
+        if self.is_last_stage():
+            if self.loss_fn is not None:
+                loss = self.loss_fn(outputs, self.pipe_buffers['labels'][b])
+            else:
+                loss = outputs
+            self.pipe_buffers['outputs'][b] = loss
+            self.fwd_losses.append(loss.detach())
+            self.total_loss = loss.detach().clone() if self.total_loss is None else self.total_loss + loss.detach()
+        else:
+            if torch.is_tensor(outputs):
+                outputs = (outputs,)
+            self.pipe_buffers['outputs'][b] = tuple(outputs)
+        if not train:
+            self.pipe_buffers['inputs'][b] = None
+
+    def _exec_backward_pass(self, cmd, train):
+        b = cmd.buffer_id
+        outputs = self.pipe_buffers['outputs'][b]
+        if self.is_last_stage():
+            (outputs / self.micro_batches).backward()
+        else:
+            grads = self.pipe_buffers['grads'][b]
+            outs = [t for t in outputs if t.is_floating_point()]
+            assert len(outs) == len(grads)
+            pairs = [(t, g) for t, g in zip(outs, grads) if t.requires_grad]
+            torch.autograd.backward(tensors=[p[0] for p in pairs], grad_tensors=[p[1] for p in pairs])
+        self.pipe_buffers['outputs'][b] = None
+        self.pipe_buffers['grads'][b] = None
+        self.pipe_buffers['labels'][b] = None
+
+    def _exec_send_activations(self, cmd, train):
+        b = cmd.buffer_id
+        self.link.send_activations(self.pipe_buffers['outputs'][b], b, cmd.micro_batch_id, keep=train)
+        if not train:
+            self.pipe_buffers['outputs'][b] = None
+
+    def _exec_recv_activations(self, cmd, train):
+        b = cmd.buffer_id
+        tensors = self.link.recv_activations(b, cmd.micro_batch_id)
+        out = []
+        for t in tensors:
+            t = t.detach()
+            t.requires_grad = t.is_floating_point() and train
+            out.append(t)
+        self.pipe_buffers['inputs'][b] = tuple(out)
+
+    def _exec_send_grads(self, cmd, train):
+        b = cmd.buffer_id
+        inputs = self.pipe_buffers['inputs'][b]
+        grads = []
+        for t in inputs:
+            if t.is_floating_point():
+                grads.append(t.grad if t.grad is not None else torch.zeros_like(t))
+        self.link.send_grads(tuple(grads), b, cmd.micro_batch_id)
+        self.pipe_buffers['inputs'][b] = None
+
+    def _exec_recv_grads(self, cmd, train):
+        b = cmd.buffer_id
+        outputs = self.pipe_buffers['outputs'][b]
+        like = [t for t in outputs if t.is_floating_point()]
+        self.pipe_buffers['grads'][b] = self.link.recv_grads(like, b, cmd.micro_batch_id)
+
+    def _exec_reduce_tied_grads(self, cmd, train):
+        pass   # no tied layers in any reference model definition
+
+    def _exec_reduce_grads(self, cmd, train):
+        if not self.is_data_parallel:
+            return
+        group = self.grid.get_data_parallel_group()
+        world = self.grid.data_parallel_size
+        params = [p for p in self.module.parameters() if p.requires_grad and p.grad is not None]
+        comm_dtype = self.communication_data_type
+        # large gradients go in place; small ones are coalesced
+        small, small_elems = [], 0
+        seen = set()
+
+        def flush_small():
+            nonlocal small, small_elems
+            if not small:
+                return
+            flat = torch.cat([g.reshape(-1).to(comm_dtype or g.dtype) for g in small])
+            dist.all_reduce(flat, group=group)
+            flat.div_(world)
+            off = 0
+            for g in small:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+            small, small_elems = [], 0
+
+        for p in params:
+            g = p.grad
+            base = g._base if g._base is not None else g
+            if base.data_ptr() in seen:
+                continue
+            if base is not g and base.is_contiguous():
+                g = base     # fused gradient buffer: reduce it once as a whole
+            seen.add(base.data_ptr())
+            if g.numel() >= (1 << 20) and g.is_contiguous() and (comm_dtype is None or comm_dtype == g.dtype):
+                dist.all_reduce(g, group=group)
+                g.div_(world)
+            else:
+                small.append(g)
+                small_elems += g.numel()
+                if small_elems >= (1 << 24):
+                    flush_small()
+        flush_small()
+
+    def _clip_grad_norm(self, params, max_norm):
+        """utils/patches.py:175-246: sqrt(sum of squared per-parameter fp32 norms) over the whole pipeline."""
+        grads = [p.grad for p in params if p.grad is not None]
+        if grads:
+            norms = torch._foreach_norm([g.detach().float() if g.dtype != torch.float32 else g.detach() for g in grads])
+            total = torch.stack(norms).square().sum().float()
+        else:
+            total = torch.zeros((), dtype=torch.float32, device=self.device)
+        total = total.to(self.device)
+        if self.is_pipe_parallel:
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.grid.get_pipe_parallel_group())
+        total_norm = total.sqrt()
+        if self.is_data_parallel:
+            # the reference averages the (identical) norm over the data-parallel group
+            scaled = total_norm / float(self.grid.data_parallel_size)
+            dist.all_reduce(scaled, group=self.grid.get_data_parallel_group())
+            total_norm = scaled
+        clip_coef = torch.clamp(max_norm / (total_norm + 1e-6), max=1.0)
+        if grads:
+            torch._foreach_mul_(grads, clip_coef.to(grads[0].device))
+        return total_norm
+
+    def _exec_optimizer_step(self, cmd, train):
+        params = [p for p in self.module.parameters() if p.requires_grad]
+        if self._gradient_clipping > 0.0:
+            self._grad_norm = self._clip_grad_norm(params, self._gradient_clipping)
+            if self.optimizer is not None:
+                self.optimizer._grad_norm = self._grad_norm
+        if self.optimizer is not None:
+            self.optimizer.step()
+            self.optimizer.zero_grad(set_to_none=True)
+        else:
+            for p in params:
+                p.grad = None
+        if self.lr_scheduler is not None:
+            self.lr_scheduler.step()
+
+    _INSTRUCTION_MAP = {
+        OptimizerStep: _exec_optimizer_step,
+        ReduceGrads: _exec_reduce_grads,
+        ReduceTiedGrads: _exec_reduce_tied_grads,
+        LoadMicroBatch: _exec_load_micro_batch,
+        ForwardPass: _exec_forward_pass,
+        BackwardPass: _exec_backward_pass,
+        SendActivation: _exec_send_activations,
+        RecvActivation: _exec_recv_activations,
+        SendGrad: _exec_send_grads,
+        RecvGrad: _exec_recv_grads,
+    }
+
+    # ------------------------------------------------------------------ loss aggregation (E10)
+    def _aggregate_total_loss(self, num_micro_batches):
+        if self.is_last_stage():
+            loss = (self.total_loss / num_micro_batches).float().reshape(1).to(self.device)
+            if self.is_data_parallel:
+                dist.all_reduce(loss, group=self.grid.get_data_parallel_group())
+                loss /= self.grid.data_parallel_size
+        else:
+            loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        if self.is_pipe_parallel:
+            src = self.grid.stage_to_global(self.num_stages - 1)
+            dist.broadcast(loss, src, group=self.grid.get_pipe_parallel_group())
+        return loss.reshape(())
+
+    # ------------------------------------------------------------------ checkpoint
+    def save_checkpoint(self, save_dir, tag=None, client_state=None, save_latest=True, exclude_frozen_parameters=False):
+        tag = tag or f'global_step{self.global_steps}'
+        path = os.path.join(save_dir, tag)
+        os.makedirs(path, exist_ok=True)
+        sd = {}
+        for name, p in self.module.named_parameters():
+            if exclude_frozen_parameters and not p.requires_grad:
+                continue
+            sd[getattr(p, 'original_name', name)] = p.detach().cpu()
+        state = {
+            'module': sd,
+            'optimizer': self.optimizer.state_dict() if self.optimizer is not None else None,
+            'lr_scheduler': self.lr_scheduler.state_dict() if self.lr_scheduler is not None else None,
+            'global_steps': self.global_steps,
+            'global_samples': self.global_samples,
+            'client_state': client_state or {},
+        }
+        fn = os.path.join(path, f'stage_{self.stage_id:02d}-dp_{self.grid.data_parallel_id:02d}_states.pt')
+        if self.grid.data_parallel_id == 0 or self.optimizer is not None:
+            torch.save(state, fn)
+        dist.barrier()
+        if save_latest and self.global_rank == 0:
+            with open(os.path.join(save_dir, 'latest'), 'w') as f:
+                f.write(tag)
+        return True
+
+    def load_checkpoint(self, load_dir, tag=None, load_module_strict=True, load_optimizer_states=True,
+                        load_lr_scheduler_states=True):
+        if tag is None:
+            latest = os.path.join(load_dir, 'latest')
+            if not os.path.isfile(latest):
+                return None, None
+            with open(latest) as f:
+                tag = f.read().strip()
+        fn = os.path.join(load_dir, tag, f'stage_{self.stage_id:02d}-dp_{self.grid.data_parallel_id:02d}_states.pt')
+        if not os.path.isfile(fn):
+            fn = os.path.join(load_dir, tag, f'stage_{self.stage_id:02d}-dp_00_states.pt')
+        state = torch.load(fn, map_location='cpu', weights_only=False)
+        by_name = {getattr(p, 'original_name', n): p for n, p in self.module.named_parameters()}
+        missing = []
+        for k, p in by_name.items():
+            if k in state['module']:
+                p.data.copy_(state['module'][k])
+            elif p.requires_grad:
+                missing.append(k)
+        if load_module_strict and missing:
+            raise RuntimeError(f'checkpoint is missing parameters: {missing[:5]}')
+        if load_optimizer_states and self.optimizer is not None and state.get('optimizer') is not None:
+            self.optimizer.load_state_dict(state['optimizer'])
+        if load_lr_scheduler_states and self.lr_scheduler is not None and state.get('lr_scheduler') is not None:
+            self.lr_scheduler.load_state_dict(state['lr_scheduler'])
+        self.global_steps = state.get('global_steps', 0)
+        self.global_samples = state.get('global_samples', 0)
+        return os.path.join(load_dir, tag), state.get('client_state', {})
+
+
+class _LinkShim:
+    """Adapts the tuple transport (DistLink) to the engine's four boundary operations."""
+
+
+def _dist_send_activations(self, outputs, buf, mb, keep=True):
+    self.send_tuple(tuple(outputs), self.engine.grid.stage_to_global(self.engine.next_stage), ('act', len(outputs)))
+
+
+def _dist_recv_activations(self, buf, mb):
+    return self.recv_tuple(self.engine.grid.stage_to_global(self.engine.prev_stage), 'act')
+
+
+def _dist_send_grads(self, grads, buf, mb):
+    dst = self.engine.grid.stage_to_global(self.engine.prev_stage)
+    for g in grads:
+        dist.send(g.contiguous(), dst)
+
+
+def _dist_recv_grads(self, like, buf, mb):
+    src = self.engine.grid.stage_to_global(self.engine.next_stage)
+    out = []
+    for t in like:
+        g = torch.empty_like(t, memory_format=torch.contiguous_format)
+        dist.recv(g, src)
+        out.append(g)
+    return out
+
+
+DistLink.send_activations = _dist_send_activations
+DistLink.recv_activations = _dist_recv_activations
+DistLink.send_grads = _dist_send_grads
+DistLink.recv_grads = _dist_recv_grads
+
+
+def initialize(args=None, model=None, config=None, **kwargs):
+    """deepspeed.initialize(args=, model=, config=) -> (engine, optimizer, None, None)   (train.py:623-627)."""
+    engine = PipelineEngine(model, config, args=args)
+    return engine, engine.optimizer, None, None

@@ -125,6 +125,88 @@ typedef struct dpipe_attn_bwd_args {
 /* backward of dpipe_attn_fwd; replaces flash-attn / SDPA backward reached via autograd from models/flux.py:502,525 */
 int dpipe_attn_bwd(const dpipe_attn_bwd_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* HBM-bound kernels around the GEMMs (LayerNorm+modulation, gated residual, q/k norm + RoPE     */
+/* backward, bias-gradient column sums, masked MSE loss).                                        */
+/* replaces: the unfused ATen kernels behind diffusers AdaLayerNormZero{,Single}/Continuous,     */
+/*           gate*out + residual, RMSNorm(q,k), apply_rotary_emb (call sites models/flux.py:     */
+/*           502,525,546-548) and F.mse_loss in models/base.py:418-436.                          */
+/* Row reductions are two-stage and atomics-free: kernels taking `partials` write                */
+/* partials[batch][nchunk][2][D] fp32 with nchunk = ceil(rows_per_batch / dpipe_row_chunk());    */
+/* dpipe_colreduce_finish folds them.  D must be a multiple of 256.                              */
+/* ------------------------------------------------------------------------------------------ */
+int dpipe_row_chunk(void);
+
+/* out = LayerNorm(x, eps, no affine) * bf16(1 + scale[b]) + shift[b]; saves mean/rstd (fp32 [batch*rows]) */
+int dpipe_ln_modulate_fwd(const void* x, int64_t ldx, const void* scale, const void* shift, int64_t mod_stride,
+                          void* out, int64_t ldo, float* mean, float* rstd, int batch, int rows_per_batch, int D,
+                          float eps, void* stream);
+/* dx = LN'(dxn * bf16(1+scale)) (+ dres);  partial slot 0 = d scale, slot 1 = d shift (per sample) */
+int dpipe_ln_modulate_bwd(const void* dxn, int64_t lddxn, const void* x, int64_t ldx, const void* scale,
+                          int64_t mod_stride, const float* mean, const float* rstd, const void* dres, int64_t lddres,
+                          void* dx, int64_t lddx, float* partials, int batch, int rows_per_batch, int D, void* stream);
+/* x_new = res + gate[b]*y:  dy = bf16(gate*dx);  partial slot 0 = sum dx*y (d gate, per sample), slot 1 = sum dy (d bias) */
+int dpipe_gate_bwd(const void* dx, int64_t lddx, const void* y, int64_t ldy, const void* gate, int64_t gate_stride,
+                   void* dy, int64_t lddy, float* partials, int batch, int rows_per_batch, int D, void* stream);
+/* slot s of partials -> per_sample{s}[b*ld{s} + d] and/or summed{s}[d] (sum over samples); NULL outputs are skipped */
+int dpipe_colreduce_finish(const float* partials, int batch, int nchunk, int nslot, int D, float* per_sample0,
+                           int64_t ld0, float* per_sample1, int64_t ld1, float* summed0, float* summed1, void* stream);
+/* out[n] = sum_rows x[r,n] (bias gradients); partials needs dpipe_colsum_chunks(rows)*N floats */
+int dpipe_colsum_chunks(int rows);
+int dpipe_colsum(const void* x, int64_t ldx, int rows, int N, float* partials, float* out, void* stream);
+
+typedef struct dpipe_qk_bwd_args {
+  const void* dq; const void* dk; const void* dv;  /* bf16 [batch, heads, seq_total, 128] from dpipe_attn_bwd */
+  const void* qhat; const void* khat;              /* bf16, saved by the QKV_ROPE epilogue */
+  const float* q_rstd; const float* k_rstd;        /* fp32 [batch, heads, seq_total] */
+  const void* q_norm_w; const void* k_norm_w;      /* bf16 [128] */
+  const float* rope_cos; const float* rope_sin;    /* fp32 [seq_total, 128] */
+  void* dqkv; int64_t ld;                          /* bf16 token-major [batch*rows_per_batch, >= 3*heads*128] */
+  float* dbias;                                    /* fp32 [3*heads*128]: += column sums of dqkv (caller zeroes) */
+  float* dw;                                       /* fp32 [2][128]: += d q_norm_w, d k_norm_w (caller zeroes) */
+  int batch, heads, seq_total, seq_offset, rows_per_batch;
+} dpipe_qk_bwd_args;
+/* backward of the DPIPE_EPI_QKV_ROPE epilogue for one stream */
+int dpipe_qknorm_rope_bwd(const dpipe_qk_bwd_args* args, void* stream);
+
+/* loss = mean((out - target)^2 * mask); dout (bf16, optional) = 2 (out-target) mask / numel.  workspace: 1024 floats */
+int dpipe_mse_loss(const void* out, const float* target, const float* mask, int64_t numel, float* workspace,
+                   float* loss, void* dout, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* 1F1B pipeline schedule planner (host only).                                                   */
+/* replaces: utils/patches.py:113-160 (train_schedule_steps) driven by deepspeed==0.18.4          */
+/*           runtime/pipe/schedule.py TrainSchedule / InferenceSchedule helpers.                  */
+/* ------------------------------------------------------------------------------------------ */
+enum {
+  DPIPE_OP_TICK_END = 0, /* closes one schedule tick (one `yield cmds` of the reference) */
+  DPIPE_OP_LOAD_MICRO_BATCH = 1,
+  DPIPE_OP_SEND_ACTIVATION = 2,
+  DPIPE_OP_RECV_ACTIVATION = 3,
+  DPIPE_OP_SEND_GRAD = 4,
+  DPIPE_OP_RECV_GRAD = 5,
+  DPIPE_OP_FORWARD_PASS = 6,
+  DPIPE_OP_BACKWARD_PASS = 7,
+  DPIPE_OP_REDUCE_TIED_GRADS = 8,
+  DPIPE_OP_REDUCE_GRADS = 9,
+  DPIPE_OP_OPTIMIZER_STEP = 10
+};
+typedef struct dpipe_instr {
+  int32_t op;          /* DPIPE_OP_* */
+  int32_t buffer;      /* pipe buffer index (-1 when not applicable) */
+  int32_t micro_batch; /* micro-batch id the instruction belongs to (-1 when not applicable) */
+} dpipe_instr;
+
+/* number of activation buffers of a stage: max(2, min(stages - stage_id, micro_batches)) */
+int dpipe_sched_num_pipe_buffers(int micro_batches, int stages, int stage_id);
+/* writes the instruction stream of one train_batch into out[0..capacity); returns the count (call with capacity 0 to size) */
+int dpipe_sched_train(int micro_batches, int stages, int stage_id, dpipe_instr* out, int capacity);
+/* forward-only schedule of eval_batch */
+int dpipe_sched_infer(int micro_batches, int stages, int stage_id, dpipe_instr* out, int capacity);
+/* contiguous min-max partition of n layer weights into `parts` stages; bounds has parts+1 entries
+ * (replaces DeepSpeed partition_balanced behind partition_method='parameters', train.py:81-90,606) */
+int dpipe_partition_balanced(const int64_t* weights, int n, int parts, int* bounds);
+
 #ifdef __cplusplus
 }
 #endif

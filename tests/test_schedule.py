@@ -1,0 +1,76 @@
+"""CPU: the C++ 1F1B planner is bit-exact with (a) traces produced by the reference's own generator
+(tests/golden/schedule_traces.json, made by tests/golden/make_golden_schedule.py from utils/patches.py:113-160),
+(b) the pure-Python oracle restatement, and (c) structural invariants at BASELINE sizes."""
+import json
+import os
+
+import pytest
+
+from diffusion_pipe_b200.pipe.schedule import InferenceSchedule, TrainSchedule
+from oracle import schedule_ref
+
+
+def _norm(ticks):
+    return [[[c.name] + ([c.buffer_id] if hasattr(c, 'buffer_id') else []) for c in t] for t in ticks]
+
+
+def test_matches_reference_generator_traces(golden_dir):
+    with open(os.path.join(golden_dir, 'schedule_traces.json')) as f:
+        golden = json.load(f)
+    assert len(golden) >= 50
+    for key, ticks in golden.items():
+        m, s, st = (int(x) for x in key.split(','))
+        assert _norm(TrainSchedule(m, s, st).steps()) == ticks, key
+
+
+def test_oracle_restatement_matches_golden(golden_dir):
+    with open(os.path.join(golden_dir, 'schedule_traces.json')) as f:
+        golden = json.load(f)
+    for key, ticks in golden.items():
+        m, s, st = (int(x) for x in key.split(','))
+        assert schedule_ref.train_schedule(m, s, st) == ticks, key
+
+
+def test_appendix_c_known_answer():
+    # SURVEY.md Appendix C, stage 1 of (M=4, S=3)
+    names = ['+'.join(c.name + str(getattr(c, 'buffer_id', '')) for c in t) for t in TrainSchedule(4, 3, 1).steps()]
+    assert names[1] == 'RecvActivation0+ForwardPass0'
+    assert names[4] == 'RecvGrad0+SendActivation1+BackwardPass0'
+    assert names[-1] == 'SendGrad1+ReduceTiedGrads+ReduceGrads+OptimizerStep'
+
+
+@pytest.mark.parametrize('m,s', [(16, 8), (16, 4), (21, 8), (64, 8), (1, 8), (3, 2)])
+def test_invariants_at_scale(m, s):
+    sends = {}
+    for st in range(s):
+        sched = TrainSchedule(m, s, st)
+        ticks = sched.steps()
+        assert len(ticks) == 2 * (m + s - 1)
+        assert _norm(ticks) == schedule_ref.train_schedule(m, s, st)
+        fwd, bwd, inflight, peak = [], [], 0, 0
+        for ti, t in enumerate(ticks):
+            for c in t:
+                if c.name == 'ForwardPass':
+                    fwd.append(c.micro_batch_id); inflight += 1; peak = max(peak, inflight)
+                elif c.name == 'BackwardPass':
+                    bwd.append(c.micro_batch_id); inflight -= 1
+                    assert c.micro_batch_id in fwd
+                elif c.name in ('SendActivation', 'RecvActivation', 'SendGrad', 'RecvGrad'):
+                    sends.setdefault((c.name, st, c.micro_batch_id), ti)
+        assert fwd == list(range(m)) and bwd == list(range(m))
+        assert peak <= sched.num_pipe_buffers()
+    # every send is matched by the neighbour's receive in the same tick
+    for (name, st, mb), ti in sends.items():
+        if name == 'SendActivation':
+            assert sends[('RecvActivation', st + 1, mb)] == ti
+        if name == 'SendGrad':
+            assert sends[('RecvGrad', st - 1, mb)] == ti
+
+
+def test_inference_schedule():
+    for m, s in [(1, 1), (4, 2), (5, 3), (9, 8)]:
+        for st in range(s):
+            ticks = InferenceSchedule(m, s, st).steps()
+            assert len(ticks) == m + s - 1
+            assert [c.micro_batch_id for t in ticks for c in t if c.name == 'ForwardPass'] == list(range(m))
+            assert _norm(ticks) == schedule_ref.inference_schedule(m, s, st)
