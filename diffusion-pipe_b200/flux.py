@@ -313,12 +313,70 @@ class FluxPipeline:
         if isinstance(tcfg, str):
             with open(tcfg) as f:
                 tcfg = json.load(f)
+        self.tcfg = dict(FLUX_DEV_CONFIG, **(tcfg or {}))
+        self.dtype, self.device = dtype, device
+        self.pipeline_model = None
+        self.model_engine = None
+        if self.model_config.get('lazy_layers', False):
+            # Stage-local construction: to_layers() hands the engine LayerSpecs and only the layers of this rank's
+            # stage are ever materialised (12 B parameters do not fit eight times on the host, and need not).
+            self.transformer = None
+            return
         self.transformer = FluxTransformer2DModel(tcfg, dtype=dtype, device=device)
         if path := self.model_config.get('transformer_path', None):
             self.load_transformer_weights(path)
         self.transformer.train()
-        self.pipeline_model = None
-        self.model_engine = None
+
+    def _lazy_layers(self):
+        from .pipe.module import LayerSpec
+        cfg, dtype, device = self.tcfg, self.dtype, self.device
+        heads = cfg['num_attention_heads']
+        dim = heads * cfg['attention_head_dim']
+
+        def name_params(module, prefix_map):
+            for n, p in module.named_parameters():
+                for local, glob in prefix_map.items():
+                    if n.startswith(local):
+                        p.original_name = glob + n[len(local):]
+                        break
+            return module
+
+        def build_embed(dev=None):
+            d = dev or device
+            w = EmbeddingWrapper(_plain(dim, cfg['in_channels'], dtype, d),
+                                 CombinedTimestepGuidanceTextProjEmbeddings(dim, cfg['pooled_projection_dim'], dtype, d,
+                                                                            cfg.get('guidance_embeds', True)),
+                                 _plain(dim, cfg['joint_attention_dim'], dtype, d), tuple(cfg['axes_dims_rope']))
+            return name_params(w, {'x_embedder.': 'x_embedder.', 'time_text_embed.': 'time_text_embed.',
+                                   'context_embedder.': 'context_embedder.'})
+
+        def build_double(i, dev=None):
+            w = TransformerWrapper(FluxTransformerBlock(dim, heads, 4, dtype, dev or device), i)
+            return name_params(w, {'block.': f'transformer_blocks.{i}.'})
+
+        def build_single(i, dev=None):
+            w = SingleTransformerWrapper(FluxSingleTransformerBlock(dim, heads, 4, dtype, dev or device), i)
+            return name_params(w, {'block.': f'single_transformer_blocks.{i}.'})
+
+        def build_out(dev=None):
+            d = dev or device
+            w = OutputWrapper(_AdaNorm(dim, 2, dtype, d), _plain(cfg['in_channels'], dim, dtype, d))
+            return name_params(w, {'norm_out.': 'norm_out.', 'proj_out.': 'proj_out.'})
+
+        def count(fn, *a):
+            return sum(p.numel() for p in fn(*a, dev='meta').parameters())
+
+        def spec(cls, fn, *a, n):
+            s = LayerSpec(cls, *a)
+            s.build = lambda fn=fn, a=a: fn(*a)
+            s.param_count = n
+            return s
+        n_double, n_single = count(build_double, 0), count(build_single, 0)
+        layers = [spec(EmbeddingWrapper, build_embed, n=count(build_embed))]
+        layers += [spec(TransformerWrapper, build_double, i, n=n_double) for i in range(cfg['num_layers'])]
+        layers += [spec(SingleTransformerWrapper, build_single, i, n=n_single) for i in range(cfg['num_single_layers'])]
+        layers.append(spec(OutputWrapper, build_out, n=count(build_out)))
+        return layers
 
     # ---- weights ----
     def load_transformer_weights(self, path):
@@ -398,6 +456,8 @@ class FluxPipeline:
 
     # ---- layers / loss ----
     def to_layers(self):
+        if self.transformer is None:
+            return self._lazy_layers()
         t = self.transformer
         layers = [EmbeddingWrapper(t.x_embedder, t.time_text_embed, t.context_embedder, t.axes_dim)]
         for i, block in enumerate(t.transformer_blocks):

@@ -16,6 +16,24 @@ EPI_MUL_GELU_GRAD = _lib.EPI_MUL_GELU_GRAD
 
 # kernel-launch counter (bench.py reports it as gpu_launches)
 LAUNCHES = 0
+# when a list, tensor-core kernels append (start_event, end_event, algorithmic_flops, kind) — bench.py's roofline
+PROFILE = None
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _prof_end(e0, flops, kind):
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    PROFILE.append((e0, e1, flops, kind))
 
 
 def _stream():
@@ -86,7 +104,9 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, epilogue=EPI_STORE, bias=Non
     args.cta_group = cta_group
     if qkv is not None:
         args.qkv = ctypes.pointer(qkv)
+    _e = _prof_begin()
     check(lib().dpipe_gemm_bf16(ctypes.byref(args), _stream()), 'dpipe_gemm_bf16')
+    _prof_end(_e, 2.0 * M * N * K, 'gemm')
     LAUNCHES += 1
     return out
 
@@ -132,7 +152,9 @@ def attn_fwd(q, k, v, out=None, lse=None, scale=None):
     a.lse = _ptr(lse)
     a.batch, a.heads, a.seq_q, a.seq_k = B, H, Lq, Lk
     a.scale = float(scale if scale is not None else 128 ** -0.5)
+    _e = _prof_begin()
     check(lib().dpipe_attn_fwd(ctypes.byref(a), _stream()), 'dpipe_attn_fwd')
+    _prof_end(_e, 4.0 * B * H * Lq * Lk * 128, 'attn_fwd')
     LAUNCHES += 1
     return out, lse
 
@@ -160,7 +182,9 @@ def attn_bwd(q, k, v, o, d_o, lse, scale=None, dq=None, dk=None, dv=None, delta=
     a.dq, a.dk, a.dv = _ptr(dq), _ptr(dk), _ptr(dv)
     a.batch, a.heads, a.seq_q, a.seq_k = B, H, Lq, Lk
     a.scale = float(scale if scale is not None else 128 ** -0.5)
+    _e = _prof_begin()
     check(lib().dpipe_attn_bwd(ctypes.byref(a), _stream()), 'dpipe_attn_bwd')
+    _prof_end(_e, 10.0 * B * H * Lq * Lk * 128, 'attn_bwd')
     LAUNCHES += 3
     return dq, dk, dv
 

@@ -180,7 +180,10 @@ class PipelineModule(nn.Module):
         counts = [0] * len(self._layer_specs)
         for idx, layer in enumerate(self._layer_specs):
             if isinstance(layer, LayerSpec):
-                counts[idx] = sum(p.numel() for p in layer.build().parameters())
+                if getattr(layer, 'param_count', None) is not None:
+                    counts[idx] = int(layer.param_count)      # known without materialising the layer
+                else:
+                    counts[idx] = sum(p.numel() for p in layer.build().parameters())
             elif isinstance(layer, nn.Module):
                 counts[idx] = sum(p.numel() for p in layer.parameters())
         return counts
