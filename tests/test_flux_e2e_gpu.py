@@ -62,12 +62,12 @@ def test_layers_and_loss_match_oracle():
         if emu:   # parameter gradients against the oracle with the reference rounding points
             rloss.backward()
             rg = {n: p.grad for n, p in ref.named_parameters()}
-            worst = 0.0
+            errs = {}
             for n, p in model.transformer.named_parameters():
                 assert p.grad is not None, n
-                r = ((p.grad.float().cpu() - rg[n]).norm() / (rg[n].norm() + 1e-12)).item()
-                worst = max(worst, r)
-                assert r <= 5e-2, (n, r)
+                errs[n] = ((p.grad.float().cpu() - rg[n]).norm() / (rg[n].norm() + 1e-12)).item()
+            bad = sorted(((v, k) for k, v in errs.items() if v > 5e-2), reverse=True)
+            assert not bad, bad[:8]
 
 
 def test_engine_train_batch_matches_oracle_engine():
