@@ -73,4 +73,11 @@ SIGNATURES['dpipe_sched_num_pipe_buffers'] = (c_int, [c_int, c_int, c_int])
 SIGNATURES['dpipe_sched_train'] = (c_int, [c_int, c_int, c_int, c_void_p, c_int])
 SIGNATURES['dpipe_sched_infer'] = (c_int, [c_int, c_int, c_int, c_void_p, c_int])
 SIGNATURES['dpipe_partition_balanced'] = (c_int, [c_void_p, c_int, c_int, c_void_p])
+SIGNATURES['dpipe_ipc_alloc'] = (c_int, [c_int64, ctypes.POINTER(c_void_p), c_void_p])
+SIGNATURES['dpipe_ipc_open'] = (c_int, [c_void_p, ctypes.POINTER(c_void_p)])
+SIGNATURES['dpipe_ipc_close'] = (c_int, [c_void_p])
+SIGNATURES['dpipe_ipc_free'] = (c_int, [c_void_p])
+SIGNATURES['dpipe_peer_copy'] = (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p])
+SIGNATURES['dpipe_flag_write'] = (c_int, [c_void_p, ctypes.c_uint64, c_void_p])
+SIGNATURES['dpipe_flag_wait_geq'] = (c_int, [c_void_p, ctypes.c_uint64, ctypes.c_double, c_void_p])
 SIGNATURES['dpipe_mse_loss'] =(c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p])

@@ -237,6 +237,8 @@ class PipelineEngine:
             self.pipe_buffers['outputs'][b] = tuple(outputs)
         if not train:
             self.pipe_buffers['inputs'][b] = None
+            if self.is_last_stage() and not self.is_first_stage() and hasattr(self.link, 'release_activations'):
+                self.link.release_activations(b, cmd.micro_batch_id)
 
     def _exec_backward_pass(self, cmd, train):
         b = cmd.buffer_id
@@ -249,6 +251,8 @@ class PipelineEngine:
             assert len(outs) == len(grads)
             pairs = [(t, g) for t, g in zip(outs, grads) if t.requires_grad]
             torch.autograd.backward(tensors=[p[0] for p in pairs], grad_tensors=[p[1] for p in pairs])
+            if hasattr(self.link, 'release_grads'):
+                self.link.release_grads(b, cmd.micro_batch_id)
         self.pipe_buffers['outputs'][b] = None
         self.pipe_buffers['grads'][b] = None
         self.pipe_buffers['labels'][b] = None

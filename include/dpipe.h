@@ -207,6 +207,24 @@ int dpipe_sched_infer(int micro_batches, int stages, int stage_id, dpipe_instr* 
  * (replaces DeepSpeed partition_balanced behind partition_method='parameters', train.py:81-90,606) */
 int dpipe_partition_balanced(const int64_t* weights, int n, int parts, int* bounds);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Stage-boundary transport: CUDA-IPC mailboxes, peer copies over NVLink, device-side flags.     */
+/* replaces: DeepSpeed _exec_send/recv_activations/_grads over NCCL p2p, as emitted by the       */
+/*           schedule at utils/patches.py:134-143.                             */
+/* ------------------------------------------------------------------------------------------ */
+/* cudaMalloc `bytes` (zero-filled) on the current device and export a 64-byte IPC handle */
+int dpipe_ipc_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64);
+/* map a peer process' allocation; the returned pointer is valid in this process */
+int dpipe_ipc_open(const unsigned char* handle64, void** dev_ptr);
+int dpipe_ipc_close(void* dev_ptr);
+int dpipe_ipc_free(void* dev_ptr);
+/* cudaMemcpyPeerAsync(dst on dst_device <- src on src_device) on `stream` */
+int dpipe_peer_copy(void* dst, int dst_device, const void* src, int src_device, int64_t bytes, void* stream);
+/* *flag = value with system-scope release semantics, ordered after all prior work on `stream` */
+int dpipe_flag_write(void* flag, uint64_t value, void* stream);
+/* blocks `stream` (not the host) until *flag >= value; traps after timeout_s seconds (0 = never) */
+int dpipe_flag_wait_geq(const void* flag, uint64_t value, double timeout_s, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,127 @@
+"""CPU / gloo: the pipeline engine (C++ 1F1B planner + torch.distributed links) reproduces the single-process oracle
+engine (oracle/engine_ref.py) for 1 and 2 pipeline stages and for 2-way data parallelism — loss, clipped gradient
+norm and post-step weights in fp32 to 1e-5.  Multi-process cases spawn world_size-2 gloo groups on 127.0.0.1."""
+import os
+import socket
+import sys
+import tempfile
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GAS, MBS, STEPS = 4, 2, 2
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, stages, outdir, partition):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import toy_model
+    from diffusion_pipe_b200.pipe import ManualPipelineModule, dist, initialize
+    torch.set_num_threads(1)
+    dist.init_distributed('gloo')
+    layers = toy_model.make_layers()
+    pm = ManualPipelineModule(layers=layers, num_stages=stages, partition_method=partition,
+                              manual_partition_split=[3] if partition == 'manual' else None, loss_fn=toy_model.loss_fn,
+                              dynamic_shape=True, device=torch.device('cpu'))
+    engine, _, _, _ = initialize(model=pm, config={'train_micro_batch_size_per_gpu': MBS, 'gradient_accumulation_steps': GAS,
+                                                   'gradient_clipping': 0.5, 'steps_per_print': 0, 'stage_link': 'dist'})
+    params = [p for p in pm.parameters() if p.requires_grad]
+    engine._configure_optimizer(lambda ps: torch.optim.SGD(ps, lr=0.1) if ps else None, params)
+    dp_rank = engine.grid.get_data_parallel_rank()
+    losses, norms = [], []
+    for step in range(STEPS):
+        engine.reset_activation_shape()
+        mbs = toy_model.make_micro_batches(GAS, MBS, seed=100 * step + dp_rank)
+        it = iter(mbs) if (engine.is_first_stage() or engine.is_last_stage()) else None
+        losses.append(float(engine.train_batch(it)))
+        norms.append(float(engine._grad_norm))
+    ev = float(engine.eval_batch(iter(toy_model.make_micro_batches(3, MBS, seed=999)), num_micro_batches=3)) \
+        if (engine.is_first_stage() or engine.is_last_stage()) else float(engine.eval_batch(None, num_micro_batches=3))
+    sd = {p.original_name: p.detach().clone() for p in pm.parameters()}
+    torch.save({'losses': losses, 'norms': norms, 'eval': ev, 'params': sd, 'stage': engine.stage_id, 'dp': dp_rank,
+                'parts': pm.parts}, os.path.join(outdir, f'rank{rank}.pt'))
+    dist.barrier()
+
+
+def _reference(dp_world):
+    import toy_model
+    from oracle.engine_ref import RefPipelineEngine
+    layers = toy_model.make_layers()
+    params = [p for l in layers for p in l.parameters() if p.requires_grad]
+    opt = torch.optim.SGD(params, lr=0.1)
+    eng = RefPipelineEngine(layers, toy_model.loss_fn, opt, None, GAS * dp_world, 0.5)
+    losses, norms = [], []
+    for step in range(STEPS):
+        mbs = []
+        for d in range(dp_world):
+            mbs += toy_model.make_micro_batches(GAS, MBS, seed=100 * step + d)
+        losses.append(float(eng.train_batch(mbs)))
+        norms.append(float(eng.grad_norm))
+    with torch.no_grad():
+        ev = sum(float(toy_model.loss_fn(eng.forward(f), l)) for f, l in toy_model.make_micro_batches(3, MBS, seed=999)) / 3
+    sd = {p.original_name: p.detach().clone() for l in layers for p in l.parameters()}
+    return losses, norms, ev, sd
+
+
+def _run(world, stages, partition='uniform'):
+    with tempfile.TemporaryDirectory() as d:
+        port = _free_port()
+        if world == 1:
+            _worker(0, 1, port, stages, d, partition)
+            import torch.distributed as tdist
+            if tdist.is_initialized():
+                tdist.destroy_process_group()
+        else:
+            mp.spawn(_worker, args=(world, port, stages, d, partition), nprocs=world, join=True)
+        return [torch.load(os.path.join(d, f'rank{r}.pt'), weights_only=False) for r in range(world)]
+
+
+def _check(results, dp_world):
+    losses, norms, ev, sd = _reference(dp_world)
+    for r in results:
+        assert r['losses'] == pytest.approx(losses, rel=1e-5, abs=1e-7), (r['losses'], losses)
+        assert r['norms'] == pytest.approx(norms, rel=1e-5)
+        assert r['eval'] == pytest.approx(ev, rel=1e-5)
+        for k, v in r['params'].items():
+            assert torch.allclose(v, sd[k], rtol=1e-5, atol=1e-6), k
+
+
+def test_single_stage_world_1():
+    res = _run(1, 1)
+    assert res[0]['parts'] == [0, 6]
+    _check(res, 1)
+
+
+def test_two_stages_world_2():
+    res = _run(2, 2, 'manual')
+    assert [r['stage'] for r in res] == [0, 1] and res[0]['parts'] == [0, 3, 6]
+    assert set(res[0]['params']) | set(res[1]['params']) == set(_reference(1)[3])   # each stage owns only its layers
+    assert not (set(res[0]['params']) & set(res[1]['params']))
+    _check(res, 1)
+
+
+def test_two_stages_parameter_partition():
+    res = _run(2, 2, 'parameters')
+    _check(res, 1)
+
+
+def test_data_parallel_world_2():
+    res = _run(2, 1)
+    assert [r['dp'] for r in res] == [0, 1]
+    _check(res, 2)
