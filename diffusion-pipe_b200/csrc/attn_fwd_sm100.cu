@@ -192,22 +192,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       mbar_wait(smem_u32(&s_full[i]), j & 1);
       tc_fence_after();
       const int valid = min(TK, p.seq_k - j * TK);  // keys of this tile that exist
-      // ---- pass 1: row max ----
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t r[32];
-        tmem_ld_x32(t_s + cc * 32, r);
-        tmem_ld_wait();
-        if (valid >= cc * 32 + 32) {
+      // ---- one TMEM read of the whole 128-column row; everything below stays in registers ----
+      uint32_t r[128];
+      tmem_ld_x32(t_s, r);
+      tmem_ld_x32(t_s + 32, r + 32);
+      tmem_ld_x32(t_s + 64, r + 64);
+      tmem_ld_x32(t_s + 96, r + 96);
+      tmem_ld_wait();
+      if (valid < TK) {   // last key tile: keys beyond seq_k get -inf (warp-uniform branch)
 #pragma unroll
-          for (int x = 0; x < 32; ++x) mx = fmaxf(mx, __uint_as_float(r[x]));
-        } else {
-#pragma unroll
-          for (int x = 0; x < 32; ++x)
-            if (cc * 32 + x < valid) mx = fmaxf(mx, __uint_as_float(r[x]));
-        }
+        for (int x = 0; x < 128; ++x)
+          if (x >= valid) r[x] = 0xff800000u;
       }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int x = 0; x < 128; x += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(r[x]));
+        mx1 = fmaxf(mx1, __uint_as_float(r[x + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(r[x + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(r[x + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       const float m_new = fmaxf(m, mx * c);
       // ---- lazy rescale: only when some row of this warp grew by more than 2^8 ----
       if (j == 0) {
@@ -220,38 +225,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
           l *= alpha;
 #pragma unroll 1
           for (int cc = 0; cc < 4; ++cc) {
-            uint32_t r[32];
-            tmem_ld_x32(t_o + cc * 32, r);
+            uint32_t ro[32];
+            tmem_ld_x32(t_o + cc * 32, ro);
             tmem_ld_wait();
 #pragma unroll
-            for (int x = 0; x < 32; ++x) r[x] = __float_as_uint(__uint_as_float(r[x]) * alpha);
-            tmem_st_x32(t_o + cc * 32, r);
+            for (int x = 0; x < 32; ++x) ro[x] = __float_as_uint(__uint_as_float(ro[x]) * alpha);
+            tmem_st_x32(t_o + cc * 32, ro);
           }
           tmem_st_wait();
         }
       }
-      // ---- pass 2: P = exp2(S*c - m), row sum, bf16 pack, store to TMEM ----
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t r[32];
-        tmem_ld_x32(t_s + cc * 32, r);
-        tmem_ld_wait();
-        uint32_t pk[16];
-        float sum = 0.f;
+      // ---- P = exp2(S*c - m) in place (bf16 pairs packed into the low half of r), fp32 row sum ----
+      float s0 = 0.f, s1 = 0.f;
+      const float neg_m = -m;
 #pragma unroll
-        for (int x = 0; x < 32; x += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(r[x]), c, -m));
-          float p1 = fast_exp2(fmaf(__uint_as_float(r[x + 1]), c, -m));
-          if (cc * 32 + x >= valid) p0 = 0.f;
-          if (cc * 32 + x + 1 >= valid) p1 = 0.f;
-          // the sum uses the same bf16-rounded probabilities the tensor core will consume
-          __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-          sum += __bfloat162float(pb.x) + __bfloat162float(pb.y);
-          pk[x >> 1] = *reinterpret_cast<uint32_t*>(&pb);
-        }
-        l += sum;
-        tmem_st_x16(t_p + cc * 16, pk);
+      for (int x = 0; x < 128; x += 2) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(r[x]), c, neg_m));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(r[x + 1]), c, neg_m));
+        s0 += p0;
+        s1 += p1;
+        r[x >> 1] = pack_bf16(p0, p1);
       }
+      l += s0 + s1;
+      tmem_st_x32(t_p, r);
+      tmem_st_x32(t_p + 32, r + 32);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();

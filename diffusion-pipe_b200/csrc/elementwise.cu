@@ -248,18 +248,30 @@ struct FinishArgs {
 };
 __global__ void colreduce_finish_kernel(const float* __restrict__ partials, int batch, int nchunk, int nslot, int D,
                                         FinishArgs fa) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  // block = 32 columns x 8 chunk groups; grid = (D/32, nslot)
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int d = blockIdx.x * 32 + tx;
   const int s = blockIdx.y;
-  if (d >= D) return;
   float total = 0.f;
   for (int b = 0; b < batch; ++b) {
     float acc = 0.f;
-    const float* p = partials + (((int64_t)b * nchunk) * nslot + s) * D + d;
-    for (int c = 0; c < nchunk; ++c) acc += p[(int64_t)c * nslot * D];
-    if (fa.per_sample[s]) fa.per_sample[s][(int64_t)b * fa.ld[s] + d] = acc;
-    total += acc;
+    if (d < D) {
+      const float* p = partials + (((int64_t)b * nchunk) * nslot + s) * D + d;
+      for (int c = ty; c < nchunk; c += 8) acc += p[(int64_t)c * nslot * D];
+    }
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0) {
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v += red[k][tx];
+      if (d < D && fa.per_sample[s]) fa.per_sample[s][(int64_t)b * fa.ld[s] + d] = v;
+      total += v;
+    }
+    __syncthreads();
   }
-  if (fa.summed[s]) fa.summed[s][d] = total;
+  if (ty == 0 && d < D && fa.summed[s]) fa.summed[s][d] = total;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -296,45 +308,73 @@ __global__ void qknorm_rope_bwd_kernel(const QkBwdParams p) {
     const uint2 w2 = *reinterpret_cast<const uint2*>((which == 0 ? p.wq : p.wk) + c0);
     wv[0] = bf16_lo(w2.x); wv[1] = bf16_hi(w2.x); wv[2] = bf16_lo(w2.y); wv[3] = bf16_hi(w2.y);
   }
-  for (int t = t0; t < t1; ++t) {
-    const int pos = p.seq_offset + t;
-    const uint2 g2 = *reinterpret_cast<const uint2*>(src + (hb + pos) * 128 + c0);
-    float g[4] = {bf16_lo(g2.x), bf16_hi(g2.x), bf16_lo(g2.y), bf16_hi(g2.y)};
-    float o[4];
-    if (which == 2) {
+  constexpr int TB = 4;   // tokens in flight per warp: all loads of a group are issued before any dependent math
+  const __nv_bfloat16* hat = which == 0 ? p.qhat : p.khat;
+  const float* rstd_p = which == 0 ? p.q_rstd : p.k_rstd;
+  for (int tb = t0; tb < t1; tb += TB) {
+    uint2 g2[TB], h2[TB];
+    float4 cs[TB], sn[TB];
+    float rs[TB];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = g[j];
-    } else {
-      const float4 cs = *reinterpret_cast<const float4*>(p.cos + (int64_t)pos * 128 + c0);
-      const float4 sn = *reinterpret_cast<const float4*>(p.sin + (int64_t)pos * 128 + c0);
-      // transpose of the rotation  out[2i] = y[2i]c[2i] - y[2i+1]s[2i] ;  out[2i+1] = y[2i+1]c[2i+1] + y[2i]s[2i+1]
-      float dy[4];
-      dy[0] = g[0] * cs.x + g[1] * sn.y;
-      dy[1] = g[1] * cs.y - g[0] * sn.x;
-      dy[2] = g[2] * cs.z + g[3] * sn.w;
-      dy[3] = g[3] * cs.w - g[2] * sn.z;
-      const uint2 h2 = *reinterpret_cast<const uint2*>((which == 0 ? p.qhat : p.khat) + (hb + pos) * 128 + c0);
-      const float xh[4] = {bf16_lo(h2.x), bf16_hi(h2.x), bf16_lo(h2.y), bf16_hi(h2.y)};
-      const float rstd = (which == 0 ? p.q_rstd : p.k_rstd)[hb + pos];
-      float dot = 0.f, dxh[4];
+    for (int u = 0; u < TB; ++u) {
+      const int t = min(tb + u, t1 - 1);
+      const int pos = p.seq_offset + t;
+      g2[u] = *reinterpret_cast<const uint2*>(src + (hb + pos) * 128 + c0);
+      if (which < 2) {
+        cs[u] = *reinterpret_cast<const float4*>(p.cos + (int64_t)pos * 128 + c0);
+        sn[u] = *reinterpret_cast<const float4*>(p.sin + (int64_t)pos * 128 + c0);
+        h2[u] = *reinterpret_cast<const uint2*>(hat + (hb + pos) * 128 + c0);
+        rs[u] = rstd_p[hb + pos];
+      }
+    }
+    float o[TB][4], xh[TB][4], dxh[TB][4], dot[TB];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        wsum[j] += dy[j] * xh[j];
-        dxh[j] = dy[j] * wv[j];
-        dot += dxh[j] * xh[j];
+    for (int u = 0; u < TB; ++u) {
+      const float g[4] = {bf16_lo(g2[u].x), bf16_hi(g2[u].x), bf16_lo(g2[u].y), bf16_hi(g2[u].y)};
+      const bool live = tb + u < t1;
+      if (which == 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[u][j] = g[j];
+      } else {
+        // transpose of the rotation  out[2i] = y[2i]c[2i] - y[2i+1]s[2i] ;  out[2i+1] = y[2i+1]c[2i+1] + y[2i]s[2i+1]
+        float dy[4];
+        dy[0] = g[0] * cs[u].x + g[1] * sn[u].y;
+        dy[1] = g[1] * cs[u].y - g[0] * sn[u].x;
+        dy[2] = g[2] * cs[u].z + g[3] * sn[u].w;
+        dy[3] = g[3] * cs[u].w - g[2] * sn[u].z;
+        xh[u][0] = bf16_lo(h2[u].x); xh[u][1] = bf16_hi(h2[u].x); xh[u][2] = bf16_lo(h2[u].y); xh[u][3] = bf16_hi(h2[u].y);
+        dot[u] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (live) wsum[j] += dy[j] * xh[u][j];
+          dxh[u][j] = dy[j] * wv[j];
+          dot[u] += dxh[u][j] * xh[u][j];
+        }
+      }
+    }
+    if (which < 2) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int u = 0; u < TB; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], off);
       }
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
-      dot *= (1.0f / 128.0f);
+      for (int u = 0; u < TB; ++u) {
+        const float d = dot[u] * (1.0f / 128.0f);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = rstd * (dxh[j] - xh[j] * dot);
+        for (int j = 0; j < 4; ++j) o[u][j] = rs[u] * (dxh[u][j] - xh[u][j] * d);
+      }
     }
-    uint2 ov;
-    ov.x = pack_bf16(o[0], o[1]);
-    ov.y = pack_bf16(o[2], o[3]);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) bsum[j] += (j & 1) ? bf16_hi((j < 2) ? ov.x : ov.y) : bf16_lo((j < 2) ? ov.x : ov.y);
-    *reinterpret_cast<uint2*>(p.dqkv + ((int64_t)b * p.rows_per_batch + t) * p.ld + (which * p.heads + head) * 128 + c0) = ov;
+    for (int u = 0; u < TB; ++u) {
+      if (tb + u >= t1) continue;
+      const int t = tb + u;
+      uint2 ov;
+      ov.x = pack_bf16(o[u][0], o[u][1]);
+      ov.y = pack_bf16(o[u][2], o[u][3]);
+      bsum[0] += bf16_lo(ov.x); bsum[1] += bf16_hi(ov.x); bsum[2] += bf16_lo(ov.y); bsum[3] += bf16_hi(ov.y);
+      *reinterpret_cast<uint2*>(p.dqkv + ((int64_t)b * p.rows_per_batch + t) * p.ld + (which * p.heads + head) * 128 + c0) = ov;
+    }
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -433,7 +473,7 @@ extern "C" int dpipe_colreduce_finish(const float* partials, int batch, int nchu
   fa.per_sample[0] = per_sample0; fa.per_sample[1] = per_sample1;
   fa.ld[0] = ld0; fa.ld[1] = ld1;
   fa.summed[0] = summed0; fa.summed[1] = summed1;
-  dim3 grid((D + 255) / 256, nslot);
+  dim3 grid((D + 31) / 32, nslot);
   colreduce_finish_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partials, batch, nchunk, nslot, D, fa);
   DPIPE_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -450,7 +490,7 @@ extern "C" int dpipe_colsum(const void* x, int64_t ldx, int rows, int N, float* 
   DPIPE_CUDA_CHECK(cudaGetLastError());
   FinishArgs fa = {};
   fa.summed[0] = out;
-  colreduce_finish_kernel<<<dim3((N + 255) / 256, 1), 256, 0, (cudaStream_t)stream>>>(partials, 1, nchunk, 1, N, fa);
+  colreduce_finish_kernel<<<dim3((N + 31) / 32, 1), 256, 0, (cudaStream_t)stream>>>(partials, 1, nchunk, 1, N, fa);
   DPIPE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
