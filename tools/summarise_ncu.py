@@ -1,0 +1,94 @@
+"""Turns gpurun_out/ ncu artefacts into the tracked summaries under profiles/ (run on the build box, no GPU needed).
+
+    python tools/summarise_ncu.py r01
+"""
+import collections
+import csv
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R = sys.argv[1] if len(sys.argv) > 1 else 'r01'
+OUT = os.path.join(ROOT, 'profiles')
+SRC = os.path.join(ROOT, 'gpurun_out')
+os.makedirs(OUT, exist_ok=True)
+
+
+def launch_list():
+    path = os.path.join(SRC, f'launches_{R}.csv')
+    if not os.path.exists(path):
+        return
+    with open(path) as f:
+        lines = [l for l in f if not l.startswith('==')]
+    rd = csv.reader(lines)
+    hdr = next(rd)
+    ki, vi, ui = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for row in rd:
+        if len(row) <= vi:
+            continue
+        try:
+            v = float(row[vi].replace(',', ''))
+        except ValueError:
+            continue
+        v *= {'ns': 1.0, 'us': 1e3, 'ms': 1e6, 's': 1e9}.get(row[ui], 1.0)
+        name = re.sub(r'\(.*', '', re.sub(r'<.*', '', row[ki])).replace('void ', '').strip()[:60]
+        agg[name][0] += 1
+        agg[name][1] += v
+    tot = sum(v[1] for v in agg.values())
+    n = sum(v[0] for v in agg.values())
+    with open(os.path.join(OUT, f'{R}_launches_summary.md'), 'w') as f:
+        f.write(f'# {R}: ncu launch list of `python bench.py --steps 1 --warmup 1` (Flux-dev 1024^2, 1 GPU)\n\n')
+        f.write('`ncu --metrics gpu__time_duration.sum --clock-control none -s 42000 -c 4000` — per-launch times are cold-cache and\n'
+                'serialised: compare SHARES with bench.py\'s live CUDA-event shares, not absolutes.\n\n')
+        f.write(f'{n} launches, {tot / 1e6:.1f} ms of device time (about 1.9 micro-batches of the steady state).\n\n')
+        f.write('| share | total ms | launches | avg us | kernel |\n|---:|---:|---:|---:|---|\n')
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            if v[1] / tot < 5e-4:
+                continue
+            f.write(f'| {v[1] / tot * 100:.2f}% | {v[1] / 1e6:.2f} | {v[0]} | {v[1] / v[0] / 1e3:.1f} | `{k}` |\n')
+    shutil.copy(path, os.path.join(OUT, f'{R}_launches.csv'))
+
+
+WANT = ['gpu__time_duration.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+        'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'launch__registers_per_thread', 'launch__grid_size',
+        'launch__cluster_dim_x', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'smsp__inst_executed.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']
+
+
+def full_captures():
+    rows_out = []
+    for fn in sorted(os.listdir(SRC)):
+        if not (fn.endswith('.ncu-rep') and R in fn):
+            continue
+        p = subprocess.run(['ncu', '-i', os.path.join(SRC, fn), '--page', 'raw', '--csv'], capture_output=True, text=True)
+        rd = list(csv.reader(p.stdout.splitlines()))
+        if len(rd) < 3:
+            continue
+        hdr, units = rd[0], rd[1]
+        idx = {h: i for i, h in enumerate(hdr)}
+        for row in rd[2:]:
+            d = {'report': fn, 'kernel': row[idx['Kernel Name']][:90]}
+            for w in WANT:
+                if w in idx:
+                    d[w] = f'{row[idx[w]]} {units[idx[w]]}'.strip()
+            rows_out.append(d)
+    if not rows_out:
+        return
+    with open(os.path.join(OUT, f'{R}_full_captures.md'), 'w') as f:
+        f.write(f'# {R}: `ncu --set full --clock-control none --import-source on` captures (1 double + 1 single block at the real shapes)\n\n')
+        for d in rows_out:
+            f.write(f"## {d['kernel']}\n\n(report {d['report']}, kept in gpurun_out/ — too large for git)\n\n")
+            for w in WANT:
+                if w in d:
+                    f.write(f'- `{w}`: {d[w]}\n')
+            f.write('\n')
+
+
+launch_list()
+full_captures()
+print(os.listdir(OUT))
