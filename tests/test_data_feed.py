@@ -1,0 +1,141 @@
+"""CPU: batch-index bookkeeping and the micro-batch loader are BIT-EXACT with the reference's own code
+(tests/golden/datafeed_traces.json, produced by tests/golden/make_golden_datafeed.py from utils/dataset.py and train.py)."""
+import json
+import os
+
+import pytest
+import torch
+
+from diffusion_pipe_b200 import data_feed as DF
+
+
+class SizeBucket:
+    def __init__(self, ds_id, size_bucket, n, with_mask=False):
+        self.ds_id, self.size_bucket, self.n, self.with_mask = ds_id, tuple(size_bucket), n, with_mask
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, idx):
+        idx = idx % self.n
+        ex = {'latents': torch.full((2, 2), float(self.ds_id * 1000 + idx)), 'id': self.ds_id * 1000 + idx, 'mask': None}
+        if self.with_mask and idx % 3 == 0:
+            ex['mask'] = torch.full((2, 2), 0.5)
+        return ex
+
+
+LAYOUTS = {
+    'single_bucket': [[((1.0, 512, 512, 1), 37)]],
+    'two_dirs_mixed': [[((1.0, 512, 512, 1), 23), ((0.75, 448, 576, 1), 11)], [((1.0, 512, 512, 1), 9), ((1.33, 576, 448, 1), 17)]],
+    'video_and_image': [[((1.0, 512, 512, 1), 20), ((1.0, 512, 512, 33), 14)], [((1.0, 1024, 1024, 1), 10)]],
+}
+
+
+def make(layout, with_mask=False):
+    out, k = [], 0
+    for d in layout:
+        for sb, n in d:
+            out.append(SizeBucket(k, sb, n, with_mask))
+            k += 1
+    return DF.BatchedDataset(out)
+
+
+class Model:
+    def prepare_inputs(self, batch, timestep_quantile=None):
+        return (batch['latents'], torch.tensor(batch['id'])), (batch['latents'] * 2, batch['mask'])
+
+
+class Engine:
+    is_pipe_parallel = False
+    micro_batches = 3
+
+    def is_first_stage(self):
+        return True
+
+    def is_last_stage(self):
+        return True
+
+
+@pytest.fixture(scope='module')
+def golden(golden_dir):
+    with open(os.path.join(golden_dir, 'datafeed_traces.json')) as f:
+        return json.load(f)
+
+
+def test_iteration_order_and_rank_slices_are_bit_exact(golden):
+    assert len(golden['order']) >= 80
+    for key, want in golden['order'].items():
+        lname, dp_world, dp_rank, mbs, gas, img = key.split('|')
+        mbs, img = json.loads(mbs), json.loads(img)
+        pd = {int(k): v for k, v in mbs.items()} if isinstance(mbs, dict) else {None: mbs}
+        pdi = {int(k): v for k, v in img.items()} if isinstance(img, dict) else {None: img}
+        ds = make(LAYOUTS[lname])
+        ds.post_init(int(dp_rank), int(dp_world), pd, int(gas), pdi)
+        assert [list(map(int, x)) for x in ds.iteration_order] == want['iteration_order'], key
+        assert [[int(x) for x in ds[i]['id']] for i in range(len(ds))] == want['batches'], key
+
+
+def test_pipeline_dataloader_epochs_and_resume(golden):
+    for key, want in golden['loader'].items():
+        lname, gas = key.split('|')
+        gas = int(gas)
+        ds = make(LAYOUTS[lname], with_mask=True)
+        ds.post_init(0, 1, {None: 2}, gas, {None: 2})
+        dl = DF.PipelineDataLoader(ds, Engine(), gas, Model(), num_dataloader_workers=0)
+        assert len(dl) == want['len']
+        saved = None
+        for i, (epoch, pulled, ids, mask_numel) in enumerate(want['trace']):
+            (lat, got_ids), (tgt, mask) = next(dl)
+            assert (dl.epoch, dl.num_batches_pulled, [int(x) for x in got_ids], int(mask.numel())) == \
+                (epoch, pulled, ids, mask_numel), (key, i)
+            assert torch.equal(tgt, lat * 2)
+            if i == want['saved_at']:
+                saved = dl.state_dict()
+        assert saved == want['saved_state']
+        ds2 = make(LAYOUTS[lname], with_mask=True)
+        ds2.post_init(0, 1, {None: 2}, gas, {None: 2})
+        dl2 = DF.PipelineDataLoader(ds2, Engine(), gas, Model(), num_dataloader_workers=0)
+        dl2.load_state_dict(saved)
+        for i, (epoch, pulled, ids) in enumerate(want['resumed']):
+            mb = next(dl2)
+            assert (dl2.epoch, dl2.num_batches_pulled, [int(x) for x in mb[0][1]]) == (epoch, pulled, ids), (key, i)
+
+
+def test_split_batch_and_none_fields(golden):
+    feats = (torch.arange(24).view(6, 4), None, torch.arange(6))
+    label = (torch.arange(12).view(6, 2), None)
+    got = [[[t.tolist() for t in f], [t.tolist() for t in l]] for f, l in DF.split_batch((feats, label), 3)]
+    assert got == golden['split']['6x3']
+    assert DF.split_batch((feats, label), 3)[0][0][1].numel() == 0
+
+
+def test_get_data_iterator_for_step(golden):
+    class Mid(Engine):
+        def is_first_stage(self):
+            return False
+
+        def is_last_stage(self):
+            return False
+    assert list(DF.get_data_iterator_for_step(iter(range(100)), Engine())) == golden['iter_for_step']['first']
+    assert DF.get_data_iterator_for_step(iter(range(100)), Mid()) is golden['iter_for_step']['middle']
+
+
+def test_seeded_shuffle_leaves_global_rng_untouched():
+    import random
+    random.seed(123)
+    a = random.random()
+    random.seed(123)
+    x = list(range(50))
+    DF.seeded_shuffle(x, 0)
+    assert random.random() == a
+    y = list(range(50))
+    DF.seeded_shuffle(y, 0)
+    assert x == y and x != list(range(50))
+
+
+def test_empty_and_dropped_buckets():
+    ds = DF.BatchedDataset([SizeBucket(0, (1.0, 512, 512, 1), 3)])
+    ds.post_init(0, 1, {None: 2}, 2, {None: 2})          # global batch 4 > 3 examples: bucket dropped entirely
+    assert len(ds) == 0
+    with pytest.raises(RuntimeError):
+        DF.PipelineDataLoader(ds, Engine(), 2, Model(), num_dataloader_workers=0)
