@@ -1,0 +1,74 @@
+"""CPU: the driver's CLI / TOML surface (train.py:41-143, 396-429).  GPU: a two-step end-to-end run of train.py on a small
+Flux model with save + resume."""
+import json
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import train as T  # noqa: E402
+
+
+def test_cli_accepts_the_reference_flags():
+    a = T.build_parser().parse_args(['--config', 'x.toml', '--deepspeed', '--local_rank', '3', '--resume_from_checkpoint',
+                                     '--reset_dataloader', '--master_port', '29999', '--i_know_what_i_am_doing'])
+    assert a.config == 'x.toml' and a.local_rank == 3 and a.resume_from_checkpoint is True and a.master_port == 29999
+    a = T.build_parser().parse_args(['--config', 'x.toml', '--resume_from_checkpoint', '20250101_00-00-00'])
+    assert a.resume_from_checkpoint == '20250101_00-00-00'
+
+
+def test_config_defaults_and_batch_tables():
+    cfg = T.load_toml(os.path.join(ROOT, 'examples', 'flux_synthetic.toml'))
+    cfg = T.set_config_defaults(cfg)
+    assert cfg['pipeline_stages'] == 1 and cfg['model']['dtype'] is torch.bfloat16 and cfg['model']['guidance'] == 1.0
+    assert cfg['eval_before_first_step'] is True and cfg['logging_steps'] == 1 and cfg['warmup_steps'] == 2
+    ds, mbs = T.make_ds_config(cfg)
+    assert ds == {'train_micro_batch_size_per_gpu': 1, 'gradient_accumulation_steps': 4, 'gradient_clipping': 1.0,
+                  'steps_per_print': 1}
+    assert T.batch_size_table([[512, 4], [1024, 1]], {None: 1}) == {512: 4, 1024: 1}
+    assert T.batch_size_table(None, {None: 3}) == {None: 3}
+    with pytest.raises(AssertionError):
+        T.set_config_defaults({'model': {'dtype': 'bfloat16'}})          # save_every_n_* is mandatory (train.py:95)
+    with pytest.raises(NotImplementedError):
+        T.set_config_defaults({'save_every_n_epochs': 1, 'model': {'dtype': 'bfloat16'}, 'adapter': {'type': 'lora', 'rank': 8}})
+
+
+@pytest.mark.gpu
+def test_train_two_steps_save_and_resume(tmp_path):
+    tcfg = {'num_attention_heads': 2, 'num_layers': 1, 'num_single_layers': 1, 'joint_attention_dim': 64,
+            'pooled_projection_dim': 32}
+    ds = tmp_path / 'ds.toml'
+    ds.write_text("[synthetic]\nnum_examples = 8\nresolution = 128\ntext_len = 32\nt5_dim = 64\nclip_dim = 32\n")
+    cfgp = tmp_path / 'cfg.toml'
+    cfgp.write_text(f"""
+output_dir = '{tmp_path}/runs'
+dataset = '{ds}'
+epochs = 1
+micro_batch_size_per_gpu = 1
+gradient_accumulation_steps = 2
+save_every_n_steps = 2
+max_steps = 2
+eval_before_first_step = false
+[model]
+type = 'flux'
+dtype = 'bfloat16'
+transformer_config = {{ num_attention_heads = 2, num_layers = 1, num_single_layers = 1, joint_attention_dim = 64, pooled_projection_dim = 32 }}
+[optimizer]
+type = 'adamw'
+lr = 1e-4
+betas = [0.9, 0.99]
+""")
+    run_dir = T.main(['--config', str(cfgp)])
+    lines = [json.loads(l) for l in open(os.path.join(run_dir, 'metrics.jsonl'))]
+    losses = [l['value'] for l in lines if l['tag'] == 'train/loss']
+    assert len(losses) == 2 and all(v == v and v < 100 for v in losses)
+    assert os.path.exists(os.path.join(run_dir, 'latest'))
+    # resume: continues at step 3 and stops immediately at max_steps... raise the limit to run one more
+    cfgp.write_text(cfgp.read_text().replace('max_steps = 2', 'max_steps = 3'))
+    run_dir2 = T.main(['--config', str(cfgp), '--resume_from_checkpoint'])
+    assert run_dir2 == run_dir
+    lines = [json.loads(l) for l in open(os.path.join(run_dir, 'metrics.jsonl'))]
+    assert [l['x'] for l in lines if l['tag'] == 'train/loss'] == [1, 2, 3]

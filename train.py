@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""train.py — the reference's training driver surface (train.py:41-143, 276-974) over the B200-native engine.
+
+    torchrun --nproc-per-node N train.py --config examples/flux_synthetic.toml        (or `deepspeed --num_gpus=N train.py --deepspeed --config ...`)
+
+Same CLI flags and TOML keys as the reference for everything on the hot path: the model table,
+`pipeline_stages`, `micro_batch_size_per_gpu` (int or [[res, bs], ...]), `gradient_accumulation_steps`,
+`gradient_clipping`, `partition_method` / `partition_split`, `[optimizer]` (type adamw / adamw_optimi-style kwargs,
+`betas`, `weight_decay`, `eps`, `lr`), `lr_scheduler`, `warmup_steps`, `epochs`, `max_steps`, `save_every_n_*`,
+`checkpoint_every_n_minutes`, `--resume_from_checkpoint`, `--reset_dataloader`, `--reset_optimizer`.
+
+What is deliberately NOT here (out of the hot path): VAE / text-encoder caching of a raw image
+folder.  The `dataset` TOML therefore points at already-cached examples:
+    [[directory]]   path = "/data/cache.pt"     # torch.save(list of dicts: latents [16,h,w], t5_embed [512,4096], clip_embed [768], mask|None)
+or  [synthetic]     num_examples = 64, resolution = 1024      # random latents / embeddings of the named shape
+"""
+import argparse
+import glob
+import json
+import os
+import random
+import time
+from datetime import datetime, timezone
+
+import torch
+
+try:
+    import toml
+except ImportError:  # pragma: no cover
+    toml = None
+    import tomllib
+
+from diffusion_pipe_b200 import data_feed
+from diffusion_pipe_b200.pipe import ManualPipelineModule, dist, initialize
+
+TIMESTEP_QUANTILES_FOR_EVAL = [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9]
+DTYPE_MAP = {'float32': torch.float32, 'float16': torch.float16, 'bfloat16': torch.bfloat16,
+             'float8': torch.float8_e4m3fn, 'float8_e4m3fn': torch.float8_e4m3fn, 'float8_e5m2': torch.float8_e5m2}
+
+
+def build_parser():
+    p = argparse.ArgumentParser()
+    p.add_argument('--config', help='Path to TOML configuration file.')
+    p.add_argument('--local_rank', type=int, default=-1, help='local rank passed from distributed launcher')
+    p.add_argument('--resume_from_checkpoint', nargs='?', const=True, default=None)
+    p.add_argument('--reset_dataloader', action='store_true')
+    p.add_argument('--reset_optimizer', action='store_true')
+    p.add_argument('--reset_optimizer_params', action='store_true')
+    p.add_argument('--regenerate_cache', action='store_true')
+    p.add_argument('--cache_only', action='store_true')
+    p.add_argument('--trust_cache', action='store_true')
+    p.add_argument('--i_know_what_i_am_doing', action='store_true')
+    p.add_argument('--master_port', type=int, default=29500)
+    p.add_argument('--dump_dataset', default=None)
+    p.add_argument('--test_sample', action='store_true')
+    # accepted and ignored: the reference adds these through deepspeed.add_config_arguments (train.py:57)
+    p.add_argument('--deepspeed', action='store_true')
+    p.add_argument('--deepspeed_config', default=None)
+    return p
+
+
+def load_toml(path):
+    if toml is not None:
+        with open(path) as f:
+            return json.loads(json.dumps(toml.load(f)))
+    with open(path, 'rb') as f:
+        return json.loads(json.dumps(tomllib.load(f)))
+
+
+def set_config_defaults(config):
+    """train.py:93-143."""
+    assert 'save_every_n_epochs' in config or 'save_every_n_steps' in config or 'save_every_n_examples' in config
+    config.setdefault('pipeline_stages', 1)
+    config.setdefault('activation_checkpointing', False)
+    config.setdefault('reentrant_activation_checkpointing', False)
+    if config['activation_checkpointing'] == 'unsloth':
+        config['reentrant_activation_checkpointing'] = True
+    config.setdefault('warmup_steps', 0)
+    if 'save_dtype' in config:
+        config['save_dtype'] = DTYPE_MAP[config['save_dtype']]
+    mc = config['model']
+    mc['dtype'] = DTYPE_MAP[mc['dtype']]
+    for k in ('transformer_dtype', 'diffusion_model_dtype'):
+        if v := mc.get(k, None):
+            mc[k] = DTYPE_MAP[v]
+    mc.setdefault('guidance', 1.0)
+    if 'adapter' in config:
+        raise NotImplementedError('LoRA / LoKr adapters are not built for the sm_100a path yet (SURVEY.md 8f item 3): '
+                                  'remove the [adapter] table for full fine-tuning')
+    config.setdefault('logging_steps', 1)
+    config.setdefault('eval_datasets', [])
+    config.setdefault('eval_gradient_accumulation_steps', 1)
+    config.setdefault('eval_every_n_steps', None)
+    config.setdefault('eval_every_n_epochs', None)
+    config.setdefault('eval_every_n_examples', None)
+    config.setdefault('eval_before_first_step', True)
+    config.setdefault('compile', False)
+    config.setdefault('x_axis_examples', False)
+    return config
+
+
+def batch_size_table(v, default):
+    """int | [[res, bs], ...] -> {None: bs} | {res: bs}   (train.py:396-418)."""
+    if v is None:
+        return dict(default)
+    if isinstance(v, int):
+        return {None: v}
+    return {x[0]: x[1] for x in v}
+
+
+def make_ds_config(config):
+    mbs = batch_size_table(config.get('micro_batch_size_per_gpu', 1), {None: 1})
+    gradient_release = config['optimizer'].get('gradient_release', False)
+    return {
+        'train_micro_batch_size_per_gpu': list(mbs.values())[0],
+        'gradient_accumulation_steps': config.get('gradient_accumulation_steps', 1),
+        'gradient_clipping': 0. if gradient_release else config.get('gradient_clipping', 1.0),
+        'steps_per_print': config.get('steps_per_print', 1),
+    }, mbs
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# cached-example datasets
+# ---------------------------------------------------------------------------------------------------------------------
+class CachedExamples:
+    """One size bucket of already-encoded examples (what utils/cache.py + utils/dataset.py hand to the hot path)."""
+
+    def __init__(self, examples, size_bucket, num_repeats=1):
+        self.examples, self.size_bucket, self.num_repeats = examples, tuple(size_bucket), num_repeats
+
+    def __len__(self):
+        return int(len(self.examples) * self.num_repeats)
+
+    def __getitem__(self, idx):
+        ex = dict(self.examples[idx % len(self.examples)])
+        ex.setdefault('mask', None)
+        ex.setdefault('caption', '')
+        return ex
+
+
+def load_size_buckets(dataset_config):
+    out = []
+    if syn := dataset_config.get('synthetic', None):
+        n, res = syn.get('num_examples', 16), syn.get('resolution', 1024)
+        g = torch.Generator().manual_seed(syn.get('seed', 0))
+        exs = [{'latents': torch.randn(16, res // 8, res // 8, generator=g),
+                't5_embed': torch.randn(syn.get('text_len', 512), syn.get('t5_dim', 4096), generator=g).bfloat16(),
+                'clip_embed': torch.randn(syn.get('clip_dim', 768), generator=g).bfloat16(), 'mask': None}
+               for _ in range(n)]
+        out.append(CachedExamples(exs, (1.0, res, res, 1), syn.get('num_repeats', 1)))
+    for d in dataset_config.get('directory', []):
+        exs = torch.load(d['path'], map_location='cpu', weights_only=False)
+        by_shape = {}
+        for ex in exs:
+            c, h, w = ex['latents'].shape[-3:]
+            by_shape.setdefault((round(w / h, 3), w * 8, h * 8, 1), []).append(ex)
+        for sb, lst in by_shape.items():
+            out.append(CachedExamples(lst, sb, d.get('num_repeats', 1)))
+    if not out:
+        raise RuntimeError('dataset config has neither [synthetic] nor [[directory]] entries')
+    return out
+
+
+def get_most_recent_run_dir(output_dir):
+    return list(sorted(glob.glob(os.path.join(output_dir, '*'))))[-1]
+
+
+def make_optimizer_factory(config, model):
+    """train.py:650-815 for the torch-native optimizers; weight-decay / no-weight-decay split as in :789-813."""
+    def factory(params):
+        if len(params) == 0:
+            return None
+        oc = dict(config['optimizer'])
+        typ = oc.pop('type').lower()
+        oc.pop('gradient_release', None)
+        if half_life := oc.pop('beta2_half_life', None):
+            b = oc['betas']
+            oc['betas'] = [b[0], 0.5 ** (1 / half_life)]
+        if 'betas' in oc:
+            oc['betas'] = tuple(oc['betas'])
+        groups = []
+        for pg in model.get_param_groups(params):
+            ps = pg.pop('params')
+            wd = [p for p in ps if p.ndim != 1]
+            nowd = [p for p in ps if p.ndim == 1]
+            if wd:
+                groups.append(dict(pg, params=wd))
+            if nowd:
+                groups.append(dict(pg, params=nowd, weight_decay=0))
+        if typ in ('adamw', 'adamw_optimi', 'stableadamw'):
+            return torch.optim.AdamW(groups, fused=torch.cuda.is_available(), **oc)
+        if typ == 'sgd':
+            return torch.optim.SGD(groups, **oc)
+        raise NotImplementedError(f'optimizer type {typ} is not wired into this driver (third-party optimizers are out of '
+                                  'the hot path: pass any torch.optim.Optimizer factory to engine._configure_optimizer)')
+    return factory
+
+
+def evaluate(model_engine, eval_dataloaders, step, egas, log):
+    if not eval_dataloaders:
+        return
+    from diffusion_pipe_b200.data_feed import get_data_iterator_for_step
+    cpu_state, cuda_state = torch.get_rng_state(), torch.cuda.get_rng_state() if torch.cuda.is_available() else None
+    py_state = random.getstate()
+    seed = dist.get_rank()
+    random.seed(seed)
+    torch.manual_seed(seed)
+    start = time.time()
+    with torch.no_grad():
+        for name, dl in eval_dataloaders.items():
+            losses = []
+            for q in TIMESTEP_QUANTILES_FOR_EVAL:
+                dl.set_eval_quantile(q)
+                total, count = 0.0, 0
+                while True:
+                    model_engine.reset_activation_shape()
+                    it = get_data_iterator_for_step(dl, model_engine, num_micro_batches=egas)
+                    total += model_engine.eval_batch(it, num_micro_batches=egas).item()
+                    dl.sync_epoch()
+                    count += 1
+                    if dl.epoch == 2:
+                        break
+                dl.reset()
+                losses.append(total / count)
+                log(f'{name}/loss_quantile_{q:.2f}', losses[-1], step)
+            log(f'{name}/loss', sum(losses) / len(losses), step)
+    log('eval/eval_time_sec', time.time() - start, step)
+    torch.set_rng_state(cpu_state)
+    if cuda_state is not None:
+        torch.cuda.set_rng_state(cuda_state)
+    random.setstate(py_state)
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    config = set_config_defaults(load_toml(args.config))
+    world_size = int(os.getenv('WORLD_SIZE', '1'))
+    local_rank = args.local_rank if args.local_rank >= 0 else int(os.getenv('LOCAL_RANK', '0'))
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    os.environ.setdefault('MASTER_PORT', str(args.master_port))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_distributed()
+    is_main = dist.get_rank() == 0
+
+    model_type = config['model']['type']
+    if model_type != 'flux':
+        raise NotImplementedError(f"model type '{model_type}': only 'flux' has an sm_100a path in this round "
+                                  '(SURVEY.md section 8: Wan / Qwen-Image are the next rows)')
+    from diffusion_pipe_b200 import flux
+    model = flux.FluxPipeline(config)
+
+    dataset_config = load_toml(config['dataset'])
+    ds_config, micro_batch_size_per_gpu = make_ds_config(config)
+    image_mbs = batch_size_table(config.get('image_micro_batch_size_per_gpu'), micro_batch_size_per_gpu)
+    eval_mbs = batch_size_table(config.get('eval_micro_batch_size_per_gpu'), micro_batch_size_per_gpu)
+    eval_image_mbs = batch_size_table(config.get('eval_image_micro_batch_size_per_gpu'), eval_mbs)
+    train_data = data_feed.BatchedDataset(load_size_buckets(dataset_config), dataset_config)
+    eval_data_map = {}
+    for i, ed in enumerate(config['eval_datasets']):
+        name = ed['name'] if isinstance(ed, dict) else f'eval{i}'
+        path = ed['config'] if isinstance(ed, dict) else ed
+        ecfg = load_toml(path)
+        eval_data_map[name] = data_feed.BatchedDataset(load_size_buckets(ecfg), ecfg)
+
+    # run directory (train.py:537-559)
+    resume = args.resume_from_checkpoint if args.resume_from_checkpoint is not None else config.get('resume_from_checkpoint', False)
+    if resume is True:
+        run_dir = get_most_recent_run_dir(config['output_dir'])
+    elif isinstance(resume, str):
+        run_dir = os.path.join(config['output_dir'], resume)
+    else:
+        run_dir = os.path.join(config['output_dir'], datetime.now(timezone.utc).strftime('%Y%m%d_%H-%M-%S'))
+        if is_main:
+            os.makedirs(run_dir, exist_ok=True)
+            with open(os.path.join(run_dir, os.path.basename(args.config)), 'w') as f, open(args.config) as src:
+                f.write(src.read())
+    if world_size > 1:
+        holder = [run_dir]
+        dist.broadcast_object_list(holder, src=0)
+        run_dir = holder[0]
+
+    layers = model.to_layers()
+    extra = {}
+    if config['activation_checkpointing']:
+        from functools import partial
+        extra = {'activation_checkpoint_interval': 1, 'checkpointable_layers': model.checkpointable_layers,
+                 'activation_checkpoint_func': partial(torch.utils.checkpoint.checkpoint,
+                                                       use_reentrant=config['reentrant_activation_checkpointing'])}
+    num_stages = config.get('pipeline_stages', 1)
+    pipeline_model = ManualPipelineModule(
+        layers=layers, num_stages=num_stages, partition_method=config.get('partition_method', 'parameters'),
+        manual_partition_split=config.get('partition_split', None), loss_fn=model.get_loss_fn(), dynamic_shape=True, **extra)
+    model.pipeline_model = pipeline_model
+    parameters_to_train = [p for p in pipeline_model.parameters() if p.requires_grad]
+    model_engine, optimizer, _, _ = initialize(args=args, model=pipeline_model, config=ds_config)
+    global_batch_size = (model_engine.train_micro_batch_size_per_gpu() * model_engine.gradient_accumulation_steps()
+                         * model_engine.grid.get_data_parallel_world_size())
+    if is_main:
+        print(f'Global batch size = {global_batch_size}')
+    if n := config.pop('save_every_n_examples', None):
+        config['save_every_n_steps'] = n // global_batch_size
+    if n := config.pop('eval_every_n_examples', None):
+        config['eval_every_n_steps'] = n // global_batch_size
+
+    model_engine._configure_optimizer(make_optimizer_factory(config, model), parameters_to_train)
+    optimizer = model_engine.optimizer
+    model.model_engine = model_engine
+    grid = model_engine.grid
+    train_data.post_init(grid.get_data_parallel_rank(), grid.get_data_parallel_world_size(), micro_batch_size_per_gpu,
+                         model_engine.gradient_accumulation_steps(), image_mbs)
+    for ed in eval_data_map.values():
+        ed.post_init(grid.get_data_parallel_rank(), grid.get_data_parallel_world_size(), eval_mbs,
+                     config['eval_gradient_accumulation_steps'], eval_image_mbs)
+    model_engine.communication_data_type = config['model']['dtype']
+    train_dataloader = data_feed.PipelineDataLoader(train_data, model_engine, model_engine.gradient_accumulation_steps(), model,
+                                                    num_dataloader_workers=config.get('num_dataloader_workers', 0))
+    steps_per_epoch = len(train_dataloader) // model_engine.gradient_accumulation_steps()
+
+    if optimizer is not None:
+        st = config.get('lr_scheduler', 'constant')
+        total = config.get('epochs', 1) * steps_per_epoch
+        if st == 'constant':
+            sched = torch.optim.lr_scheduler.ConstantLR(optimizer, factor=1.0)
+        elif st == 'linear':
+            sched = torch.optim.lr_scheduler.LinearLR(optimizer, start_factor=1.0, end_factor=0.0, total_iters=total)
+        elif st == 'cosine':
+            sched = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=total, eta_min=1e-6)
+        else:
+            raise NotImplementedError(f'Unknown lr_scheduler: {st}')
+        if config['warmup_steps'] > 0:
+            w = config['warmup_steps']
+            warm = torch.optim.lr_scheduler.LinearLR(optimizer, start_factor=1 / w, total_iters=w)
+            sched = torch.optim.lr_scheduler.SequentialLR(optimizer, schedulers=[warm, sched], milestones=[w])
+        model_engine.lr_scheduler = sched
+
+    step, examples = 1, global_batch_size
+    if resume:
+        load_path, client_state = model_engine.load_checkpoint(
+            run_dir, load_module_strict=False,
+            load_lr_scheduler_states='force_constant_lr' not in config and not args.reset_optimizer and not args.reset_optimizer_params,
+            load_optimizer_states=not args.reset_optimizer)
+        assert load_path is not None
+        if args.reset_dataloader:
+            train_dataloader.epoch = client_state['custom_loader']['epoch']
+        else:
+            train_dataloader.load_state_dict(client_state['custom_loader'])
+        step = client_state['step'] + 1
+        examples = client_state.get('examples', step * global_batch_size - global_batch_size) + global_batch_size
+        if is_main:
+            print(f'Resuming training from checkpoint. Resuming at epoch: {train_dataloader.epoch}, step: {step}')
+    if 'force_constant_lr' in config and optimizer is not None:
+        model_engine.lr_scheduler = torch.optim.lr_scheduler.ConstantLR(optimizer, factor=1.0)
+        for pg in optimizer.param_groups:
+            pg['lr'] = config['force_constant_lr']
+
+    eval_dataloaders = {name: data_feed.PipelineDataLoader(ed, model_engine, config['eval_gradient_accumulation_steps'], model,
+                                                           num_dataloader_workers=0) for name, ed in eval_data_map.items()}
+    metrics = []
+
+    def log(tag, value, x):
+        if is_main:
+            metrics.append({'tag': tag, 'value': float(value), 'x': x})
+            with open(os.path.join(run_dir, 'metrics.jsonl'), 'a') as f:
+                f.write(json.dumps(metrics[-1]) + '\n')
+
+    def save_checkpoint(step, examples):
+        model_engine.save_checkpoint(run_dir, client_state={'step': step, 'examples': examples,
+                                                            'custom_loader': train_dataloader.state_dict()},
+                                     save_latest=True, exclude_frozen_parameters=True)
+
+    if config['eval_before_first_step'] and not resume:
+        evaluate(model_engine, eval_dataloaders, 0, config['eval_gradient_accumulation_steps'], log)
+
+    epoch = train_dataloader.epoch
+    epoch_loss, num_steps = 0.0, 0
+    last_checkpoint_time = time.time()
+    while True:
+        model_engine.reset_activation_shape()
+        iterator = data_feed.get_data_iterator_for_step(train_dataloader, model_engine)
+        loss = model_engine.train_batch(iterator).item()
+        epoch_loss += loss
+        num_steps += 1
+        train_dataloader.sync_epoch()
+        new_epoch = train_dataloader.epoch
+        finished_epoch = new_epoch != epoch
+        x_axis = examples if config['x_axis_examples'] else step
+        if step % config['logging_steps'] == 0:
+            log('train/loss', loss, x_axis)
+            if model_engine._grad_norm is not None:
+                log('train/grad_norm', float(model_engine._grad_norm), x_axis)
+        checkpointed = False
+        if (config['eval_every_n_steps'] and step % config['eval_every_n_steps'] == 0) or \
+                (finished_epoch and config['eval_every_n_epochs'] and epoch % config['eval_every_n_epochs'] == 0):
+            evaluate(model_engine, eval_dataloaders, x_axis, config['eval_gradient_accumulation_steps'], log)
+        if finished_epoch:
+            log('train/epoch_loss', epoch_loss / num_steps, epoch)
+            epoch_loss, num_steps = 0.0, 0
+            if ce := config.get('checkpoint_every_n_epochs', None):
+                if epoch % ce == 0:
+                    save_checkpoint(step, examples)
+                    checkpointed = True
+            if new_epoch > config.get('epochs', 1 << 30):
+                break
+            epoch = new_epoch
+        if (n := config.get('save_every_n_steps', None)) and step % n == 0:
+            save_checkpoint(step, examples)
+            checkpointed = True
+        if (m := config.get('checkpoint_every_n_minutes', None)) and time.time() - last_checkpoint_time > m * 60:
+            save_checkpoint(step, examples)
+            checkpointed = True
+            last_checkpoint_time = time.time()
+        if 'max_steps' in config and step >= config['max_steps']:
+            break
+        step += 1
+        examples += global_batch_size
+    if not checkpointed:
+        save_checkpoint(step, examples)
+    if is_main:
+        print('TRAINING COMPLETE!')
+    return run_dir
+
+
+if __name__ == '__main__':
+    main()
