@@ -19,6 +19,8 @@
 //
 // LSE is the log2-domain logsumexp written by attn_fwd.  Outputs dQ/dK/dV are head-major [B,H,L,128] bf16.
 // Replaces flash-attn / SDPA backward reached through autograd from models/flux.py:502,525.
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "sm100_common.cuh"
 
@@ -492,6 +494,396 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
   if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 
+// =============================================================================================
+// v2: software-pipelined variants.  The 128-wide score tile is processed as two 64-wide sub-tiles with double-buffered
+// S / dP accumulators in TMEM, so the tensor core computes the scores of sub-tile t+1 while the softmax warps turn
+// sub-tile t into P / dS, and the dV / dK (or dQ) MMAs of sub-tile t run while the softmax warps are already on t+1.
+//   dkv TMEM: St[2] 2x64 | dPt[2] 2x64 | dV 128 | dK 128          dq TMEM: S[2] 2x64 | dP[2] 2x64 | dQ 128
+// bf16 P / dS for the 32 columns a warp owns are written over the first 16 of those same columns.
+// =============================================================================================
+__device__ __forceinline__ uint32_t packed_col64(int kstep) { return (kstep >> 1) * 32 + (kstep & 1) * 8; }
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                     const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do,
+                     const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* k_smem = smem;
+  uint8_t* v_smem = smem + BTILE;
+  uint8_t* q_smem = smem + 2 * BTILE;   // 2 stages of [128 q][128 d]
+  uint8_t* do_smem = smem + 4 * BTILE;  // 2 stages
+  float* lse_smem = reinterpret_cast<float*>(smem + 6 * BTILE);  // [2][128]
+  float* dl_smem = lse_smem + 256;                               // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * BTILE + 4 * 512);
+  uint64_t* kv_full = bars;        // [1]
+  uint64_t* q_full = bars + 1;     // [2]
+  uint64_t* q_empty = bars + 3;    // [2]
+  uint64_t* do_full = bars + 5;    // [2]
+  uint64_t* do_empty = bars + 7;   // [2]
+  uint64_t* sd_full = bars + 9;    // [2] MMA -> softmax: St and dPt of buffer b complete
+  uint64_t* p_ready = bars + 11;   // [2] softmax -> MMA (8 warps)
+  uint64_t* ds_ready = bars + 13;  // [2] softmax -> MMA (8 warps)
+  uint64_t* acc_done = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const uint32_t warp = warp_id_uniform();
+  const uint32_t lane = lane_id();
+  const int kv0 = blockIdx.x * BT;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int bh = b * p.heads + head;
+  const int nq = (p.seq_q + BT - 1) / BT;   // 128-row query tiles
+  const int nsub = 2 * nq;                  // 64-row sub-tiles (the last one may be entirely out of range: harmless)
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tma_q); tma_prefetch_desc(&tma_k); tma_prefetch_desc(&tma_v); tma_prefetch_desc(&tma_do);
+  }
+  if (warp == 1 && elect_one()) {
+    mbar_init(smem_u32(kv_full), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&q_full[s]), 1); mbar_init(smem_u32(&q_empty[s]), 1);
+      mbar_init(smem_u32(&do_full[s]), 1); mbar_init(smem_u32(&do_empty[s]), 1);
+      mbar_init(smem_u32(&sd_full[s]), 1);
+      mbar_init(smem_u32(&p_ready[s]), 8); mbar_init(smem_u32(&ds_ready[s]), 8);
+    }
+    mbar_init(smem_u32(acc_done), 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<1>(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t T_ST = tmem_base, T_DPT = tmem_base + 128, T_DV = tmem_base + 256, T_DK = tmem_base + 384;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t kvb = smem_u32(kv_full);
+      mbar_expect_tx(kvb, 2 * BTILE);
+      for (int h = 0; h < 2; ++h) {
+        tma_load_3d(&tma_k, kvb, smem_u32(k_smem + h * BHALF), h * 64, kv0, bh, kEvictFirst);
+        tma_load_3d(&tma_v, kvb, smem_u32(v_smem + h * BHALF), h * 64, kv0, bh, kEvictFirst);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nq; ++j) {
+        const int q0 = j * BT;
+        mbar_wait(smem_u32(&q_empty[stage]), phase ^ 1);
+        const uint32_t qb = smem_u32(&q_full[stage]);
+        mbar_expect_tx(qb, BTILE);
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(&tma_q, qb, smem_u32(q_smem + stage * BTILE + h * BHALF), h * 64, q0, bh, kEvictLast);
+        mbar_wait(smem_u32(&do_empty[stage]), phase ^ 1);
+        const uint32_t db = smem_u32(&do_full[stage]);
+        mbar_expect_tx(db, BTILE);
+        for (int h = 0; h < 2; ++h)
+          tma_load_4d(&tma_do, db, smem_u32(do_smem + stage * BTILE + h * BHALF), h * 64, q0, head, b, kEvictLast);
+        if (++stage == 2) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(BT, 64, false, false);   // [128 kv] x [64 q]
+      constexpr uint32_t idesc_g = make_idesc_bf16(BT, 128, false, true);   // [128 kv] x [128 d], K = 64 queries
+      mbar_wait(smem_u32(kv_full), 0);
+      const uint32_t kb = smem_u32(k_smem), vb = smem_u32(v_smem);
+      // scores of sub-tile t: 64 query rows starting at row 64*(t&1) of query tile t>>1
+      auto issue_scores = [&](int t) {
+        const int j = t >> 1, stage = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        if ((t & 1) == 0) { mbar_wait(smem_u32(&q_full[stage]), ph); mbar_wait(smem_u32(&do_full[stage]), ph); }
+        tc_fence_after();
+        const uint32_t qb = smem_u32(q_smem + stage * BTILE) + (t & 1) * 8192;
+        const uint32_t dob = smem_u32(do_smem + stage * BTILE) + (t & 1) * 8192;
+        const uint32_t buf = t & 1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss<1>(T_ST + buf * 64, make_smem_desc(kb + kmajor_off(k), 16, 1024), make_smem_desc(qb + kmajor_off(k), 16, 1024),
+                     idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss<1>(T_DPT + buf * 64, make_smem_desc(vb + kmajor_off(k), 16, 1024), make_smem_desc(dob + kmajor_off(k), 16, 1024),
+                     idesc_s, k != 0);
+        umma_commit<1>(smem_u32(&sd_full[buf]));
+      };
+      issue_scores(0);
+      for (int t = 0; t < nsub; ++t) {
+        if (t + 1 < nsub) issue_scores(t + 1);
+        const int j = t >> 1, stage = j & 1;
+        const uint32_t buf = t & 1, rph = (t >> 1) & 1;
+        const uint32_t qb = smem_u32(q_smem + stage * BTILE) + (t & 1) * 8192;
+        const uint32_t dob = smem_u32(do_smem + stage * BTILE) + (t & 1) * 8192;
+        mbar_wait(smem_u32(&p_ready[buf]), rph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // dV[kv, d] += Pt[kv, 64 q] dO[64 q, d]
+          umma_ts(T_DV, T_ST + buf * 64 + packed_col64(k), make_smem_desc(dob + k * 2048, BHALF, 1024), idesc_g, (t | k) != 0);
+        if (t & 1) umma_commit<1>(smem_u32(&do_empty[stage]));
+        mbar_wait(smem_u32(&ds_ready[buf]), rph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // dK[kv, d] += dSt[kv, 64 q] Q[64 q, d]
+          umma_ts(T_DK, T_DPT + buf * 64 + packed_col64(k), make_smem_desc(qb + k * 2048, BHALF, 1024), idesc_g, (t | k) != 0);
+        if (t & 1) umma_commit<1>(smem_u32(&q_empty[stage]));
+      }
+      umma_commit<1>(smem_u32(acc_done));
+    }
+  } else if (warp >= 4) {
+    const uint32_t quad = warp & 3;
+    const int half = (warp - 4) >> 2;          // which 32 of the 64 sub-tile columns this warp owns
+    const int sm_tid = (warp - 4) * 32 + lane;
+    const uint32_t lane_base = (quad * 32u) << 16;
+    const float c = p.scale_log2;
+    for (int t = 0; t < nsub; ++t) {
+      const int j = t >> 1, st = j & 1;
+      const uint32_t buf = t & 1, rph = (t >> 1) & 1;
+      if ((t & 1) == 0) {   // stage LSE / D of the 128-row query tile (invalid queries: +inf -> P = 0)
+        const int tt = sm_tid & 127;
+        const int q = j * BT + tt;
+        if (sm_tid < 128) lse_smem[st * 128 + tt] = (q < p.seq_q) ? p.lse[(int64_t)bh * p.seq_q + q] : INFINITY;
+        else dl_smem[st * 128 + tt] = (q < p.seq_q) ? p.delta[(int64_t)bh * p.seq_q + q] : 0.f;
+        named_bar_sync(1, 256);
+      }
+      const float* lse_s = lse_smem + st * 128 + (t & 1) * 64 + half * 32;
+      const float* dl_s = dl_smem + st * 128 + (t & 1) * 64 + half * 32;
+      mbar_wait(smem_u32(&sd_full[buf]), rph);
+      tc_fence_after();
+      uint32_t r[32], pk[16];
+      float pv[32];
+      tmem_ld_x32(T_ST + lane_base + buf * 64 + half * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int x = 0; x < 32; x += 2) {
+        pv[x] = fast_exp2(fmaf(__uint_as_float(r[x]), c, -lse_s[x]));
+        pv[x + 1] = fast_exp2(fmaf(__uint_as_float(r[x + 1]), c, -lse_s[x + 1]));
+        pk[x >> 1] = pack_bf16(pv[x], pv[x + 1]);
+      }
+      tmem_st_x16(T_ST + lane_base + buf * 64 + half * 32, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&p_ready[buf]));
+      tmem_ld_x32(T_DPT + lane_base + buf * 64 + half * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int x = 0; x < 32; x += 2)
+        pk[x >> 1] = pack_bf16(pv[x] * (__uint_as_float(r[x]) - dl_s[x]), pv[x + 1] * (__uint_as_float(r[x + 1]) - dl_s[x + 1]));
+      tmem_st_x16(T_DPT + lane_base + buf * 64 + half * 32, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ds_ready[buf]));
+    }
+    mbar_wait(smem_u32(acc_done), 0);
+    tc_fence_after();
+    const int kv = kv0 + quad * 32 + lane;
+    const bool ok = kv < p.seq_k;
+    const int chalf = (warp - 4) >> 2;
+    const int64_t o = ((int64_t)bh * p.seq_k + kv) * 128 + chalf * 64;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t tt = (which == 0 ? T_DV : T_DK) + lane_base + chalf * 64;
+      __nv_bfloat16* dst = (which == 0 ? p.dv : p.dk) + o;
+      const float mul = which == 0 ? 1.0f : p.scale;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t rr[32];
+        tmem_ld_x32(tt + cc * 32, rr);
+        tmem_ld_wait();
+        if (ok) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + cc * 32);
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            uint4 qv;
+            qv.x = pack_bf16(__uint_as_float(rr[x * 8 + 0]) * mul, __uint_as_float(rr[x * 8 + 1]) * mul);
+            qv.y = pack_bf16(__uint_as_float(rr[x * 8 + 2]) * mul, __uint_as_float(rr[x * 8 + 3]) * mul);
+            qv.z = pack_bf16(__uint_as_float(rr[x * 8 + 4]) * mul, __uint_as_float(rr[x * 8 + 5]) * mul);
+            qv.w = pack_bf16(__uint_as_float(rr[x * 8 + 6]) * mul, __uint_as_float(rr[x * 8 + 7]) * mul);
+            d4[x] = qv;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                    const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do,
+                    const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* q_smem = smem;
+  uint8_t* do_smem = smem + BTILE;
+  uint8_t* k_smem = smem + 2 * BTILE;  // 2 stages of [128 kv][128 d]
+  uint8_t* v_smem = smem + 4 * BTILE;  // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * BTILE + 4 * 512);
+  uint64_t* qdo_full = bars;       // [1]
+  uint64_t* k_full = bars + 1;     // [2]
+  uint64_t* k_empty = bars + 3;    // [2]
+  uint64_t* v_full = bars + 5;     // [2]
+  uint64_t* v_empty = bars + 7;    // [2]
+  uint64_t* sd_full = bars + 9;    // [2]
+  uint64_t* ds_ready = bars + 11;  // [2] (8 warps)
+  uint64_t* acc_done = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const uint32_t warp = warp_id_uniform();
+  const uint32_t lane = lane_id();
+  const int q0 = blockIdx.x * BT;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int bh = b * p.heads + head;
+  const int nkv = (p.seq_k + BT - 1) / BT;
+  const int nsub = 2 * nkv;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tma_q); tma_prefetch_desc(&tma_k); tma_prefetch_desc(&tma_v); tma_prefetch_desc(&tma_do);
+  }
+  if (warp == 1 && elect_one()) {
+    mbar_init(smem_u32(qdo_full), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&k_full[s]), 1); mbar_init(smem_u32(&k_empty[s]), 1);
+      mbar_init(smem_u32(&v_full[s]), 1); mbar_init(smem_u32(&v_empty[s]), 1);
+      mbar_init(smem_u32(&sd_full[s]), 1);
+      mbar_init(smem_u32(&ds_ready[s]), 8);
+    }
+    mbar_init(smem_u32(acc_done), 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<1>(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t T_S = tmem_base, T_DP = tmem_base + 128, T_DQ = tmem_base + 256;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t qb = smem_u32(qdo_full);
+      mbar_expect_tx(qb, 2 * BTILE);
+      for (int h = 0; h < 2; ++h) {
+        tma_load_3d(&tma_q, qb, smem_u32(q_smem + h * BHALF), h * 64, q0, bh, kEvictFirst);
+        tma_load_4d(&tma_do, qb, smem_u32(do_smem + h * BHALF), h * 64, q0, head, b, kEvictFirst);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nkv; ++j) {
+        const int kv0 = j * BT;
+        mbar_wait(smem_u32(&k_empty[stage]), phase ^ 1);
+        const uint32_t kb = smem_u32(&k_full[stage]);
+        mbar_expect_tx(kb, BTILE);
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(&tma_k, kb, smem_u32(k_smem + stage * BTILE + h * BHALF), h * 64, kv0, bh, kEvictLast);
+        mbar_wait(smem_u32(&v_empty[stage]), phase ^ 1);
+        const uint32_t vb = smem_u32(&v_full[stage]);
+        mbar_expect_tx(vb, BTILE);
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(&tma_v, vb, smem_u32(v_smem + stage * BTILE + h * BHALF), h * 64, kv0, bh, kEvictLast);
+        if (++stage == 2) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(BT, 64, false, false);   // [128 q] x [64 kv]
+      constexpr uint32_t idesc_g = make_idesc_bf16(BT, 128, false, true);   // [128 q] x [128 d], K = 64 keys
+      const uint32_t qb = smem_u32(q_smem), dob = smem_u32(do_smem);
+      mbar_wait(smem_u32(qdo_full), 0);
+      auto issue_scores = [&](int t) {
+        const int j = t >> 1, stage = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        if ((t & 1) == 0) { mbar_wait(smem_u32(&k_full[stage]), ph); mbar_wait(smem_u32(&v_full[stage]), ph); }
+        tc_fence_after();
+        const uint32_t kb = smem_u32(k_smem + stage * BTILE) + (t & 1) * 8192;
+        const uint32_t vb = smem_u32(v_smem + stage * BTILE) + (t & 1) * 8192;
+        const uint32_t buf = t & 1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss<1>(T_S + buf * 64, make_smem_desc(qb + kmajor_off(k), 16, 1024), make_smem_desc(kb + kmajor_off(k), 16, 1024),
+                     idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss<1>(T_DP + buf * 64, make_smem_desc(dob + kmajor_off(k), 16, 1024), make_smem_desc(vb + kmajor_off(k), 16, 1024),
+                     idesc_s, k != 0);
+        umma_commit<1>(smem_u32(&sd_full[buf]));
+        if (t & 1) umma_commit<1>(smem_u32(&v_empty[stage]));   // V tile fully consumed by the two dP sub-tiles
+      };
+      issue_scores(0);
+      for (int t = 0; t < nsub; ++t) {
+        if (t + 1 < nsub) issue_scores(t + 1);
+        const int j = t >> 1, stage = j & 1;
+        const uint32_t buf = t & 1, rph = (t >> 1) & 1;
+        const uint32_t kb = smem_u32(k_smem + stage * BTILE) + (t & 1) * 8192;
+        mbar_wait(smem_u32(&ds_ready[buf]), rph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // dQ[q, d] += dS[q, 64 kv] K[64 kv, d]
+          umma_ts(T_DQ, T_DP + buf * 64 + packed_col64(k), make_smem_desc(kb + k * 2048, BHALF, 1024), idesc_g, (t | k) != 0);
+        if (t & 1) umma_commit<1>(smem_u32(&k_empty[stage]));
+      }
+      umma_commit<1>(smem_u32(acc_done));
+    }
+  } else if (warp >= 4) {
+    const uint32_t quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const uint32_t lane_base = (quad * 32u) << 16;
+    const int q = q0 + quad * 32 + lane;
+    const bool ok = q < p.seq_q;
+    const float lse = ok ? p.lse[(int64_t)bh * p.seq_q + q] : INFINITY;
+    const float dl = ok ? p.delta[(int64_t)bh * p.seq_q + q] : 0.f;
+    const float c = p.scale_log2;
+    for (int t = 0; t < nsub; ++t) {
+      const uint32_t buf = t & 1, rph = (t >> 1) & 1;
+      const int valid = p.seq_k - t * 64 - half * 32;   // keys of this warp's 32 columns that exist (may be <= 0)
+      mbar_wait(smem_u32(&sd_full[buf]), rph);
+      tc_fence_after();
+      uint32_t r[32], rd[32], pk[16];
+      tmem_ld_x32(T_S + lane_base + buf * 64 + half * 32, r);
+      tmem_ld_x32(T_DP + lane_base + buf * 64 + half * 32, rd);
+      tmem_ld_wait();
+#pragma unroll
+      for (int x = 0; x < 32; x += 2) {
+        float p0 = fast_exp2(fmaf(__uint_as_float(r[x]), c, -lse));
+        float p1 = fast_exp2(fmaf(__uint_as_float(r[x + 1]), c, -lse));
+        if (x >= valid) p0 = 0.f;
+        if (x + 1 >= valid) p1 = 0.f;
+        pk[x >> 1] = pack_bf16(p0 * (__uint_as_float(rd[x]) - dl), p1 * (__uint_as_float(rd[x + 1]) - dl));
+      }
+      tmem_st_x16(T_DP + lane_base + buf * 64 + half * 32, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ds_ready[buf]));
+    }
+    mbar_wait(smem_u32(acc_done), 0);
+    tc_fence_after();
+    __nv_bfloat16* dst = p.dq + ((int64_t)bh * p.seq_q + q) * 128 + half * 64;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      uint32_t rr[32];
+      tmem_ld_x32(T_DQ + lane_base + half * 64 + cc * 32, rr);
+      tmem_ld_wait();
+      if (ok) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + cc * 32);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          uint4 qv;
+          qv.x = pack_bf16(__uint_as_float(rr[x * 8 + 0]) * p.scale, __uint_as_float(rr[x * 8 + 1]) * p.scale);
+          qv.y = pack_bf16(__uint_as_float(rr[x * 8 + 2]) * p.scale, __uint_as_float(rr[x * 8 + 3]) * p.scale);
+          qv.z = pack_bf16(__uint_as_float(rr[x * 8 + 4]) * p.scale, __uint_as_float(rr[x * 8 + 5]) * p.scale);
+          qv.w = pack_bf16(__uint_as_float(rr[x * 8 + 6]) * p.scale, __uint_as_float(rr[x * 8 + 7]) * p.scale);
+          d4[x] = qv;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
 }  // namespace dpipe
 
 extern "C" int dpipe_attn_bwd(const dpipe_attn_bwd_args* a, void* stream) {
@@ -525,6 +917,8 @@ extern "C" int dpipe_attn_bwd(const dpipe_attn_bwd_args* a, void* stream) {
   if (!configured) {
     DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
     DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
+    DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
+    DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
     configured = true;
   }
   AttnBwdParams p;
@@ -534,9 +928,18 @@ extern "C" int dpipe_attn_bwd(const dpipe_attn_bwd_args* a, void* stream) {
   p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv);
   p.batch = B; p.heads = H; p.seq_q = Lq; p.seq_k = Lk;
   p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
-  attn_bwd_dkv_kernel<<<dim3((Lk + BT - 1) / BT, H, B), AB_THREADS, AB_SMEM_BYTES, s>>>(tq, tk, tv, tdo, p);
-  DPIPE_CUDA_CHECK(cudaGetLastError());
-  attn_bwd_dq_kernel<<<dim3((Lq + BT - 1) / BT, H, B), AB_THREADS, AB_SMEM_BYTES, s>>>(tq, tk, tv, tdo, p);
-  DPIPE_CUDA_CHECK(cudaGetLastError());
+  static int variant = -1;   // DPIPE_ATTN_BWD=1 selects the un-pipelined v1 kernels (kept for A/B measurements)
+  if (variant < 0) { const char* e = getenv("DPIPE_ATTN_BWD"); variant = (e && e[0] == '1') ? 1 : 2; }
+  if (variant == 1) {
+    attn_bwd_dkv_kernel<<<dim3((Lk + BT - 1) / BT, H, B), AB_THREADS, AB_SMEM_BYTES, s>>>(tq, tk, tv, tdo, p);
+    DPIPE_CUDA_CHECK(cudaGetLastError());
+    attn_bwd_dq_kernel<<<dim3((Lq + BT - 1) / BT, H, B), AB_THREADS, AB_SMEM_BYTES, s>>>(tq, tk, tv, tdo, p);
+    DPIPE_CUDA_CHECK(cudaGetLastError());
+  } else {
+    attn_bwd_dkv2_kernel<<<dim3((Lk + BT - 1) / BT, H, B), AB_THREADS, AB_SMEM_BYTES, s>>>(tq, tk, tv, tdo, p);
+    DPIPE_CUDA_CHECK(cudaGetLastError());
+    attn_bwd_dq2_kernel<<<dim3((Lq + BT - 1) / BT, H, B), AB_THREADS, AB_SMEM_BYTES, s>>>(tq, tk, tv, tdo, p);
+    DPIPE_CUDA_CHECK(cudaGetLastError());
+  }
   return 0;
 }
