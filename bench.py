@@ -313,13 +313,28 @@ def main():
     roof = None
     if prof:
         torch.cuda.synchronize()
-        tot_ms = sum(s.elapsed_time(e) for s, e, _, _ in prof)
-        tot_fl = sum(f for _, _, f, _ in prof)
-        gemm_ms = sum(s.elapsed_time(e) for s, e, _, k in prof if k == 'gemm')
-        gemm_fl = sum(f for _, _, f, k in prof if k == 'gemm')
-        attn_ms = sum(s.elapsed_time(e) for s, e, _, k in prof if k.startswith('attn'))
-        attn_fl = sum(f for _, _, f, k in prof if k.startswith('attn'))
+        tot_ms = sum(s.elapsed_time(e) for s, e, _, _, _ in prof)
+        tot_fl = sum(f for _, _, f, _, _ in prof)
+        gemm_ms = sum(s.elapsed_time(e) for s, e, _, k, _ in prof if k == 'gemm')
+        gemm_fl = sum(f for _, _, f, k, _ in prof if k == 'gemm')
+        attn_ms = sum(s.elapsed_time(e) for s, e, _, k, _ in prof if k.startswith('attn'))
+        attn_fl = sum(f for _, _, f, k, _ in prof if k.startswith('attn'))
         n_gemm = sum(1 for p in prof if p[3] == 'gemm')
+        by_shape = {}
+        for s_, e_, f_, k_, tag in prof:
+            if k_ == 'gemm':
+                d = by_shape.setdefault(tag, [0, 0.0, 0.0])
+                d[0] += 1
+                d[1] += s_.elapsed_time(e_)
+                d[2] += f_
+        breakdown = [{'MNK_aMN_bMN_epi_acc': list(t), 'n': v[0], 'ms': round(v[1], 2), 'tflops': round(v[2] / v[1] / 1e9, 1)}
+                     for t, v in sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:14]]
+        try:
+            os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+            with open(os.path.join(ROOT, 'gpurun_out', f'bench_gemm_breakdown_rank{rank}.json'), 'w') as f:
+                json.dump(breakdown, f, indent=1)
+        except OSError:
+            pass
         peaks = {}
         try:
             with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:

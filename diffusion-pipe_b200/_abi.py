@@ -80,4 +80,8 @@ SIGNATURES['dpipe_ipc_free'] = (c_int, [c_void_p])
 SIGNATURES['dpipe_peer_copy'] = (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p])
 SIGNATURES['dpipe_flag_write'] = (c_int, [c_void_p, ctypes.c_uint64, c_void_p])
 SIGNATURES['dpipe_flag_wait_geq'] = (c_int, [c_void_p, ctypes.c_uint64, ctypes.c_double, c_void_p])
+SIGNATURES['dpipe_mod_fwd'] = (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p])
+SIGNATURES['dpipe_mod_bwd_chunks'] = (c_int, [c_int])
+SIGNATURES['dpipe_mod_bwd'] = (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                        c_int, c_int, c_int, c_void_p])
 SIGNATURES['dpipe_mse_loss'] =(c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p])

@@ -83,18 +83,17 @@ class AdaLNContinuousFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, temb, lin):
         B, L, D = x.shape
-        s = _silu_bf16(temb)
-        mod = _mod_fwd(s, lin)                                  # [B, 2D]: scale, shift
+        mod = _mod_fwd(temb, lin)                               # [B, 2D]: scale, shift
         x2 = x.reshape(B * L, D)
         xn, mean, rstd = ops.ln_modulate_fwd(x2, mod[:, 0:D], mod[:, D:2 * D], B, L)
         ctx.lin = lin
-        ctx.save_for_backward(x2, temb, s, mod, mean, rstd)
+        ctx.save_for_backward(x2, temb, mod, mean, rstd)
         ctx.dims = (B, L, D)
         return xn.view(B, L, D)
 
     @staticmethod
     def backward(ctx, dxn):
-        x2, temb, s, mod, mean, rstd = ctx.saved_tensors
+        x2, temb, mod, mean, rstd = ctx.saved_tensors
         B, L, D = ctx.dims
         dxn2 = dxn.reshape(B * L, D)
         if dxn2.dtype != torch.bfloat16:
@@ -102,7 +101,8 @@ class AdaLNContinuousFn(torch.autograd.Function):
         dmod = torch.empty((B, 2 * D), dtype=torch.float32, device=x2.device)
         dx, part = ops.ln_modulate_bwd(dxn2.contiguous(), x2, mod[:, 0:D], mean, rstd, B, L)
         ops.colreduce_finish(part, per_sample0=dmod[:, 0:D], per_sample1=dmod[:, D:2 * D])
-        d_temb = _mod_bwd(dmod, s, temb, ctx.lin)
+        d_temb = torch.zeros((B, D), dtype=torch.float32, device=x2.device)
+        _mod_bwd(dmod, temb, ctx.lin, d_temb)
         return dx.view(B, L, D), d_temb.to(temb.dtype), None
 
 
@@ -260,9 +260,9 @@ class OutputWrapper(nn.Module):
 
     def forward(self, inputs):
         hidden_states, encoder_hidden_states, temb, freqs_cos, freqs_sin, img_seq_len = inputs
-        n = int(img_seq_len[0].item())
-        if n != hidden_states.shape[1]:
-            hidden_states = hidden_states[:, :n, ...].contiguous()
+        # The reference slices `hidden_states[:, :img_seq_len[0].item()]` here (models/flux.py:545-546) — a host sync per
+        # micro-batch whose only effect is to drop Kontext control tokens.  The prediction is computed for every token
+        # instead and the loss keeps the first target.shape[1] of them (shape metadata, no device read).
         hidden_states = AdaLNContinuousFn.apply(hidden_states, temb, self.norm_out.linear)
         return linear(hidden_states, self.proj_out)
 
@@ -482,6 +482,8 @@ class FluxPipeline:
                 if mask.numel() > 0:
                     loss = loss * mask.to(o.device, torch.float32)
                 return loss.mean()
+            if output.shape[1] != target.shape[1]:
+                output = output[:, :target.shape[1]]
             m = mask.to(output.device) if mask.numel() > 0 else None
             return MseLossFn.apply(output, target.to(output.device), m)
         return loss_fn

@@ -118,21 +118,19 @@ def _acc_fused_bias(fp, bgrad, acc, g32):
 # =====================================================================================================================
 # modulation linear: mod[B, n*D] = silu(temb) @ W^T + b      (AdaLayerNormZero{,Single}.linear)
 # =====================================================================================================================
-def _mod_fwd(s, lin):
-    return ops.gemm(s, lin.weight, bias=lin.bias, cta_group=1)
+def _mod_fwd(temb, lin):
+    """mod = Linear(SiLU(temb)) on the rank-batch kernel (csrc/modulation.cu)."""
+    return ops.mod_fwd(temb if temb.is_contiguous() else temb.contiguous(), lin.weight, lin.bias)
 
 
-def _mod_bwd(dmod32, s, temb, lin):
-    """dmod32: fp32 [B, n*D] gradient of the modulation vector.  Returns d temb (fp32 [B, D])."""
-    dmod = dmod32.to(torch.bfloat16)
+def _mod_bwd(dmod32, temb, lin, d_temb32):
+    """dmod32: fp32 [B, n*D] gradient of the modulation vector; accumulates d temb into d_temb32 (fp32 [B, D])."""
+    wg, acc = (None, False)
     if lin.weight.requires_grad:
         wg, acc = _grad_buf(lin.weight)
-        ops.gemm(dmod, s, a_mn=True, b_mn=True, out=wg, accumulate=acc, cta_group=1)   # dW = dmod^T s  (K = batch)
-        _acc_vec(lin.bias, dmod32.sum(0))
-    ds = ops.gemm(dmod, lin.weight, b_mn=True, cta_group=1).float()                    # [B, D]
-    t = temb.float()
-    sig = torch.sigmoid(t)
-    return ds * (sig * (1 + t * (1 - sig)))
+    dbias = ops.mod_bwd(dmod32, temb if temb.is_contiguous() else temb.contiguous(), lin.weight, wg, acc, d_temb32)
+    if lin.weight.requires_grad:
+        _acc_vec(lin.bias, dbias)
 
 
 # =====================================================================================================================
@@ -152,7 +150,6 @@ class FluxDoubleBlockFn(torch.autograd.Function):
         H = blk.heads
         dev = hidden.device
         bf = torch.bfloat16
-        s = _silu_bf16(temb)
         shp = (B, H, Ltot, HD)
         q = torch.empty(shp, dtype=bf, device=dev)
         k = torch.empty(shp, dtype=bf, device=dev)
@@ -169,7 +166,7 @@ class FluxDoubleBlockFn(torch.autograd.Function):
             st = _Stream()
             st.L, st.off = L, off
             st.x = x3.reshape(B * L, D)
-            st.mod = _mod_fwd(s, modlin)                                  # [B, 6D]: shift,scale,gate (msa), shift,scale,gate (mlp)
+            st.mod = _mod_fwd(temb, modlin)                               # [B, 6D]: shift,scale,gate (msa), shift,scale,gate (mlp)
             m = st.mod
             xn, st.mean1, st.rstd1 = ops.ln_modulate_fwd(st.x, m[:, D:2 * D], m[:, 0:D], B, L)
             e = ops.make_qkv_epilogue(q, k, v, nq.weight, nk.weight, cos, sin, H, Ltot, off, qhat, khat, q_rstd, k_rstd)
@@ -198,14 +195,14 @@ class FluxDoubleBlockFn(torch.autograd.Function):
         ctx.blk = blk
         ctx.streams = streams
         ctx.attn = (q, k, v, qhat, khat, q_rstd, k_rstd, o, lse)
-        ctx.save_for_backward(temb, cos, sin, s)
+        ctx.save_for_backward(temb, cos, sin)
         ctx.dims = (B, Li, Lt, D, H)
         return outs[0], outs[1]
 
     @staticmethod
     def backward(ctx, d_hidden, d_enc):
         blk = ctx.blk
-        temb, cos, sin, s = ctx.saved_tensors
+        temb, cos, sin = ctx.saved_tensors
         B, Li, Lt, D, H = ctx.dims
         Ltot = Li + Lt
         dev = temb.device
@@ -277,7 +274,7 @@ class FluxDoubleBlockFn(torch.autograd.Function):
             dxn = ops.gemm(dqkv, fq.weight, b_mn=True, out=xn)
             dx, part = ops.ln_modulate_bwd(dxn, st.x, m[:, D:2 * D], st.mean1, st.rstd1, B, L, dres=dx1)
             ops.colreduce_finish(part, per_sample0=dmod[:, D:2 * D], per_sample1=dmod[:, 0:D])
-            d_temb += _mod_bwd(dmod, s, temb, modlin)
+            _mod_bwd(dmod, temb, modlin, d_temb)
             grads.append(dx.view(B, L, D))
         ctx.streams = None
         ctx.attn = None
@@ -349,9 +346,8 @@ class FluxSingleBlockFn(torch.autograd.Function):
         H = blk.heads
         dev = hidden.device
         bf = torch.bfloat16
-        s = _silu_bf16(temb)
         x = torch.cat([enc, hidden], dim=1).reshape(B * L, D)
-        mod = _mod_fwd(s, blk.norm.linear)                               # [B, 3D]: shift, scale, gate
+        mod = _mod_fwd(temb, blk.norm.linear)                               # [B, 3D]: shift, scale, gate
         xn, mean, rstd = ops.ln_modulate_fwd(x, mod[:, D:2 * D], mod[:, 0:D], B, L)
         shp = (B, H, L, HD)
         q = torch.empty(shp, dtype=bf, device=dev)
@@ -376,14 +372,14 @@ class FluxSingleBlockFn(torch.autograd.Function):
         xo3 = xo.view(B, L, D)
         ctx.blk = blk
         ctx.saved = (x, mod, mean, rstd, q, k, v, qhat, khat, q_rstd, k_rstd, cat, u, lse, y)
-        ctx.save_for_backward(temb, cos, sin, s)
+        ctx.save_for_backward(temb, cos, sin)
         ctx.dims = (B, Li, Lt, D, H)
         return xo3[:, Lt:], xo3[:, :Lt]
 
     @staticmethod
     def backward(ctx, d_hidden, d_enc):
         blk = ctx.blk
-        temb, cos, sin, s = ctx.saved_tensors
+        temb, cos, sin = ctx.saved_tensors
         B, Li, Lt, D, H = ctx.dims
         L = Li + Lt
         dev = temb.device
@@ -423,7 +419,8 @@ class FluxSingleBlockFn(torch.autograd.Function):
         dxn = ops.gemm(dlin1, f1.weight, b_mn=True, out=xn)
         dx, part = ops.ln_modulate_bwd(dxn, x, mod[:, D:2 * D], mean, rstd, B, L, dres=dxo)
         ops.colreduce_finish(part, per_sample0=dmod[:, D:2 * D], per_sample1=dmod[:, 0:D])
-        d_temb = _mod_bwd(dmod, s, temb, blk.norm.linear)
+        d_temb = torch.zeros((B, D), dtype=torch.float32, device=dev)
+        _mod_bwd(dmod, temb, blk.norm.linear, d_temb)
         dx3 = dx.view(B, L, D)
         ctx.saved = None
         return None, dx3[:, Lt:], dx3[:, :Lt], d_temb.to(temb.dtype), None, None

@@ -28,12 +28,12 @@ def _prof_begin():
     return e
 
 
-def _prof_end(e0, flops, kind):
+def _prof_end(e0, flops, kind, tag=None):
     if e0 is None:
         return
     e1 = torch.cuda.Event(enable_timing=True)
     e1.record()
-    PROFILE.append((e0, e1, flops, kind))
+    PROFILE.append((e0, e1, flops, kind, tag))
 
 
 def _stream():
@@ -106,7 +106,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, epilogue=EPI_STORE, bias=Non
         args.qkv = ctypes.pointer(qkv)
     _e = _prof_begin()
     check(lib().dpipe_gemm_bf16(ctypes.byref(args), _stream()), 'dpipe_gemm_bf16')
-    _prof_end(_e, 2.0 * M * N * K, 'gemm')
+    _prof_end(_e, 2.0 * M * N * K, 'gemm', (M, N, K, int(a_mn), int(b_mn), epilogue, int(bool(accumulate))))
     LAUNCHES += 1
     return out
 
@@ -313,6 +313,37 @@ def qknorm_rope_bwd(dq, dk, dv, qhat, khat, q_rstd, k_rstd, q_norm_w, k_norm_w, 
     a.batch, a.heads, a.seq_total, a.seq_offset, a.rows_per_batch = batch, heads, seq_total, seq_offset, rows_per_batch
     check(lib().dpipe_qknorm_rope_bwd(ctypes.byref(a), _stream()), 'dpipe_qknorm_rope_bwd')
     LAUNCHES += 1
+
+
+def mod_fwd(temb, weight, bias):
+    """mod[B, N] = W @ bf16(silu(temb)) + bias  (rank-B, HBM-bound kernel; temb [B, K] bf16)."""
+    global LAUNCHES
+    _req_bf16(temb, 'temb')
+    _req_bf16(weight, 'weight')
+    assert temb.is_contiguous() and weight.is_contiguous()
+    B, K = temb.shape
+    N = weight.shape[0]
+    out = torch.empty((B, N), dtype=torch.bfloat16, device=temb.device)
+    check(lib().dpipe_mod_fwd(_ptr(temb), _ptr(weight), _ptr(bias), _ptr(out), B, N, K, _stream()), 'dpipe_mod_fwd')
+    LAUNCHES += 1
+    return out
+
+
+def mod_bwd(dmod32, temb, weight, wgrad, accumulate, dtemb32):
+    """Backward of mod_fwd.  dmod32 fp32 [B, N]; wgrad bf16 [N, K] or None; dtemb32 fp32 [B, K] is accumulated into.
+    Returns dbias fp32 [N]."""
+    global LAUNCHES
+    _req_f32(dmod32, 'dmod32')
+    _req_f32(dtemb32, 'dtemb32')
+    B, K = temb.shape
+    N = weight.shape[0]
+    nc = lib().dpipe_mod_bwd_chunks(N)
+    partials = torch.empty((nc, B, K), dtype=torch.float32, device=temb.device)
+    dbias = torch.empty(N, dtype=torch.float32, device=temb.device)
+    check(lib().dpipe_mod_bwd(_ptr(dmod32), dmod32.stride(0), _ptr(temb), _ptr(weight), _ptr(wgrad), int(bool(accumulate)),
+                              _ptr(dbias), _ptr(partials), _ptr(dtemb32), B, N, K, _stream()), 'dpipe_mod_bwd')
+    LAUNCHES += 2
+    return dbias
 
 
 def mse_loss(out, target, mask=None, want_grad=True):

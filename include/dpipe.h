@@ -169,6 +169,16 @@ typedef struct dpipe_qk_bwd_args {
 /* backward of the DPIPE_EPI_QKV_ROPE epilogue for one stream */
 int dpipe_qknorm_rope_bwd(const dpipe_qk_bwd_args* args, void* stream);
 
+/* AdaLayerNorm modulation linear for a micro-batch of B <= 8 samples (HBM-bound, rank-B):
+ *   out[b,:] = W * bf16(silu(temb[b,:])) + bias.   replaces nn.Linear(SiLU(temb)) of AdaLayerNormZero{,Single}/Continuous
+ *   (models/flux.py:502,525,547). */
+int dpipe_mod_fwd(const void* temb, const void* W, const void* bias, void* out, int B, int N, int K, void* stream);
+/* its backward in one pass over W/dW: dW (+)= bf16(dmod)^T silu(temb); dbias[n] = sum_b dmod[b,n] (overwritten);
+ * dtemb[b,:] += silu'(temb) * (dmod W).  partials: dpipe_mod_bwd_chunks(N) * B * K floats.  dW may be NULL. */
+int dpipe_mod_bwd_chunks(int N);
+int dpipe_mod_bwd(const float* dmod, int64_t ldd, const void* temb, const void* W, void* dW, int accumulate, float* dbias,
+                  float* partials, float* dtemb, int B, int N, int K, void* stream);
+
 /* loss = mean((out - target)^2 * mask); dout (bf16, optional) = 2 (out-target) mask / numel.  workspace: 1024 floats */
 int dpipe_mse_loss(const void* out, const float* target, const float* mask, int64_t numel, float* workspace,
                    float* loss, void* dout, void* stream);
