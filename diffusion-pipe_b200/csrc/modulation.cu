@@ -85,10 +85,12 @@ __global__ void mod_bwd_kernel(const float* __restrict__ dmod, int64_t ldd, cons
     }
   }
   __syncthreads();
-  if (dbias && threadIdx.x < MOD_ROWS && n0 + threadIdx.x < N) {
-    float v = 0.f;
-    for (int b = 0; b < B; ++b) v += dm[b][threadIdx.x];
-    dbias[n0 + threadIdx.x] = v;
+  if (dbias) {
+    for (int r = threadIdx.x; r < MOD_ROWS && n0 + r < N; r += blockDim.x) {   // blockDim may be smaller than MOD_ROWS
+      float v = 0.f;
+      for (int b = 0; b < B; ++b) v += dm[b][r];
+      dbias[n0 + r] = v;
+    }
   }
   const int rows = min(MOD_ROWS, N - n0);
 #pragma unroll 4
