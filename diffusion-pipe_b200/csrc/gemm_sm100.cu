@@ -24,7 +24,7 @@ constexpr int BK = 64;   // K per pipeline stage = one 128-byte swizzle row of b
 constexpr int UK = 16;   // K per tcgen05.mma (kind::f16)
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int SUB_BYTES = 64 * 64 * 2;     // one 64(mn) x 64(k) MN-major sub-tile = 8 KiB
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps (2 per TMEM lane quarter)
 
 template <int CG>
 struct GemmCfg {
@@ -114,7 +114,8 @@ __device__ __forceinline__ void epi_bias_gelu_chunk(const GemmParams& p, bool ok
 }
 
 template <int EPI>
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, int row, int n0, uint32_t taddr) {
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, int row, int n0, uint32_t taddr, int half) {
+  // `half` selects which 128 of the tile's 256 accumulator columns this warp drains
   const bool row_ok = row < p.M;
   const int batch = row_ok ? row / p.rows_per_batch : 0;
 
@@ -127,7 +128,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int row, int 
       const int tok = row_ok ? row - batch * p.rows_per_batch : 0;
       const int pos = e.seq_offset + tok;
 #pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
+      for (int hh = half; hh <= half; ++hh) {
         const int col_h = n0 + hh * 128;  // global column of this head's first element
         if (col_h >= p.N) break;
         const int head = (col_h - which * hd) >> 7;
@@ -201,7 +202,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int row, int 
   }
 
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = half * 4; c < half * 4 + 4; ++c) {
     const int col = n0 + c * 32;
     if (col >= p.N) break;  // warp-uniform
     uint32_t r[32];
@@ -298,7 +299,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
-      mbar_init(smem_u32(&tempty_bar[a]), 4 * CG);  // one arrival per epilogue warp of every CTA in the group
+      mbar_init(smem_u32(&tempty_bar[a]), 8 * CG);  // one arrival per epilogue warp of every CTA in the group
     }
     fence_barrier_init();
   }
@@ -410,7 +411,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       tc_fence_after();
       const int row = (mt * CG + (int)cta_rank) * BM + quad * 32 + lane;
       const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * BN;
-      epilogue_tile<EPI>(p, row, nt * BN, taddr);
+      epilogue_tile<EPI>(p, row, nt * BN, taddr, (int)((warp - 4) >> 2));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
