@@ -320,6 +320,10 @@ def main():
         attn_ms = sum(s.elapsed_time(e) for s, e, _, k, _ in prof if k.startswith('attn'))
         attn_fl = sum(f for _, _, f, k, _ in prof if k.startswith('attn'))
         n_gemm = sum(1 for p in prof if p[3] == 'gemm')
+        kind_ms = {}
+        for s_, e_, f_, k_, _t in prof:
+            kind_ms[k_] = kind_ms.get(k_, 0.0) + s_.elapsed_time(e_)
+        kind_share = {k: round(v / (ms_dev if ms_dev else 1), 4) for k, v in sorted(kind_ms.items(), key=lambda kv: -kv[1])}
         by_shape = {}
         for s_, e_, f_, k_, tag in prof:
             if k_ == 'gemm':
@@ -350,7 +354,7 @@ def main():
                 'share_of_step': gemm_ms / (ms_dev if ms_dev else 1),
                 'attention': {'achieved': attn_fl / attn_ms / 1e9 if attn_ms > 0 else None, 'unit': 'TFLOP/s (algorithmic: 4LqLkD fwd, 2.5x bwd)',
                               'share_of_step': attn_ms / (ms_dev if ms_dev else 1)},
-                'kernels_share_of_step': tot_ms / (ms_dev if ms_dev else 1),
+                'kernels_share_of_step': tot_ms / (ms_dev if ms_dev else 1), 'share_by_kernel': kind_share,
                 'step_tflops': TRAIN_TFLOP_PER_SAMPLE * (n_double + n_single) / 57.0 * value / max(1, world)}
 
     cpu = None

@@ -72,6 +72,8 @@ SIGNATURES['dpipe_qknorm_rope_bwd'] = (c_int, [ctypes.POINTER(QkBwdArgs), c_void
 SIGNATURES['dpipe_sched_num_pipe_buffers'] = (c_int, [c_int, c_int, c_int])
 SIGNATURES['dpipe_sched_train'] = (c_int, [c_int, c_int, c_int, c_void_p, c_int])
 SIGNATURES['dpipe_sched_infer'] = (c_int, [c_int, c_int, c_int, c_void_p, c_int])
+SIGNATURES['dpipe_sched_zb'] = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int])
+SIGNATURES['dpipe_sched_zb_makespan'] = (ctypes.c_longlong, [c_int, c_int, c_int, c_int, c_int, c_int])
 SIGNATURES['dpipe_partition_balanced'] = (c_int, [c_void_p, c_int, c_int, c_void_p])
 SIGNATURES['dpipe_ipc_alloc'] = (c_int, [c_int64, ctypes.POINTER(c_void_p), c_void_p])
 SIGNATURES['dpipe_ipc_open'] = (c_int, [c_void_p, ctypes.POINTER(c_void_p)])

@@ -158,3 +158,156 @@ extern "C" int dpipe_partition_balanced(const int64_t* weights, int n, int parts
   }
   return 0;
 }
+
+// -------------------------------------------------------------------------------------------------------------------
+// Split-backward ("zero-bubble") schedule.  Not in the reference: it is loss-equivalent to 1F1B (same per-micro-batch
+// arithmetic, gradients accumulated in micro-batch order) but separates the backward pass into
+//   B = input-gradient pass (on the critical path: its result is what the previous stage waits for) and
+//   W = weight-gradient pass (no consumer on another stage),
+// so W work can fill what would be pipeline bubbles (Qi et al., "Zero Bubble Pipeline Parallelism", ZB-H1/ZB-2p).
+// The order is produced by a deterministic list-scheduling simulation of ALL stages with the given relative costs
+// (tf, tb, tw): whenever a stage becomes free it runs, in priority order, the oldest ready B, else the next F if fewer
+// than `max_inflight` micro-batches are in flight on it, else a pending W; it idles only when nothing is ready.  Every
+// rank runs the same simulation, so all stages agree on the global order without communication.
+// Needs a one-sided stage link (IpcLink) or asynchronous sends: a stage pushes activations right after F and gradients
+// right after B, whenever the neighbour will get to them.
+// -------------------------------------------------------------------------------------------------------------------
+extern "C" int dpipe_sched_zb(int micro_batches, int stages, int stage_id, int tf, int tb, int tw, int max_inflight,
+                              dpipe_instr* out, int capacity) {
+  const int M = micro_batches, S = stages;
+  if (M < 1 || S < 1 || stage_id < 0 || stage_id >= S || tf < 1 || tb < 1 || tw < 1 || max_inflight < 1 || (!out && capacity > 0))
+    return dpipe::fail(DPIPE_EINVAL, "dpipe_sched_zb: bad arguments");
+  struct St { long long free_at; int nf, nb, nw; bool done; };
+  St* st = new St[S];
+  long long* fin_f = new long long[(size_t)S * M];
+  long long* fin_b = new long long[(size_t)S * M];
+  const long long INF = (1LL << 60);
+  for (int s = 0; s < S; ++s) { st[s] = {0, 0, 0, 0, false}; }
+  for (size_t i = 0; i < (size_t)S * M; ++i) { fin_f[i] = INF; fin_b[i] = INF; }
+  Emit e{out, capacity, 0, false};
+  int remaining = S;
+  while (remaining > 0) {
+    // stage with the smallest clock acts next (ties: lowest index)
+    int s = -1;
+    for (int i = 0; i < S; ++i)
+      if (!st[i].done && (s < 0 || st[i].free_at < st[s].free_at)) s = i;
+    St& a = st[s];
+    const long long now = a.free_at;
+    auto f_ready = [&](int m) { return s == 0 ? 0 : fin_f[(size_t)(s - 1) * M + m]; };
+    auto b_ready = [&](int m) { return s == S - 1 ? fin_f[(size_t)s * M + m] : fin_b[(size_t)(s + 1) * M + m]; };
+    int op = 0, m = -1;   // 1 = F, 2 = B, 3 = W
+    if (a.nb < M && a.nb < a.nf && b_ready(a.nb) <= now) { op = 2; m = a.nb; }
+    else if (a.nf < M && (a.nf - a.nb) < max_inflight && f_ready(a.nf) <= now) { op = 1; m = a.nf; }
+    else if (a.nw < a.nb) { op = 3; m = a.nw; }
+    if (op == 0) {
+      // nothing ready: sleep until the next point in time at which something can have changed
+      long long next = INF;
+      if (a.nb < M && a.nb < a.nf && b_ready(a.nb) < INF) next = b_ready(a.nb);
+      if (a.nf < M && (a.nf - a.nb) < max_inflight && f_ready(a.nf) < INF && f_ready(a.nf) < next) next = f_ready(a.nf);
+      if (next == INF || next <= now) {
+        for (int i = 0; i < S; ++i)
+          if (i != s && !st[i].done && st[i].free_at > now && st[i].free_at < next) next = st[i].free_at;
+      }
+      if (next == INF || next <= now) next = now + 1;
+      a.free_at = next;
+      continue;
+    }
+    const bool mine = (s == stage_id);
+    if (op == 1) {
+      if (mine) {
+        if (s == 0 || s == S - 1) e.push(DPIPE_OP_LOAD_MICRO_BATCH, m, m);
+        if (s > 0) e.push(DPIPE_OP_RECV_ACTIVATION, m, m);
+        e.push(DPIPE_OP_FORWARD_PASS, m, m);
+        if (s < S - 1) e.push(DPIPE_OP_SEND_ACTIVATION, m, m);
+        e.push(DPIPE_OP_TICK_END, -1, -1);
+      }
+      a.free_at = now + tf;
+      fin_f[(size_t)s * M + m] = a.free_at;
+      a.nf++;
+    } else if (op == 2) {
+      if (mine) {
+        if (s < S - 1) e.push(DPIPE_OP_RECV_GRAD, m, m);
+        e.push(DPIPE_OP_BACKWARD_INPUT, m, m);
+        if (s > 0) e.push(DPIPE_OP_SEND_GRAD, m, m);
+        e.push(DPIPE_OP_TICK_END, -1, -1);
+      }
+      a.free_at = now + tb;
+      fin_b[(size_t)s * M + m] = a.free_at;
+      a.nb++;
+    } else {
+      if (mine) {
+        e.push(DPIPE_OP_BACKWARD_WEIGHT, m, m);
+        e.push(DPIPE_OP_TICK_END, -1, -1);
+      }
+      a.free_at = now + tw;
+      a.nw++;
+    }
+    if (a.nf == M && a.nb == M && a.nw == M) { a.done = true; --remaining; }
+  }
+  e.push(DPIPE_OP_REDUCE_TIED_GRADS, -1, -1);
+  e.push(DPIPE_OP_REDUCE_GRADS, -1, -1);
+  e.push(DPIPE_OP_OPTIMIZER_STEP, -1, -1);
+  e.push(DPIPE_OP_TICK_END, -1, -1);
+  long long makespan = 0;
+  for (int i = 0; i < S; ++i) if (st[i].free_at > makespan) makespan = st[i].free_at;
+  delete[] st; delete[] fin_f; delete[] fin_b;
+  if (e.overflow && capacity > 0) return dpipe::fail(DPIPE_EINVAL, "dpipe_sched_zb: capacity %d < %d", capacity, e.n);
+  (void)makespan;
+  return e.n;
+}
+
+// simulated makespan of the zero-bubble order (same simulation as dpipe_sched_zb), for tests / reporting
+extern "C" long long dpipe_sched_zb_makespan(int micro_batches, int stages, int tf, int tb, int tw, int max_inflight) {
+  const int M = micro_batches, S = stages;
+  if (M < 1 || S < 1 || tf < 1 || tb < 1 || tw < 1 || max_inflight < 1) return -1;
+  long long best = 0;
+  // derive it from the per-stage instruction streams: replay with dependencies
+  struct Op { int kind, m; };
+  Op** ops = new Op*[S];
+  int* cnt = new int[S];
+  for (int s = 0; s < S; ++s) {
+    const int n = dpipe_sched_zb(M, S, s, tf, tb, tw, max_inflight, nullptr, 0);
+    dpipe_instr* buf = new dpipe_instr[n];
+    dpipe_sched_zb(M, S, s, tf, tb, tw, max_inflight, buf, n);
+    ops[s] = new Op[3 * M];
+    cnt[s] = 0;
+    for (int i = 0; i < n; ++i) {
+      if (buf[i].op == DPIPE_OP_FORWARD_PASS) ops[s][cnt[s]++] = {1, buf[i].micro_batch};
+      else if (buf[i].op == DPIPE_OP_BACKWARD_INPUT) ops[s][cnt[s]++] = {2, buf[i].micro_batch};
+      else if (buf[i].op == DPIPE_OP_BACKWARD_WEIGHT) ops[s][cnt[s]++] = {3, buf[i].micro_batch};
+    }
+    delete[] buf;
+  }
+  const long long INF = (1LL << 60);
+  long long* ff = new long long[(size_t)S * M];
+  long long* fb = new long long[(size_t)S * M];
+  for (size_t i = 0; i < (size_t)S * M; ++i) { ff[i] = INF; fb[i] = INF; }
+  int* pos = new int[S];
+  long long* t = new long long[S];
+  for (int s = 0; s < S; ++s) { pos[s] = 0; t[s] = 0; }
+  bool progress = true;
+  while (progress) {
+    progress = false;
+    for (int s = 0; s < S; ++s) {
+      while (pos[s] < cnt[s]) {
+        const Op o = ops[s][pos[s]];
+        long long ready = 0;
+        if (o.kind == 1) ready = s == 0 ? 0 : ff[(size_t)(s - 1) * M + o.m];
+        else if (o.kind == 2) ready = s == S - 1 ? ff[(size_t)s * M + o.m] : fb[(size_t)(s + 1) * M + o.m];
+        else ready = fb[(size_t)s * M + o.m];
+        if (ready == INF) break;
+        const long long start = ready > t[s] ? ready : t[s];
+        t[s] = start + (o.kind == 1 ? tf : o.kind == 2 ? tb : tw);
+        if (o.kind == 1) ff[(size_t)s * M + o.m] = t[s];
+        if (o.kind == 2) fb[(size_t)s * M + o.m] = t[s];
+        ++pos[s];
+        progress = true;
+      }
+    }
+  }
+  bool complete = true;
+  for (int s = 0; s < S; ++s) { if (pos[s] != cnt[s]) complete = false; if (t[s] > best) best = t[s]; }
+  for (int s = 0; s < S; ++s) delete[] ops[s];
+  delete[] ops; delete[] cnt; delete[] ff; delete[] fb; delete[] pos; delete[] t;
+  return complete ? best : -2;   // -2: the per-stage orders deadlock (must never happen)
+}

@@ -62,10 +62,12 @@ class LinearFn(torch.autograd.Function):
             dy2 = dy2.contiguous()
         cg = 2 if x2.shape[0] > 128 else 1
         if lin.weight.requires_grad:
-            g, acc = _grad_buf(lin.weight)
-            ops.gemm(dy2, x2, a_mn=True, b_mn=True, out=g, accumulate=acc, cta_group=cg)
-            if lin.bias is not None:
-                _acc_vec(lin.bias, ops.colsum(dy2))
+            def wgrad(lin=lin, dy2=dy2, x2=x2, cg=cg):
+                g, acc = _grad_buf(lin.weight)
+                ops.gemm(dy2, x2, a_mn=True, b_mn=True, out=g, accumulate=acc, cta_group=cg)
+                if lin.bias is not None:
+                    _acc_vec(lin.bias, ops.colsum(dy2))
+            ops.defer(wgrad)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = ops.gemm(dy2, lin.weight, b_mn=True, cta_group=cg).view(ctx.shp).to(ctx.in_dtype)

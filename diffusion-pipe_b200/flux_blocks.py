@@ -226,30 +226,39 @@ class FluxDoubleBlockFn(torch.autograd.Function):
             ops.colreduce_finish(part, per_sample0=dmod[:, 5 * D:6 * D], summed1=db2)
             du = ops.gemm(dy2, w2.weight, b_mn=True, epilogue=ops.EPI_MUL_GELU_GRAD, aux=st.u)        # [BL, 4D]
             if w2.weight.requires_grad:
-                g, acc = _grad_buf(w2.weight)
-                ops.gemm(dy2, st.h, a_mn=True, b_mn=True, out=g, accumulate=acc)                       # dW2 = dy2^T h
-                _acc_vec(w2.bias, db2)
+                def wgrad_w2(w2=w2, dy2=dy2, h=st.h, db2=db2):
+                    g, acc = _grad_buf(w2.weight)
+                    ops.gemm(dy2, h, a_mn=True, b_mn=True, out=g, accumulate=acc)                      # dW2 = dy2^T h
+                    _acc_vec(w2.bias, db2)
+                ops.defer(wgrad_w2)
             xn2, _, _ = ops.ln_modulate_fwd(st.x1, m[:, 4 * D:5 * D], m[:, 3 * D:4 * D], B, L, save_stats=False)
             if w1.weight.requires_grad:
-                g, acc = _grad_buf(w1.weight)
-                ops.gemm(du, xn2, a_mn=True, b_mn=True, out=g, accumulate=acc)                         # dW1 = du^T xn2
-                _acc_vec(w1.bias, ops.colsum(du))
-            dxn2 = ops.gemm(du, w1.weight, b_mn=True, out=xn2)                                         # reuse xn2 storage
+                db1 = ops.colsum(du)
+
+                def wgrad_w1(w1=w1, du=du, xn2=xn2, db1=db1):
+                    g, acc = _grad_buf(w1.weight)
+                    ops.gemm(du, xn2, a_mn=True, b_mn=True, out=g, accumulate=acc)                     # dW1 = du^T xn2
+                    _acc_vec(w1.bias, db1)
+                ops.defer(wgrad_w1)
+            # (the xn2 storage is recycled for the result unless a deferred weight-gradient still needs xn2)
+            dxn2 = ops.gemm(du, w1.weight, b_mn=True, out=None if ops.deferring() else xn2)
             dx1, part = ops.ln_modulate_bwd(dxn2, st.x1, m[:, 4 * D:5 * D], st.mean2, st.rstd2, B, L, dres=dx2)
             ops.colreduce_finish(part, per_sample0=dmod[:, 4 * D:5 * D], per_sample1=dmod[:, 3 * D:4 * D])
             # ---- attention branch: x1 = x + gate_msa * (o W_o^T + b_o) ----
             dy1, part = ops.gate_bwd(dx1, st.y_attn, m[:, 2 * D:3 * D], B, L, dy=dxn2)
             dbo = torch.empty(D, dtype=torch.float32, device=dev)
             ops.colreduce_finish(part, per_sample0=dmod[:, 2 * D:3 * D], summed1=dbo)
-            wg = acc = None
-            if wo.weight.requires_grad:
-                wg, acc = _grad_buf(wo.weight)
-                _acc_vec(wo.bias, dbo)
             for b in range(B):
                 rs = slice(b * L, (b + 1) * L)
                 ops.gemm(dy1[rs], wo.weight, b_mn=True, out=d_o3[b, off:off + L])                      # d o (this stream's rows)
-                if wg is not None:
-                    ops.gemm(dy1[rs], o3[b, off:off + L], a_mn=True, b_mn=True, out=wg, accumulate=acc or b > 0)
+            if wo.weight.requires_grad:
+                def wgrad_wo(wo=wo, dy1=dy1, o3=o3, dbo=dbo, L=L, off=off):
+                    wg, acc = _grad_buf(wo.weight)
+                    for b in range(B):
+                        ops.gemm(dy1[b * L:(b + 1) * L], o3[b, off:off + L], a_mn=True, b_mn=True, out=wg,
+                                 accumulate=acc or b > 0)                                              # dWo = dy1^T o
+                    _acc_vec(wo.bias, dbo)
+                ops.defer(wgrad_wo)
             dmods.append(dmod)
             dx1s.append(dx1)
         dq, dk, dv = ops.attn_bwd(q, k, v, o, d_o, lse)
@@ -266,12 +275,14 @@ class FluxDoubleBlockFn(torch.autograd.Function):
                                 B, H, Ltot, off, L)
             xn, _, _ = ops.ln_modulate_fwd(st.x, m[:, D:2 * D], m[:, 0:D], B, L, save_stats=False)
             if fq.requires_grad():
-                wgrad, bgrad, acc = fq.grads()
-                ops.gemm(dqkv, xn, a_mn=True, b_mn=True, out=wgrad, accumulate=acc)                    # dWqkv = dqkv^T xn
-                _acc_fused_bias(fq, bgrad, acc, dbias)
-                _acc_vec(nq.weight, dw[0])
-                _acc_vec(nk.weight, dw[1])
-            dxn = ops.gemm(dqkv, fq.weight, b_mn=True, out=xn)
+                def wgrad_qkv(fq=fq, nq=nq, nk=nk, dqkv=dqkv, xn=xn, dbias=dbias, dw=dw):
+                    wgrad, bgrad, acc = fq.grads()
+                    ops.gemm(dqkv, xn, a_mn=True, b_mn=True, out=wgrad, accumulate=acc)                # dWqkv = dqkv^T xn
+                    _acc_fused_bias(fq, bgrad, acc, dbias)
+                    _acc_vec(nq.weight, dw[0])
+                    _acc_vec(nk.weight, dw[1])
+                ops.defer(wgrad_qkv)
+            dxn = ops.gemm(dqkv, fq.weight, b_mn=True, out=None if ops.deferring() else xn)
             dx, part = ops.ln_modulate_bwd(dxn, st.x, m[:, D:2 * D], st.mean1, st.rstd1, B, L, dres=dx1)
             ops.colreduce_finish(part, per_sample0=dmod[:, D:2 * D], per_sample1=dmod[:, 0:D])
             _mod_bwd(dmod, temb, modlin, d_temb)
@@ -400,9 +411,11 @@ class FluxSingleBlockFn(torch.autograd.Function):
         ops.gemm(dy, po.weight[:, :D], b_mn=True, out=d_o)                                              # d attn
         ops.gemm(dy, po.weight[:, D:], b_mn=True, epilogue=ops.EPI_MUL_GELU_GRAD, aux=u, out=dlin1[:, 3 * H * HD:])
         if po.weight.requires_grad:
-            g, acc = _grad_buf(po.weight)
-            ops.gemm(dy, cat, a_mn=True, b_mn=True, out=g, accumulate=acc)
-            _acc_vec(po.bias, dbo)
+            def wgrad_po(po=po, dy=dy, cat=cat, dbo=dbo):
+                g, acc = _grad_buf(po.weight)
+                ops.gemm(dy, cat, a_mn=True, b_mn=True, out=g, accumulate=acc)
+                _acc_vec(po.bias, dbo)
+            ops.defer(wgrad_po)
         dq, dk, dv = ops.attn_bwd(q, k, v, cat, d_o, lse)
         dbias = torch.zeros(n1, dtype=torch.float32, device=dev)
         dw = torch.zeros((2, HD), dtype=torch.float32, device=dev)
@@ -410,13 +423,16 @@ class FluxSingleBlockFn(torch.autograd.Function):
                             sin, dlin1, dbias[:3 * H * HD], dw, B, H, L, 0, L)
         xn, _, _ = ops.ln_modulate_fwd(x, mod[:, D:2 * D], mod[:, 0:D], B, L, save_stats=False)
         if f1.requires_grad():
-            wgrad, bgrad, acc = f1.grads()
-            ops.gemm(dlin1, xn, a_mn=True, b_mn=True, out=wgrad, accumulate=acc)
             ops.colsum(dlin1[:, 3 * H * HD:], out=dbias[3 * H * HD:])
-            _acc_fused_bias(f1, bgrad, acc, dbias)
-            _acc_vec(blk.attn.norm_q.weight, dw[0])
-            _acc_vec(blk.attn.norm_k.weight, dw[1])
-        dxn = ops.gemm(dlin1, f1.weight, b_mn=True, out=xn)
+
+            def wgrad_lin1(f1=f1, blk=blk, dlin1=dlin1, xn=xn, dbias=dbias, dw=dw):
+                wgrad, bgrad, acc = f1.grads()
+                ops.gemm(dlin1, xn, a_mn=True, b_mn=True, out=wgrad, accumulate=acc)
+                _acc_fused_bias(f1, bgrad, acc, dbias)
+                _acc_vec(blk.attn.norm_q.weight, dw[0])
+                _acc_vec(blk.attn.norm_k.weight, dw[1])
+            ops.defer(wgrad_lin1)
+        dxn = ops.gemm(dlin1, f1.weight, b_mn=True, out=None if ops.deferring() else xn)
         dx, part = ops.ln_modulate_bwd(dxn, x, mod[:, D:2 * D], mean, rstd, B, L, dres=dxo)
         ops.colreduce_finish(part, per_sample0=dmod[:, D:2 * D], per_sample1=dmod[:, 0:D])
         d_temb = torch.zeros((B, D), dtype=torch.float32, device=dev)

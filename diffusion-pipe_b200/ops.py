@@ -20,6 +20,23 @@ LAUNCHES = 0
 PROFILE = None
 
 
+# when a list, weight-gradient work is queued instead of launched (split-backward / zero-bubble schedule): the engine
+# sets it around a BackwardInput pass and runs the queued closures in the matching BackwardWeight pass
+WGRAD_DEFER = None
+
+
+def deferring():
+    return WGRAD_DEFER is not None
+
+
+def defer(fn):
+    """run `fn` now, or queue it when a split-backward pass is active"""
+    if WGRAD_DEFER is not None:
+        WGRAD_DEFER.append(fn)
+    else:
+        fn()
+
+
 def _prof_begin():
     if PROFILE is None:
         return None
@@ -221,9 +238,11 @@ def ln_modulate_fwd(x, scale, shift, batch, rows_per_batch, eps=1e-6, out=None, 
     if save_stats:
         mean = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
         rstd = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    _e = _prof_begin()
     check(lib().dpipe_ln_modulate_fwd(_ptr(x), x.stride(0), _ptr(scale), _ptr(shift), scale.stride(0), _ptr(out),
                                       out.stride(0), _ptr(mean), _ptr(rstd), batch, rows_per_batch, D, eps, _stream()),
           'dpipe_ln_modulate_fwd')
+    _prof_end(_e, 0.0, 'ln_fwd')
     LAUNCHES += 1
     return out, mean, rstd
 
@@ -242,10 +261,12 @@ def ln_modulate_bwd(dxn, x, scale, mean, rstd, batch, rows_per_batch, dres=None,
         partials = torch.empty((batch, nc, 2, D), dtype=torch.float32, device=x.device)
     if dres is not None:
         _req_bf16(dres, 'dres')
+    _e = _prof_begin()
     check(lib().dpipe_ln_modulate_bwd(_ptr(dxn), dxn.stride(0), _ptr(x), x.stride(0), _ptr(scale), scale.stride(0),
                                       _ptr(mean), _ptr(rstd), _ptr(dres), dres.stride(0) if dres is not None else 0,
                                       _ptr(dx), dx.stride(0), _ptr(partials), batch, rows_per_batch, D, _stream()),
           'dpipe_ln_modulate_bwd')
+    _prof_end(_e, 0.0, 'ln_bwd')
     LAUNCHES += 1
     return dx, partials
 
@@ -262,8 +283,10 @@ def gate_bwd(dx, y, gate, batch, rows_per_batch, dy=None, partials=None):
         dy = torch.empty((y.shape[0], D), dtype=torch.bfloat16, device=y.device)
     if partials is None:
         partials = torch.empty((batch, nc, 2, D), dtype=torch.float32, device=y.device)
+    _e = _prof_begin()
     check(lib().dpipe_gate_bwd(_ptr(dx), dx.stride(0), _ptr(y), y.stride(0), _ptr(gate), gate.stride(0), _ptr(dy),
                                dy.stride(0), _ptr(partials), batch, rows_per_batch, D, _stream()), 'dpipe_gate_bwd')
+    _prof_end(_e, 0.0, 'gate_bwd')
     LAUNCHES += 1
     return dy, partials
 
@@ -275,8 +298,10 @@ def colreduce_finish(partials, per_sample0=None, per_sample1=None, summed0=None,
     batch, nc, nslot, D = partials.shape
     ld0 = per_sample0.stride(0) if per_sample0 is not None else 0
     ld1 = per_sample1.stride(0) if per_sample1 is not None else 0
+    _e = _prof_begin()
     check(lib().dpipe_colreduce_finish(_ptr(partials), batch, nc, nslot, D, _ptr(per_sample0), ld0, _ptr(per_sample1),
                                        ld1, _ptr(summed0), _ptr(summed1), _stream()), 'dpipe_colreduce_finish')
+    _prof_end(_e, 0.0, 'finish')
     LAUNCHES += 1
 
 
@@ -289,7 +314,9 @@ def colsum(x, out=None):
     partials = torch.empty((nc, N), dtype=torch.float32, device=x.device)
     if out is None:
         out = torch.empty(N, dtype=torch.float32, device=x.device)
+    _e = _prof_begin()
     check(lib().dpipe_colsum(_ptr(x), x.stride(0), rows, N, _ptr(partials), _ptr(out), _stream()), 'dpipe_colsum')
+    _prof_end(_e, 0.0, 'colsum')
     LAUNCHES += 2
     return out
 
@@ -311,7 +338,9 @@ def qknorm_rope_bwd(dq, dk, dv, qhat, khat, q_rstd, k_rstd, q_norm_w, k_norm_w, 
     _req_f32(dw, 'dw')
     a.dbias, a.dw = _ptr(dbias), _ptr(dw)
     a.batch, a.heads, a.seq_total, a.seq_offset, a.rows_per_batch = batch, heads, seq_total, seq_offset, rows_per_batch
+    _e = _prof_begin()
     check(lib().dpipe_qknorm_rope_bwd(ctypes.byref(a), _stream()), 'dpipe_qknorm_rope_bwd')
+    _prof_end(_e, 0.0, 'qknorm_bwd')
     LAUNCHES += 1
 
 
@@ -324,7 +353,9 @@ def mod_fwd(temb, weight, bias):
     B, K = temb.shape
     N = weight.shape[0]
     out = torch.empty((B, N), dtype=torch.bfloat16, device=temb.device)
+    _e = _prof_begin()
     check(lib().dpipe_mod_fwd(_ptr(temb), _ptr(weight), _ptr(bias), _ptr(out), B, N, K, _stream()), 'dpipe_mod_fwd')
+    _prof_end(_e, 0.0, 'mod_fwd')
     LAUNCHES += 1
     return out
 
@@ -340,8 +371,10 @@ def mod_bwd(dmod32, temb, weight, wgrad, accumulate, dtemb32):
     nc = lib().dpipe_mod_bwd_chunks(N)
     partials = torch.empty((nc, B, K), dtype=torch.float32, device=temb.device)
     dbias = torch.empty(N, dtype=torch.float32, device=temb.device)
+    _e = _prof_begin()
     check(lib().dpipe_mod_bwd(_ptr(dmod32), dmod32.stride(0), _ptr(temb), _ptr(weight), _ptr(wgrad), int(bool(accumulate)),
                               _ptr(dbias), _ptr(partials), _ptr(dtemb32), B, N, K, _stream()), 'dpipe_mod_bwd')
+    _prof_end(_e, 0.0, 'mod_bwd')
     LAUNCHES += 2
     return dbias
 
@@ -357,7 +390,9 @@ def mse_loss(out, target, mask=None, want_grad=True):
     ws = torch.empty(1024, dtype=torch.float32, device=out.device)
     loss = torch.empty((), dtype=torch.float32, device=out.device)
     dout = torch.empty_like(out) if want_grad else None
+    _e = _prof_begin()
     check(lib().dpipe_mse_loss(_ptr(out), _ptr(target), _ptr(mask), out.numel(), _ptr(ws), _ptr(loss), _ptr(dout),
                                _stream()), 'dpipe_mse_loss')
+    _prof_end(_e, 0.0, 'mse')
     LAUNCHES += 2
     return loss, dout

@@ -3,4 +3,5 @@
 from .module import LayerSpec, ManualPipelineModule, PipelineModule  # noqa: F401
 from .engine import PipelineEngine, initialize  # noqa: F401
 from .schedule import (BackwardPass, ForwardPass, InferenceSchedule, LoadMicroBatch, OptimizerStep, RecvActivation,  # noqa: F401
-                       RecvGrad, ReduceGrads, ReduceTiedGrads, SendActivation, SendGrad, TrainSchedule)
+                       RecvGrad, ReduceGrads, ReduceTiedGrads, SendActivation, SendGrad, TrainSchedule, ZeroBubbleSchedule,
+                       BackwardInput, BackwardWeight)

@@ -6,6 +6,7 @@ import torch
 import torch.distributed as tdist
 
 ReduceOp = tdist.ReduceOp
+tdist = tdist
 
 
 def init_distributed(dist_backend=None, timeout=None):

@@ -24,8 +24,9 @@ import torch
 
 from . import dist
 from .module import PipelineModule
-from .schedule import (BackwardPass, ForwardPass, InferenceSchedule, LoadMicroBatch, OptimizerStep, RecvActivation, RecvGrad,
-                       ReduceGrads, ReduceTiedGrads, SendActivation, SendGrad, TrainSchedule)
+from .schedule import (BackwardInput, BackwardPass, BackwardWeight, ForwardPass, InferenceSchedule, LoadMicroBatch,
+                       OptimizerStep, RecvActivation, RecvGrad, ReduceGrads, ReduceTiedGrads, SendActivation, SendGrad,
+                       TrainSchedule, ZeroBubbleSchedule)
 
 _DTYPES = [torch.float32, torch.float16, torch.bfloat16, torch.int64, torch.int32, torch.int16, torch.int8, torch.uint8,
            torch.bool, torch.float64, torch.complex64]
@@ -39,11 +40,25 @@ class DistLink:
     def __init__(self, engine):
         self.engine = engine
         self.device = engine.device
+        self._pending = []
         self.reset()
 
     def reset(self):
         self._send_meta_done = {}
         self._recv_meta = {}
+
+    def _send(self, t, dst):
+        """blocking send for the reference order; isend (completed in flush) when a stage may run ahead of its
+        neighbour (zero-bubble order), where two blocking sends could face each other"""
+        if self.engine.pipeline_schedule == 'zb':
+            self._pending.append((dist.tdist.isend(t, dst), t))
+        else:
+            dist.send(t, dst)
+
+    def flush(self):
+        for w, _t in self._pending:
+            w.wait()
+        self._pending = []
 
     def _meta_device(self):
         return self.device if self.device.type == 'cuda' else torch.device('cpu')
@@ -54,11 +69,11 @@ class DistLink:
             for t in tensors:
                 meta += [_DTYPE_ID[t.dtype], t.dim()] + list(t.shape)
             m = torch.tensor([len(meta)] + meta, dtype=torch.int64, device=self._meta_device())
-            dist.send(m[:1].clone(), dst)
-            dist.send(m[1:].contiguous(), dst)
+            self._send(m[:1].clone(), dst)
+            self._send(m[1:].contiguous(), dst)
             self._send_meta_done[key] = True
         for t in tensors:
-            dist.send(t.contiguous(), dst)
+            self._send(t.contiguous(), dst)
 
     def recv_tuple(self, src, key):
         if key not in self._recv_meta:
@@ -111,6 +126,11 @@ class PipelineEngine:
         self._grad_norm = None
         self.loss_fn = model.loss_fn
         self.pipe_buffers = {'inputs': [], 'labels': [], 'outputs': [], 'grads': []}
+        # 'pipeline_schedule': '1f1b' (the reference's instruction stream) or 'zb' (split-backward zero-bubble order)
+        self.pipeline_schedule = str(self.config.get('pipeline_schedule', '1f1b')).lower()
+        self.zb_costs = tuple(self.config.get('zb_costs', (13, 17, 10)))
+        self.zb_max_inflight = self.config.get('zb_max_inflight', None)
+        self._wgrad_queues = {}
         self.link = self._make_link()
         self.total_loss = None
         self.fwd_losses = []
@@ -161,7 +181,10 @@ class PipelineEngine:
         self.total_loss = None
         self.fwd_losses = []
         self._data_iter = data_iter
-        sched = TrainSchedule(self.micro_batches, self.num_stages, self.stage_id)
+        if self.pipeline_schedule == 'zb':
+            sched = ZeroBubbleSchedule(self.micro_batches, self.num_stages, self.stage_id, self.zb_costs, self.zb_max_inflight)
+        else:
+            sched = TrainSchedule(self.micro_batches, self.num_stages, self.stage_id)
         self._reserve_buffers(sched.num_pipe_buffers())
         self._exec_schedule(sched, train=True)
         self.global_steps += 1
@@ -239,6 +262,21 @@ class PipelineEngine:
             self.pipe_buffers['inputs'][b] = None
             if self.is_last_stage() and not self.is_first_stage() and hasattr(self.link, 'release_activations'):
                 self.link.release_activations(b, cmd.micro_batch_id)
+
+    def _exec_backward_input(self, cmd, train):
+        """split backward: weight-gradient work of the layers that support it is queued instead of launched"""
+        from .. import ops
+        q = []
+        ops.WGRAD_DEFER = q
+        try:
+            self._exec_backward_pass(cmd, train)
+        finally:
+            ops.WGRAD_DEFER = None
+        self._wgrad_queues[cmd.micro_batch_id] = q
+
+    def _exec_backward_weight(self, cmd, train):
+        for fn in self._wgrad_queues.pop(cmd.micro_batch_id, ()):
+            fn()
 
     def _exec_backward_pass(self, cmd, train):
         b = cmd.buffer_id
@@ -378,6 +416,8 @@ class PipelineEngine:
         LoadMicroBatch: _exec_load_micro_batch,
         ForwardPass: _exec_forward_pass,
         BackwardPass: _exec_backward_pass,
+        BackwardInput: _exec_backward_input,
+        BackwardWeight: _exec_backward_weight,
         SendActivation: _exec_send_activations,
         RecvActivation: _exec_recv_activations,
         SendGrad: _exec_send_grads,
@@ -470,7 +510,7 @@ def _dist_recv_activations(self, buf, mb):
 def _dist_send_grads(self, grads, buf, mb):
     dst = self.engine.grid.stage_to_global(self.engine.prev_stage)
     for g in grads:
-        dist.send(g.contiguous(), dst)
+        self._send(g.contiguous(), dst)
 
 
 def _dist_recv_grads(self, like, buf, mb):

@@ -243,7 +243,8 @@ class IpcLink:
         self.device = engine.device
         assert self.device.type == 'cuda'
         grid = engine.grid
-        self.nslots = max(2, engine.num_stages)
+        # 1F1B keeps at most `stages` micro-batches in flight on a stage; the zero-bubble order may hold 2x as many
+        self.nslots = max(2, engine.num_stages) * (2 if engine.pipeline_schedule == 'zb' else 1)
         self.copy_stream = torch.cuda.Stream(device=self.device)
         # host control plane: one gloo group per pipeline (every rank creates all of them, in the same order)
         self.ctrl_group = None

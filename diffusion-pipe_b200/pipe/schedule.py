@@ -73,24 +73,32 @@ class RecvGrad(BufferOpInstruction):
     pass
 
 
+class BackwardInput(BufferOpInstruction):
+    """split backward: input-gradient pass of one micro-batch (weight gradients are queued)"""
+
+
+class BackwardWeight(BufferOpInstruction):
+    """split backward: run the queued weight-gradient work of one micro-batch"""
+
+
 _OP_CLASSES = {1: LoadMicroBatch, 2: SendActivation, 3: RecvActivation, 4: SendGrad, 5: RecvGrad, 6: ForwardPass,
-               7: BackwardPass, 8: ReduceTiedGrads, 9: ReduceGrads, 10: OptimizerStep}
+               7: BackwardPass, 8: ReduceTiedGrads, 9: ReduceGrads, 10: OptimizerStep, 11: BackwardInput, 12: BackwardWeight}
 
 
-def _plan(fn_name, micro_batches, stages, stage_id):
+def _plan(fn_name, micro_batches, stages, stage_id, extra=()):
     lib = _lib.lib()
     fn = getattr(lib, fn_name)
-    n = fn(micro_batches, stages, stage_id, None, 0)
+    n = fn(micro_batches, stages, stage_id, *extra, None, 0)
     _lib.check(0 if n >= 0 else n, fn_name)
     buf = (_Instr * n)()
-    n2 = fn(micro_batches, stages, stage_id, buf, n)
+    n2 = fn(micro_batches, stages, stage_id, *extra, buf, n)
     _lib.check(0 if n2 == n else -1, fn_name)
     ticks, cur = [], []
     for ins in buf:
         if ins.op == 0:
             ticks.append(cur)
             cur = []
-        elif ins.op >= 8:
+        elif 8 <= ins.op <= 10:
             cur.append(_OP_CLASSES[ins.op]())
         else:
             cur.append(_OP_CLASSES[ins.op](ins.buffer, micro_batch_id=ins.micro_batch))
@@ -135,3 +143,26 @@ class InferenceSchedule(PipeSchedule):
 
     def num_pipe_buffers(self):
         return 2
+
+
+class ZeroBubbleSchedule(PipeSchedule):
+    """Split-backward schedule from the C++ list-scheduling planner (csrc/sched.cpp: dpipe_sched_zb).  Not in the
+    reference; loss-equivalent to TrainSchedule.  `costs` = relative (forward, input-grad, weight-grad) durations;
+    `max_inflight` = micro-batches a stage may hold between forward and input-grad (default 2 * stages: ZB-2p-like)."""
+
+    def __init__(self, micro_batches, stages, stage_id, costs=(13, 17, 10), max_inflight=None):
+        super().__init__(micro_batches, stages, stage_id)
+        self.costs = tuple(int(c) for c in costs)
+        self.max_inflight = int(max_inflight or 2 * stages)
+
+    def steps(self):
+        return _plan('dpipe_sched_zb', self.micro_batches, self.stages, self.stage_id, (*self.costs, self.max_inflight))
+
+    def num_pipe_buffers(self):
+        return self.micro_batches     # buffers are indexed by micro-batch id
+
+    def simulated_makespan(self):
+        v = _lib.lib().dpipe_sched_zb_makespan(self.micro_batches, self.stages, *self.costs, self.max_inflight)
+        if v < 0:
+            raise _lib.DpipeError(f'dpipe_sched_zb_makespan failed ({v})')
+        return v

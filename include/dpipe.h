@@ -199,7 +199,9 @@ enum {
   DPIPE_OP_BACKWARD_PASS = 7,
   DPIPE_OP_REDUCE_TIED_GRADS = 8,
   DPIPE_OP_REDUCE_GRADS = 9,
-  DPIPE_OP_OPTIMIZER_STEP = 10
+  DPIPE_OP_OPTIMIZER_STEP = 10,
+  DPIPE_OP_BACKWARD_INPUT = 11,  /* split backward: input gradients only (zero-bubble schedule) */
+  DPIPE_OP_BACKWARD_WEIGHT = 12  /* split backward: the deferred weight gradients of one micro-batch */
 };
 typedef struct dpipe_instr {
   int32_t op;          /* DPIPE_OP_* */
@@ -213,6 +215,13 @@ int dpipe_sched_num_pipe_buffers(int micro_batches, int stages, int stage_id);
 int dpipe_sched_train(int micro_batches, int stages, int stage_id, dpipe_instr* out, int capacity);
 /* forward-only schedule of eval_batch */
 int dpipe_sched_infer(int micro_batches, int stages, int stage_id, dpipe_instr* out, int capacity);
+/* split-backward ("zero-bubble") order for one stage from a deterministic list-scheduling simulation of all stages with
+ * relative costs tf / tb / tw (forward, input-gradient, weight-gradient) and at most max_inflight micro-batches in
+ * flight per stage.  Not in the reference; loss-equivalent to 1F1B.  Same calling convention as dpipe_sched_train. */
+int dpipe_sched_zb(int micro_batches, int stages, int stage_id, int tf, int tb, int tw, int max_inflight,
+                   dpipe_instr* out, int capacity);
+/* simulated makespan of that order in the same cost units (for tests / reporting); < 0 on error */
+long long dpipe_sched_zb_makespan(int micro_batches, int stages, int tf, int tb, int tw, int max_inflight);
 /* contiguous min-max partition of n layer weights into `parts` stages; bounds has parts+1 entries
  * (replaces DeepSpeed partition_balanced behind partition_method='parameters', train.py:81-90,606) */
 int dpipe_partition_balanced(const int64_t* weights, int n, int parts, int* bounds);

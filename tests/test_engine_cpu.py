@@ -27,7 +27,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, stages, outdir, partition):
+def _worker(rank, world, port, stages, outdir, partition, schedule='1f1b'):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
@@ -40,7 +40,8 @@ def _worker(rank, world, port, stages, outdir, partition):
                               manual_partition_split=[3] if partition == 'manual' else None, loss_fn=toy_model.loss_fn,
                               dynamic_shape=True, device=torch.device('cpu'))
     engine, _, _, _ = initialize(model=pm, config={'train_micro_batch_size_per_gpu': MBS, 'gradient_accumulation_steps': GAS,
-                                                   'gradient_clipping': 0.5, 'steps_per_print': 0, 'stage_link': 'dist'})
+                                                   'gradient_clipping': 0.5, 'steps_per_print': 0, 'stage_link': 'dist',
+                                                   'pipeline_schedule': schedule})
     params = [p for p in pm.parameters() if p.requires_grad]
     engine._configure_optimizer(lambda ps: torch.optim.SGD(ps, lr=0.1) if ps else None, params)
     dp_rank = engine.grid.get_data_parallel_rank()
@@ -79,16 +80,16 @@ def _reference(dp_world):
     return losses, norms, ev, sd
 
 
-def _run(world, stages, partition='uniform'):
+def _run(world, stages, partition='uniform', schedule='1f1b'):
     with tempfile.TemporaryDirectory() as d:
         port = _free_port()
         if world == 1:
-            _worker(0, 1, port, stages, d, partition)
+            _worker(0, 1, port, stages, d, partition, schedule)
             import torch.distributed as tdist
             if tdist.is_initialized():
                 tdist.destroy_process_group()
         else:
-            mp.spawn(_worker, args=(world, port, stages, d, partition), nprocs=world, join=True)
+            mp.spawn(_worker, args=(world, port, stages, d, partition, schedule), nprocs=world, join=True)
         return [torch.load(os.path.join(d, f'rank{r}.pt'), weights_only=False) for r in range(world)]
 
 
@@ -125,3 +126,9 @@ def test_data_parallel_world_2():
     res = _run(2, 1)
     assert [r['dp'] for r in res] == [0, 1]
     _check(res, 2)
+
+
+def test_zero_bubble_schedule_single_and_two_stages():
+    """the split-backward order changes when things run, not what is computed"""
+    _check(_run(1, 1, 'uniform', 'zb'), 1)
+    _check(_run(2, 2, 'manual', 'zb'), 1)
