@@ -44,6 +44,8 @@ def parse():
     ap.add_argument('--layers', type=str, default='19,38', help='double,single block counts (default = Flux-dev)')
     ap.add_argument('--no-optimizer', action='store_true', help='diagnostic: skip the optimizer step (INVALID as a bench value)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--schedule', default='auto', choices=['auto', '1f1b', 'zb'],
+                    help="pipeline order: the reference's 1F1B or the split-backward zero-bubble order (auto: zb when stages > 1)")
     ap.add_argument('--profile-kernels', action='store_true', default=True)
     return ap.parse_args()
 
@@ -241,7 +243,8 @@ def main():
                               manual_partition_split=split if stages > 1 else None, loss_fn=model.get_loss_fn(),
                               dynamic_shape=True)
     engine, _, _, _ = initialize(model=pm, config={'train_micro_batch_size_per_gpu': mbs, 'gradient_accumulation_steps': M,
-                                                   'gradient_clipping': 1.0, 'steps_per_print': 0})
+                                                   'gradient_clipping': 1.0, 'steps_per_print': 0,
+                                                   'pipeline_schedule': ('zb' if stages > 1 else '1f1b') if a.schedule == 'auto' else a.schedule})
     params = [p for p in pm.parameters() if p.requires_grad]
     if not a.no_optimizer:
         engine._configure_optimizer(lambda ps: torch.optim.AdamW(ps, lr=1e-5, betas=(0.9, 0.99), weight_decay=0.01,
@@ -376,7 +379,7 @@ def main():
                        'activation_recompute': False, 'train_tflop_per_sample': TRAIN_TFLOP_PER_SAMPLE,
                        'optimizer': 'none (diagnostic)' if a.no_optimizer else 'torch.optim.AdamW(fused) bf16, clip 1.0',
                        'l2_flush': 'working set (>=24 GB of weights+grads per step) is far larger than the 126 MB L2',
-                       'stage_link': type(engine.link).__name__},
+                       'stage_link': type(engine.link).__name__, 'pipeline_schedule': engine.pipeline_schedule},
             'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                     'ms_per_step': ms_e2e / a.steps},
             'gpu_launches': int(lt.item()),

@@ -501,7 +501,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
 //   dkv TMEM: St[2] 2x64 | dPt[2] 2x64 | dV 128 | dK 128          dq TMEM: S[2] 2x64 | dP[2] 2x64 | dQ 128
 // bf16 P / dS for the 32 columns a warp owns are written over the first 16 of those same columns.
 // =============================================================================================
-__device__ __forceinline__ uint32_t packed_col64(int kstep) { return (kstep >> 1) * 32 + (kstep & 1) * 8; }
 
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
@@ -514,7 +513,6 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   uint8_t* q_smem = smem + 2 * BTILE;   // 2 stages of [128 q][128 d]
   uint8_t* do_smem = smem + 4 * BTILE;  // 2 stages
   float* lse_smem = reinterpret_cast<float*>(smem + 6 * BTILE);  // [2][128]
-  float* dl_smem = lse_smem + 256;                               // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * BTILE + 4 * 512);
   uint64_t* kv_full = bars;        // [1]
   uint64_t* q_full = bars + 1;     // [2]
@@ -544,7 +542,7 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       mbar_init(smem_u32(&q_full[s]), 1); mbar_init(smem_u32(&q_empty[s]), 1);
       mbar_init(smem_u32(&do_full[s]), 1); mbar_init(smem_u32(&do_empty[s]), 1);
       mbar_init(smem_u32(&sd_full[s]), 1);
-      mbar_init(smem_u32(&p_ready[s]), 8); mbar_init(smem_u32(&ds_ready[s]), 8);
+      mbar_init(smem_u32(&p_ready[s]), 4); mbar_init(smem_u32(&ds_ready[s]), 4);   // one softmax warpgroup per buffer
     }
     mbar_init(smem_u32(acc_done), 1);
     fence_barrier_init();
@@ -617,58 +615,68 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // dV[kv, d] += Pt[kv, 64 q] dO[64 q, d]
-          umma_ts(T_DV, T_ST + buf * 64 + packed_col64(k), make_smem_desc(dob + k * 2048, BHALF, 1024), idesc_g, (t | k) != 0);
+          umma_ts(T_DV, T_ST + buf * 64 + k * 8, make_smem_desc(dob + k * 2048, BHALF, 1024), idesc_g, (t | k) != 0);
         if (t & 1) umma_commit<1>(smem_u32(&do_empty[stage]));
         mbar_wait(smem_u32(&ds_ready[buf]), rph);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // dK[kv, d] += dSt[kv, 64 q] Q[64 q, d]
-          umma_ts(T_DK, T_DPT + buf * 64 + packed_col64(k), make_smem_desc(qb + k * 2048, BHALF, 1024), idesc_g, (t | k) != 0);
+          umma_ts(T_DK, T_DPT + buf * 64 + k * 8, make_smem_desc(qb + k * 2048, BHALF, 1024), idesc_g, (t | k) != 0);
         if (t & 1) umma_commit<1>(smem_u32(&q_empty[stage]));
       }
       umma_commit<1>(smem_u32(acc_done));
     }
   } else if (warp >= 4) {
+    // Warpgroup wg (warps 4-7 / 8-11) owns TMEM buffer wg and therefore every sub-tile t with t % 2 == wg: the two
+    // warpgroups work on different sub-tiles at any time, so their TMEM waits and MUFU bursts interleave.
     const uint32_t quad = warp & 3;
-    const int half = (warp - 4) >> 2;          // which 32 of the 64 sub-tile columns this warp owns
-    const int sm_tid = (warp - 4) * 32 + lane;
+    const int wg = (warp - 4) >> 2;
+    const int wg_tid = ((warp - 4) & 3) * 32 + lane;   // 0..127 inside the warpgroup
     const uint32_t lane_base = (quad * 32u) << 16;
     const float c = p.scale_log2;
-    for (int t = 0; t < nsub; ++t) {
-      const int j = t >> 1, st = j & 1;
-      const uint32_t buf = t & 1, rph = (t >> 1) & 1;
-      if ((t & 1) == 0) {   // stage LSE / D of the 128-row query tile (invalid queries: +inf -> P = 0)
-        const int tt = sm_tid & 127;
-        const int q = j * BT + tt;
-        if (sm_tid < 128) lse_smem[st * 128 + tt] = (q < p.seq_q) ? p.lse[(int64_t)bh * p.seq_q + q] : INFINITY;
-        else dl_smem[st * 128 + tt] = (q < p.seq_q) ? p.delta[(int64_t)bh * p.seq_q + q] : 0.f;
-        named_bar_sync(1, 256);
+    float* lse_s = lse_smem + wg * 128;                // [64] LSE then [64] D of the current sub-tile
+    float* dl_s = lse_s + 64;
+    const uint32_t buf = wg;
+    for (int t = wg, it = 0; t < nsub; t += 2, ++it) {
+      const uint32_t rph = it & 1;
+      {   // stage LSE / D of the 64 query rows of this sub-tile (rows beyond seq_q: +inf -> P = 0)
+        const int q = t * 64 + (wg_tid & 63);
+        named_bar_sync(1 + wg, 128);                   // previous sub-tile's readers are done
+        if (wg_tid < 64) lse_s[wg_tid] = (q < p.seq_q) ? p.lse[(int64_t)bh * p.seq_q + q] : INFINITY;
+        else dl_s[wg_tid - 64] = (q < p.seq_q) ? p.delta[(int64_t)bh * p.seq_q + q] : 0.f;
+        named_bar_sync(1 + wg, 128);
       }
-      const float* lse_s = lse_smem + st * 128 + (t & 1) * 64 + half * 32;
-      const float* dl_s = dl_smem + st * 128 + (t & 1) * 64 + half * 32;
       mbar_wait(smem_u32(&sd_full[buf]), rph);
       tc_fence_after();
-      uint32_t r[32], pk[16];
-      float pv[32];
-      tmem_ld_x32(T_ST + lane_base + buf * 64 + half * 32, r);
-      tmem_ld_wait();
+      float pv[64];
 #pragma unroll
-      for (int x = 0; x < 32; x += 2) {
-        pv[x] = fast_exp2(fmaf(__uint_as_float(r[x]), c, -lse_s[x]));
-        pv[x + 1] = fast_exp2(fmaf(__uint_as_float(r[x + 1]), c, -lse_s[x + 1]));
-        pk[x >> 1] = pack_bf16(pv[x], pv[x + 1]);
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32], pk[16];
+        tmem_ld_x32(T_ST + lane_base + buf * 64 + hh * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int x = 0; x < 32; x += 2) {
+          pv[hh * 32 + x] = fast_exp2(fmaf(__uint_as_float(r[x]), c, -lse_s[hh * 32 + x]));
+          pv[hh * 32 + x + 1] = fast_exp2(fmaf(__uint_as_float(r[x + 1]), c, -lse_s[hh * 32 + x + 1]));
+          pk[x >> 1] = pack_bf16(pv[hh * 32 + x], pv[hh * 32 + x + 1]);
+        }
+        tmem_st_x16(T_ST + lane_base + buf * 64 + hh * 16, pk);   // packed P over columns this thread has already read
       }
-      tmem_st_x16(T_ST + lane_base + buf * 64 + half * 32, pk);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&p_ready[buf]));
-      tmem_ld_x32(T_DPT + lane_base + buf * 64 + half * 32, r);
-      tmem_ld_wait();
 #pragma unroll
-      for (int x = 0; x < 32; x += 2)
-        pk[x >> 1] = pack_bf16(pv[x] * (__uint_as_float(r[x]) - dl_s[x]), pv[x + 1] * (__uint_as_float(r[x + 1]) - dl_s[x + 1]));
-      tmem_st_x16(T_DPT + lane_base + buf * 64 + half * 32, pk);
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32], pk[16];
+        tmem_ld_x32(T_DPT + lane_base + buf * 64 + hh * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int x = 0; x < 32; x += 2)
+          pk[x >> 1] = pack_bf16(pv[hh * 32 + x] * (__uint_as_float(r[x]) - dl_s[hh * 32 + x]),
+                                 pv[hh * 32 + x + 1] * (__uint_as_float(r[x + 1]) - dl_s[hh * 32 + x + 1]));
+        tmem_st_x16(T_DPT + lane_base + buf * 64 + hh * 16, pk);
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -748,7 +756,7 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
       mbar_init(smem_u32(&k_full[s]), 1); mbar_init(smem_u32(&k_empty[s]), 1);
       mbar_init(smem_u32(&v_full[s]), 1); mbar_init(smem_u32(&v_empty[s]), 1);
       mbar_init(smem_u32(&sd_full[s]), 1);
-      mbar_init(smem_u32(&ds_ready[s]), 8);
+      mbar_init(smem_u32(&ds_ready[s]), 4);
     }
     mbar_init(smem_u32(acc_done), 1);
     fence_barrier_init();
@@ -820,38 +828,43 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // dQ[q, d] += dS[q, 64 kv] K[64 kv, d]
-          umma_ts(T_DQ, T_DP + buf * 64 + packed_col64(k), make_smem_desc(kb + k * 2048, BHALF, 1024), idesc_g, (t | k) != 0);
+          umma_ts(T_DQ, T_DP + buf * 64 + k * 8, make_smem_desc(kb + k * 2048, BHALF, 1024), idesc_g, (t | k) != 0);
         if (t & 1) umma_commit<1>(smem_u32(&k_empty[stage]));
       }
       umma_commit<1>(smem_u32(acc_done));
     }
   } else if (warp >= 4) {
     const uint32_t quad = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int wg = (warp - 4) >> 2;          // warpgroup wg owns TMEM buffer wg, i.e. key sub-tiles t with t % 2 == wg
+    const int half = wg;                     // (epilogue: which 64 output columns this warp stores)
     const uint32_t lane_base = (quad * 32u) << 16;
     const int q = q0 + quad * 32 + lane;
     const bool ok = q < p.seq_q;
     const float lse = ok ? p.lse[(int64_t)bh * p.seq_q + q] : INFINITY;
     const float dl = ok ? p.delta[(int64_t)bh * p.seq_q + q] : 0.f;
     const float c = p.scale_log2;
-    for (int t = 0; t < nsub; ++t) {
-      const uint32_t buf = t & 1, rph = (t >> 1) & 1;
-      const int valid = p.seq_k - t * 64 - half * 32;   // keys of this warp's 32 columns that exist (may be <= 0)
+    const uint32_t buf = wg;
+    for (int t = wg, it = 0; t < nsub; t += 2, ++it) {
+      const uint32_t rph = it & 1;
+      const int valid = p.seq_k - t * 64;    // keys of this sub-tile that exist (may be <= 0 or >= 64)
       mbar_wait(smem_u32(&sd_full[buf]), rph);
       tc_fence_after();
-      uint32_t r[32], rd[32], pk[16];
-      tmem_ld_x32(T_S + lane_base + buf * 64 + half * 32, r);
-      tmem_ld_x32(T_DP + lane_base + buf * 64 + half * 32, rd);
-      tmem_ld_wait();
 #pragma unroll
-      for (int x = 0; x < 32; x += 2) {
-        float p0 = fast_exp2(fmaf(__uint_as_float(r[x]), c, -lse));
-        float p1 = fast_exp2(fmaf(__uint_as_float(r[x + 1]), c, -lse));
-        if (x >= valid) p0 = 0.f;
-        if (x + 1 >= valid) p1 = 0.f;
-        pk[x >> 1] = pack_bf16(p0 * (__uint_as_float(rd[x]) - dl), p1 * (__uint_as_float(rd[x + 1]) - dl));
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32], rd[32], pk[16];
+        tmem_ld_x32(T_S + lane_base + buf * 64 + hh * 32, r);
+        tmem_ld_x32(T_DP + lane_base + buf * 64 + hh * 32, rd);
+        tmem_ld_wait();
+#pragma unroll
+        for (int x = 0; x < 32; x += 2) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(r[x]), c, -lse));
+          float p1 = fast_exp2(fmaf(__uint_as_float(r[x + 1]), c, -lse));
+          if (hh * 32 + x >= valid) p0 = 0.f;
+          if (hh * 32 + x + 1 >= valid) p1 = 0.f;
+          pk[x >> 1] = pack_bf16(p0 * (__uint_as_float(rd[x]) - dl), p1 * (__uint_as_float(rd[x + 1]) - dl));
+        }
+        tmem_st_x16(T_DP + lane_base + buf * 64 + hh * 16, pk);
       }
-      tmem_st_x16(T_DP + lane_base + buf * 64 + half * 32, pk);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();

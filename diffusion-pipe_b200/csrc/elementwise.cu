@@ -279,7 +279,7 @@ __global__ void colreduce_finish_kernel(const float* __restrict__ partials, int 
 // One warp walks the tokens of one (sample, head, which in {q,k,v}) slice; each lane owns 4 of the 128 channels.
 // grid (ceil(rows_per_batch / TOK_PER_WARP / warps), heads*3, batch)
 // ---------------------------------------------------------------------------------------------
-constexpr int QK_TOK_PER_WARP = 64;
+constexpr int QK_TOK_PER_WARP = 128;
 struct QkBwdParams {
   const __nv_bfloat16 *dq, *dk, *dv;      // [B,H,seq_total,128]
   const __nv_bfloat16 *qhat, *khat;       // [B,H,seq_total,128]
@@ -296,9 +296,9 @@ __global__ void qknorm_rope_bwd_kernel(const QkBwdParams p) {
   const int wglobal = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int head = blockIdx.y % p.heads, which = blockIdx.y / p.heads;
   const int b = blockIdx.z;
-  const int t0 = wglobal * QK_TOK_PER_WARP;
-  if (t0 >= p.rows_per_batch) return;
-  const int t1 = min(t0 + QK_TOK_PER_WARP, p.rows_per_batch);
+  __shared__ float cta_sum[4][2][128];   // per-warp partial column sums, folded before touching global atomics
+  const int t0 = min(wglobal * QK_TOK_PER_WARP, p.rows_per_batch);
+  const int t1 = min(t0 + QK_TOK_PER_WARP, p.rows_per_batch);   // (possibly empty: the warp still joins the reduction)
   const int c0 = lane * 4;
   const __nv_bfloat16* src = which == 0 ? p.dq : (which == 1 ? p.dk : p.dv);
   const int64_t hb = ((int64_t)b * p.heads + head) * p.seq_total;
@@ -376,10 +376,17 @@ __global__ void qknorm_rope_bwd_kernel(const QkBwdParams p) {
       *reinterpret_cast<uint2*>(p.dqkv + ((int64_t)b * p.rows_per_batch + t) * p.ld + (which * p.heads + head) * 128 + c0) = ov;
     }
   }
+  const int wid = threadIdx.x >> 5;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    atomicAdd(p.dbias + (which * p.heads + head) * 128 + c0 + j, bsum[j]);
-    if (which < 2) atomicAdd(p.dw + which * 128 + c0 + j, wsum[j]);
+  for (int j = 0; j < 4; ++j) { cta_sum[wid][0][c0 + j] = bsum[j]; cta_sum[wid][1][c0 + j] = wsum[j]; }
+  __syncthreads();
+  // 256 threads-worth of sums (2 x 128): every thread of the CTA folds one or two entries over the 4 warps
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    const int kind = i >> 7, c = i & 127;
+    float v = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += cta_sum[w][kind][c];
+    if (kind == 0) atomicAdd(p.dbias + (which * p.heads + head) * 128 + c, v);
+    else if (which < 2) atomicAdd(p.dw + which * 128 + c, v);
   }
 }
 

@@ -39,7 +39,7 @@ def _batches(step):
     return out
 
 
-def _worker(rank, world, port, link, outdir):
+def _worker(rank, world, port, link, outdir, schedule='1f1b'):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1',
                       MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
@@ -54,7 +54,8 @@ def _worker(rank, world, port, link, outdir):
     pm = ManualPipelineModule(layers=model.to_layers(), num_stages=world, partition_method='manual' if world > 1 else 'uniform',
                               manual_partition_split=[3] if world > 1 else None, loss_fn=model.get_loss_fn(), dynamic_shape=True)
     engine, _, _, _ = initialize(model=pm, config={'train_micro_batch_size_per_gpu': 1, 'gradient_accumulation_steps': GAS,
-                                                   'gradient_clipping': 1.0, 'steps_per_print': 0, 'stage_link': link})
+                                                   'gradient_clipping': 1.0, 'steps_per_print': 0, 'stage_link': link,
+                                                   'pipeline_schedule': schedule})
     engine._configure_optimizer(lambda ps: torch.optim.SGD(ps, lr=0.02), [p for p in pm.parameters()])
     losses = []
     for step in range(3):
@@ -68,10 +69,10 @@ def _worker(rank, world, port, link, outdir):
         dist.barrier()
 
 
-def _run(world, link):
+def _run(world, link, schedule='1f1b'):
     with tempfile.TemporaryDirectory() as d:
         port = _free_port()
-        mp.spawn(_worker, args=(world, port, link, d), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, link, d, schedule), nprocs=world, join=True)
         return [torch.load(os.path.join(d, f'r{r}.pt'), weights_only=False) for r in range(world)]
 
 
@@ -85,3 +86,16 @@ def test_two_stage_pipeline_matches_single_stage(link):
         assert r['losses'] == pytest.approx(base['losses'], rel=2e-3), (r['losses'], base['losses'])
         assert r['eval'] == pytest.approx(base['eval'], rel=2e-3)
     assert res[0]['losses'] == res[1]['losses']     # the loss is broadcast to every stage
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+@pytest.mark.parametrize('link', ['ipc', 'dist'])
+def test_zero_bubble_schedule_matches_single_stage(link):
+    """split backward (deferred weight gradients) + one-sided sends: same losses as the fused 1-stage run"""
+    base = _run(1, 'dist')[0]
+    zb1 = _run(1, 'dist', 'zb')[0]                       # deferral alone, no pipeline
+    assert zb1['losses'] == pytest.approx(base['losses'], rel=1e-6)
+    res = _run(2, link, 'zb')
+    for r in res:
+        assert r['losses'] == pytest.approx(base['losses'], rel=2e-3), (r['losses'], base['losses'])
+        assert r['eval'] == pytest.approx(base['eval'], rel=2e-3)
