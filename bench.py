@@ -309,8 +309,10 @@ def main():
     value = samples_per_step * a.steps / (ms_dev / 1000.0)
     e2e_value = samples_per_step * a.steps / (ms_e2e / 1000.0)
     lt = torch.tensor([launches], device=device, dtype=torch.float64)
+    mem_t = torch.tensor([torch.cuda.max_memory_allocated(device) / 2**30], device=device, dtype=torch.float64)
     if world > 1:
         tdist.all_reduce(lt)
+        tdist.all_reduce(mem_t, op=tdist.ReduceOp.MAX)
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): algorithmic 2MNK per launch / CUDA-event duration ----
     roof = None
@@ -384,6 +386,7 @@ def main():
                     'ms_per_step': ms_e2e / a.steps},
             'gpu_launches': int(lt.item()),
             'loss': loss_dev,
+            'peak_mem_gib_max_rank': round(float(mem_t.item()), 1),
             'clocks': clk,
         }
         if roof:

@@ -166,8 +166,9 @@ extern "C" int dpipe_partition_balanced(const int64_t* weights, int n, int parts
 //   W = weight-gradient pass (no consumer on another stage),
 // so W work can fill what would be pipeline bubbles (Qi et al., "Zero Bubble Pipeline Parallelism", ZB-H1/ZB-2p).
 // The order is produced by a deterministic list-scheduling simulation of ALL stages with the given relative costs
-// (tf, tb, tw): whenever a stage becomes free it runs, in priority order, the oldest ready B, else the next F if fewer
-// than `max_inflight` micro-batches are in flight on it, else a pending W; it idles only when nothing is ready.  Every
+// (tf, tb, tw): whenever a stage becomes free it runs, in priority order, the oldest ready B, else the next F if it holds fewer
+// than `max_inflight` micro-batches (forward done, weight-gradient pass not yet done: that is what pins activation and
+// output-gradient memory), else a pending W; it idles only when nothing is ready.  Every
 // rank runs the same simulation, so all stages agree on the global order without communication.
 // Needs a one-sided stage link (IpcLink) or asynchronous sends: a stage pushes activations right after F and gradients
 // right after B, whenever the neighbour will get to them.
@@ -197,13 +198,13 @@ extern "C" int dpipe_sched_zb(int micro_batches, int stages, int stage_id, int t
     auto b_ready = [&](int m) { return s == S - 1 ? fin_f[(size_t)s * M + m] : fin_b[(size_t)(s + 1) * M + m]; };
     int op = 0, m = -1;   // 1 = F, 2 = B, 3 = W
     if (a.nb < M && a.nb < a.nf && b_ready(a.nb) <= now) { op = 2; m = a.nb; }
-    else if (a.nf < M && (a.nf - a.nb) < max_inflight && f_ready(a.nf) <= now) { op = 1; m = a.nf; }
+    else if (a.nf < M && (a.nf - a.nw) < max_inflight && f_ready(a.nf) <= now) { op = 1; m = a.nf; }
     else if (a.nw < a.nb) { op = 3; m = a.nw; }
     if (op == 0) {
       // nothing ready: sleep until the next point in time at which something can have changed
       long long next = INF;
       if (a.nb < M && a.nb < a.nf && b_ready(a.nb) < INF) next = b_ready(a.nb);
-      if (a.nf < M && (a.nf - a.nb) < max_inflight && f_ready(a.nf) < INF && f_ready(a.nf) < next) next = f_ready(a.nf);
+      if (a.nf < M && (a.nf - a.nw) < max_inflight && f_ready(a.nf) < INF && f_ready(a.nf) < next) next = f_ready(a.nf);
       if (next == INF || next <= now) {
         for (int i = 0; i < S; ++i)
           if (i != s && !st[i].done && st[i].free_at > now && st[i].free_at < next) next = st[i].free_at;

@@ -148,7 +148,8 @@ class InferenceSchedule(PipeSchedule):
 class ZeroBubbleSchedule(PipeSchedule):
     """Split-backward schedule from the C++ list-scheduling planner (csrc/sched.cpp: dpipe_sched_zb).  Not in the
     reference; loss-equivalent to TrainSchedule.  `costs` = relative (forward, input-grad, weight-grad) durations;
-    `max_inflight` = micro-batches a stage may hold between forward and input-grad (default 2 * stages: ZB-2p-like)."""
+    `max_inflight` = micro-batches a stage may hold between forward and weight-grad pass, i.e. the bound on
+    activation memory (default 2 * stages: ZB-2p-like)."""
 
     def __init__(self, micro_batches, stages, stage_id, costs=(13, 17, 10), max_inflight=None):
         super().__init__(micro_batches, stages, stage_id)

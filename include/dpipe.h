@@ -216,8 +216,8 @@ int dpipe_sched_train(int micro_batches, int stages, int stage_id, dpipe_instr* 
 /* forward-only schedule of eval_batch */
 int dpipe_sched_infer(int micro_batches, int stages, int stage_id, dpipe_instr* out, int capacity);
 /* split-backward ("zero-bubble") order for one stage from a deterministic list-scheduling simulation of all stages with
- * relative costs tf / tb / tw (forward, input-gradient, weight-gradient) and at most max_inflight micro-batches in
- * flight per stage.  Not in the reference; loss-equivalent to 1F1B.  Same calling convention as dpipe_sched_train. */
+ * relative costs tf / tb / tw (forward, input-gradient, weight-gradient) and at most max_inflight micro-batches held
+ * per stage (forward done, weight-gradient pass pending).  Not in the reference; loss-equivalent to 1F1B.  Same calling convention as dpipe_sched_train. */
 int dpipe_sched_zb(int micro_batches, int stages, int stage_id, int tf, int tb, int tw, int max_inflight,
                    dpipe_instr* out, int capacity);
 /* simulated makespan of that order in the same cost units (for tests / reporting); < 0 on error */
