@@ -54,6 +54,29 @@ class QkBwdArgs(ctypes.Structure):
     ]
 
 
+class WanNormProj(ctypes.Structure):
+    _fields_ = [('src', c_void_p), ('ld', c_int64), ('weight', c_void_p), ('dst', c_void_p), ('xhat', c_void_p),
+                ('rstd', c_void_p), ('rope', c_int)]
+
+
+class WanNormFwdArgs(ctypes.Structure):
+    _fields_ = [('proj', WanNormProj * 3), ('nproj', c_int), ('cos', c_void_p), ('sin', c_void_p),
+                ('batch', c_int), ('seq', c_int), ('heads', c_int), ('eps', c_float)]
+
+
+class WanNormBwdProj(ctypes.Structure):
+    _fields_ = [('dy', c_void_p), ('xhat', c_void_p), ('rstd', c_void_p), ('weight', c_void_p), ('dx', c_void_p),
+                ('ld', c_int64), ('dw_partials', c_void_p), ('rope', c_int)]
+
+
+class WanNormBwdArgs(ctypes.Structure):
+    _fields_ = [('proj', WanNormBwdProj * 3), ('nproj', c_int), ('cos', c_void_p), ('sin', c_void_p),
+                ('batch', c_int), ('seq', c_int), ('heads', c_int)]
+
+
+SIGNATURES['dpipe_wan_norm_rope_fwd'] = (c_int, [ctypes.POINTER(WanNormFwdArgs), c_void_p])
+SIGNATURES['dpipe_wan_norm_rope_bwd'] = (c_int, [ctypes.POINTER(WanNormBwdArgs), c_void_p])
+SIGNATURES['dpipe_wan_norm_rows'] = (c_int, [])
 SIGNATURES['dpipe_attn_fwd'] = (c_int, [ctypes.POINTER(AttnArgs), c_void_p])
 SIGNATURES['dpipe_attn_bwd'] = (c_int, [ctypes.POINTER(AttnBwdArgs), c_void_p])
 SIGNATURES['dpipe_row_chunk'] = (c_int, [])
@@ -62,6 +85,11 @@ SIGNATURES['dpipe_ln_modulate_fwd'] = (c_int, [c_void_p, c_int64, c_void_p, c_vo
 SIGNATURES['dpipe_ln_modulate_bwd'] = (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                                c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int,
                                                c_int, c_void_p])
+SIGNATURES['dpipe_ln_modulate_fwd_ex'] = (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                                  c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p])
+SIGNATURES['dpipe_ln_modulate_bwd_ex'] = (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                                  c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int,
+                                                  c_int, c_int, c_void_p])
 SIGNATURES['dpipe_gate_bwd'] = (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                                         c_void_p, c_int, c_int, c_int, c_void_p])
 SIGNATURES['dpipe_colreduce_finish'] = (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_void_p,
@@ -74,6 +102,8 @@ SIGNATURES['dpipe_sched_train'] = (c_int, [c_int, c_int, c_int, c_void_p, c_int]
 SIGNATURES['dpipe_sched_infer'] = (c_int, [c_int, c_int, c_int, c_void_p, c_int])
 SIGNATURES['dpipe_sched_zb'] = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int])
 SIGNATURES['dpipe_sched_zb_makespan'] = (ctypes.c_longlong, [c_int, c_int, c_int, c_int, c_int, c_int])
+SIGNATURES['dpipe_sched_zb_ex'] = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int])
+SIGNATURES['dpipe_sched_zb_makespan_ex'] = (ctypes.c_longlong, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p])
 SIGNATURES['dpipe_partition_balanced'] = (c_int, [c_void_p, c_int, c_int, c_void_p])
 SIGNATURES['dpipe_ipc_alloc'] = (c_int, [c_int64, ctypes.POINTER(c_void_p), c_void_p])
 SIGNATURES['dpipe_ipc_open'] = (c_int, [c_void_p, ctypes.POINTER(c_void_p)])

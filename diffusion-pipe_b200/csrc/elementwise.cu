@@ -60,7 +60,7 @@ __global__ void ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, int6
                                        const __nv_bfloat16* __restrict__ scale, const __nv_bfloat16* __restrict__ shift,
                                        int64_t mod_stride, __nv_bfloat16* __restrict__ out, int64_t ldo,
                                        float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows_per_batch,
-                                       int D, float eps) {
+                                       int D, float eps, int flags) {
   __shared__ float red[32 * RG];
   const int b = blockIdx.y;
   const int r0 = blockIdx.x * RG;
@@ -93,16 +93,24 @@ __global__ void ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, int6
   float sc[8], sh[8];
   unpack8(*reinterpret_cast<const uint4*>(scale + (int64_t)b * mod_stride + col), sc);
   unpack8(*reinterpret_cast<const uint4*>(shift + (int64_t)b * mod_stride + col), sh);
+  if (!(flags & DPIPE_LN_MULT_DIRECT)) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) sc[j] = bf16_round(1.0f + sc[j]);  // (1 + scale) is formed in bf16 by the reference
+    for (int j = 0; j < 8; ++j) sc[j] = bf16_round(1.0f + sc[j]);  // (1 + scale) is formed in bf16 by the reference
+  }
+  const bool steps = flags & DPIPE_LN_ROUND_STEPS;
 #pragma unroll
   for (int i = 0; i < RG; ++i) {
     const int r = r0 + i;
     if (r >= rows_per_batch) continue;
     const float rstd = rsqrtf(var[i] / D + eps);
     float o[8];
+    if (steps) {   // every elementwise op of the reference yields a bf16 tensor (Wan: norm(x) * (1 + e1) + e0)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = (xv[i][j] - mean[i]) * rstd * sc[j] + sh[j];
+      for (int j = 0; j < 8; ++j) o[j] = bf16_round(bf16_round((xv[i][j] - mean[i]) * rstd) * sc[j]) + sh[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (xv[i][j] - mean[i]) * rstd * sc[j] + sh[j];
+    }
     const int64_t row = (int64_t)b * rows_per_batch + r;
     *reinterpret_cast<uint4*>(out + row * ldo + col) = pack8(o);
     if (threadIdx.x == 0 && mean_out) { mean_out[row] = mean[i]; rstd_out[row] = rstd; }
@@ -118,14 +126,16 @@ __global__ void ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, in
                                        const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                        const __nv_bfloat16* __restrict__ dres, int64_t lddres,
                                        __nv_bfloat16* __restrict__ dx, int64_t lddx, float* __restrict__ partials,
-                                       int rows_per_batch, int D) {
+                                       int rows_per_batch, int D, int flags) {
   __shared__ float red[32 * 2 * RG];
   const int b = blockIdx.y;
   const int col = threadIdx.x * 8;
   float sc[8];
   unpack8(*reinterpret_cast<const uint4*>(scale + (int64_t)b * mod_stride + col), sc);
+  if (!(flags & DPIPE_LN_MULT_DIRECT)) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) sc[j] = bf16_round(1.0f + sc[j]);
+    for (int j = 0; j < 8; ++j) sc[j] = bf16_round(1.0f + sc[j]);
+  }
   float acc_scale[8], acc_shift[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { acc_scale[j] = 0.f; acc_shift[j] = 0.f; }
@@ -434,13 +444,19 @@ extern "C" int dpipe_row_chunk(void) { return ROW_CHUNK; }
 extern "C" int dpipe_ln_modulate_fwd(const void* x, int64_t ldx, const void* scale, const void* shift, int64_t mod_stride,
                                      void* out, int64_t ldo, float* mean, float* rstd, int batch, int rows_per_batch, int D,
                                      float eps, void* stream) {
+  return dpipe_ln_modulate_fwd_ex(x, ldx, scale, shift, mod_stride, out, ldo, mean, rstd, batch, rows_per_batch, D, eps, 0, stream);
+}
+
+extern "C" int dpipe_ln_modulate_fwd_ex(const void* x, int64_t ldx, const void* scale, const void* shift, int64_t mod_stride,
+                                        void* out, int64_t ldo, float* mean, float* rstd, int batch, int rows_per_batch, int D,
+                                        float eps, int flags, void* stream) {
   int rc = check_cols("dpipe_ln_modulate_fwd", D);
   if (rc) return rc;
   if (!x || !scale || !shift || !out) return fail(DPIPE_EINVAL, "dpipe_ln_modulate_fwd: null pointer");
   if (ldx % 8 || ldo % 8 || mod_stride % 8) return fail(DPIPE_EINVAL, "dpipe_ln_modulate_fwd: strides must be multiples of 8");
   dim3 grid((rows_per_batch + RG - 1) / RG, batch);
   ln_modulate_fwd_kernel<<<grid, D / 8, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)scale, (const bf16*)shift,
-                                                                    mod_stride, (bf16*)out, ldo, mean, rstd, rows_per_batch, D, eps);
+                                                                    mod_stride, (bf16*)out, ldo, mean, rstd, rows_per_batch, D, eps, flags);
   DPIPE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -449,13 +465,21 @@ extern "C" int dpipe_ln_modulate_bwd(const void* dxn, int64_t lddxn, const void*
                                      int64_t mod_stride, const float* mean, const float* rstd, const void* dres,
                                      int64_t lddres, void* dx, int64_t lddx, float* partials, int batch, int rows_per_batch,
                                      int D, void* stream) {
+  return dpipe_ln_modulate_bwd_ex(dxn, lddxn, x, ldx, scale, mod_stride, mean, rstd, dres, lddres, dx, lddx, partials, batch,
+                                  rows_per_batch, D, 0, stream);
+}
+
+extern "C" int dpipe_ln_modulate_bwd_ex(const void* dxn, int64_t lddxn, const void* x, int64_t ldx, const void* scale,
+                                        int64_t mod_stride, const float* mean, const float* rstd, const void* dres,
+                                        int64_t lddres, void* dx, int64_t lddx, float* partials, int batch, int rows_per_batch,
+                                        int D, int flags, void* stream) {
   int rc = check_cols("dpipe_ln_modulate_bwd", D);
   if (rc) return rc;
   if (!dxn || !x || !scale || !mean || !rstd || !dx || !partials) return fail(DPIPE_EINVAL, "dpipe_ln_modulate_bwd: null pointer");
   dim3 grid((rows_per_batch + ROW_CHUNK - 1) / ROW_CHUNK, batch);
   ln_modulate_bwd_kernel<<<grid, D / 8, 0, (cudaStream_t)stream>>>((const bf16*)dxn, lddxn, (const bf16*)x, ldx, (const bf16*)scale,
                                                                     mod_stride, mean, rstd, (const bf16*)dres, lddres, (bf16*)dx,
-                                                                    lddx, partials, rows_per_batch, D);
+                                                                    lddx, partials, rows_per_batch, D, flags);
   DPIPE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -165,43 +165,47 @@ extern "C" int dpipe_partition_balanced(const int64_t* weights, int n, int parts
 //   B = input-gradient pass (on the critical path: its result is what the previous stage waits for) and
 //   W = weight-gradient pass (no consumer on another stage),
 // so W work can fill what would be pipeline bubbles (Qi et al., "Zero Bubble Pipeline Parallelism", ZB-H1/ZB-2p).
-// The order is produced by a deterministic list-scheduling simulation of ALL stages with the given relative costs
-// (tf, tb, tw): whenever a stage becomes free it runs, in priority order, the oldest ready B, else the next F if it holds fewer
-// than `max_inflight` micro-batches (forward done, weight-gradient pass not yet done: that is what pins activation and
-// output-gradient memory), else a pending W; it idles only when nothing is ready.  Every
-// rank runs the same simulation, so all stages agree on the global order without communication.
+//
+// The order comes from a deterministic list-scheduling simulation of ALL stages: whenever a stage becomes free it
+// runs, in priority order, the oldest ready B, else the next F if it holds fewer than `max_inflight` micro-batches
+// (forward done, weight-gradient pass not yet done: that is what pins activation and output-gradient memory), else a
+// pending W; it idles only when nothing is ready.  Stage s is charged (tf, tb, tw) * stage_weight[s] per operation, so
+// uneven partitions (57 blocks over 8 stages) are planned for what they are.  List scheduling is a heuristic whose
+// result depends on the cost model it is driven with, so the planner tries a few cost models (the true one, the true
+// one without the per-stage weights, all-ones), replays each resulting order under the TRUE costs and keeps the order
+// with the smallest simulated makespan.  Every rank runs the same search, so all stages agree without communication.
 // Needs a one-sided stage link (IpcLink) or asynchronous sends: a stage pushes activations right after F and gradients
 // right after B, whenever the neighbour will get to them.
 // -------------------------------------------------------------------------------------------------------------------
-extern "C" int dpipe_sched_zb(int micro_batches, int stages, int stage_id, int tf, int tb, int tw, int max_inflight,
-                              dpipe_instr* out, int capacity) {
-  const int M = micro_batches, S = stages;
-  if (M < 1 || S < 1 || stage_id < 0 || stage_id >= S || tf < 1 || tb < 1 || tw < 1 || max_inflight < 1 || (!out && capacity > 0))
-    return dpipe::fail(DPIPE_EINVAL, "dpipe_sched_zb: bad arguments");
-  struct St { long long free_at; int nf, nb, nw; bool done; };
+namespace {
+
+struct ZbCost { long long f, b, w; };
+enum ZbOp : unsigned char { ZB_F = 1, ZB_B = 2, ZB_W = 3 };
+
+// list-scheduling simulation under `cost`; fills order[s * 3M + i] (kinds; the micro-batch of the i-th F/B/W of a stage
+// is its ordinal among operations of that kind)
+void zb_list_schedule(int M, int S, const ZbCost* cost, int max_inflight, unsigned char* order) {
+  struct St { long long free_at; int nf, nb, nw, n; bool done; };
   St* st = new St[S];
   long long* fin_f = new long long[(size_t)S * M];
   long long* fin_b = new long long[(size_t)S * M];
   const long long INF = (1LL << 60);
-  for (int s = 0; s < S; ++s) { st[s] = {0, 0, 0, 0, false}; }
+  for (int s = 0; s < S; ++s) st[s] = {0, 0, 0, 0, 0, false};
   for (size_t i = 0; i < (size_t)S * M; ++i) { fin_f[i] = INF; fin_b[i] = INF; }
-  Emit e{out, capacity, 0, false};
   int remaining = S;
   while (remaining > 0) {
-    // stage with the smallest clock acts next (ties: lowest index)
-    int s = -1;
+    int s = -1;   // the stage with the smallest clock acts next (ties: lowest index)
     for (int i = 0; i < S; ++i)
       if (!st[i].done && (s < 0 || st[i].free_at < st[s].free_at)) s = i;
     St& a = st[s];
     const long long now = a.free_at;
     auto f_ready = [&](int m) { return s == 0 ? 0 : fin_f[(size_t)(s - 1) * M + m]; };
     auto b_ready = [&](int m) { return s == S - 1 ? fin_f[(size_t)s * M + m] : fin_b[(size_t)(s + 1) * M + m]; };
-    int op = 0, m = -1;   // 1 = F, 2 = B, 3 = W
-    if (a.nb < M && a.nb < a.nf && b_ready(a.nb) <= now) { op = 2; m = a.nb; }
-    else if (a.nf < M && (a.nf - a.nw) < max_inflight && f_ready(a.nf) <= now) { op = 1; m = a.nf; }
-    else if (a.nw < a.nb) { op = 3; m = a.nw; }
-    if (op == 0) {
-      // nothing ready: sleep until the next point in time at which something can have changed
+    int op = 0;
+    if (a.nb < M && a.nb < a.nf && b_ready(a.nb) <= now) op = ZB_B;
+    else if (a.nf < M && (a.nf - a.nw) < max_inflight && f_ready(a.nf) <= now) op = ZB_F;
+    else if (a.nw < a.nb) op = ZB_W;
+    if (op == 0) {   // nothing ready: sleep until the next point in time at which something can have changed
       long long next = INF;
       if (a.nb < M && a.nb < a.nf && b_ready(a.nb) < INF) next = b_ready(a.nb);
       if (a.nf < M && (a.nf - a.nw) < max_inflight && f_ready(a.nf) < INF && f_ready(a.nf) < next) next = f_ready(a.nf);
@@ -213,102 +217,148 @@ extern "C" int dpipe_sched_zb(int micro_batches, int stages, int stage_id, int t
       a.free_at = next;
       continue;
     }
-    const bool mine = (s == stage_id);
-    if (op == 1) {
-      if (mine) {
-        if (s == 0 || s == S - 1) e.push(DPIPE_OP_LOAD_MICRO_BATCH, m, m);
-        if (s > 0) e.push(DPIPE_OP_RECV_ACTIVATION, m, m);
-        e.push(DPIPE_OP_FORWARD_PASS, m, m);
-        if (s < S - 1) e.push(DPIPE_OP_SEND_ACTIVATION, m, m);
-        e.push(DPIPE_OP_TICK_END, -1, -1);
-      }
-      a.free_at = now + tf;
-      fin_f[(size_t)s * M + m] = a.free_at;
-      a.nf++;
-    } else if (op == 2) {
-      if (mine) {
-        if (s < S - 1) e.push(DPIPE_OP_RECV_GRAD, m, m);
-        e.push(DPIPE_OP_BACKWARD_INPUT, m, m);
-        if (s > 0) e.push(DPIPE_OP_SEND_GRAD, m, m);
-        e.push(DPIPE_OP_TICK_END, -1, -1);
-      }
-      a.free_at = now + tb;
-      fin_b[(size_t)s * M + m] = a.free_at;
-      a.nb++;
-    } else {
-      if (mine) {
-        e.push(DPIPE_OP_BACKWARD_WEIGHT, m, m);
-        e.push(DPIPE_OP_TICK_END, -1, -1);
-      }
-      a.free_at = now + tw;
-      a.nw++;
-    }
+    if (op == ZB_F) { a.free_at = now + cost[s].f; fin_f[(size_t)s * M + a.nf] = a.free_at; a.nf++; }
+    else if (op == ZB_B) { a.free_at = now + cost[s].b; fin_b[(size_t)s * M + a.nb] = a.free_at; a.nb++; }
+    else { a.free_at = now + cost[s].w; a.nw++; }
+    order[(size_t)s * 3 * M + a.n++] = (unsigned char)op;
     if (a.nf == M && a.nb == M && a.nw == M) { a.done = true; --remaining; }
   }
-  e.push(DPIPE_OP_REDUCE_TIED_GRADS, -1, -1);
-  e.push(DPIPE_OP_REDUCE_GRADS, -1, -1);
-  e.push(DPIPE_OP_OPTIMIZER_STEP, -1, -1);
-  e.push(DPIPE_OP_TICK_END, -1, -1);
-  long long makespan = 0;
-  for (int i = 0; i < S; ++i) if (st[i].free_at > makespan) makespan = st[i].free_at;
   delete[] st; delete[] fin_f; delete[] fin_b;
-  if (e.overflow && capacity > 0) return dpipe::fail(DPIPE_EINVAL, "dpipe_sched_zb: capacity %d < %d", capacity, e.n);
-  (void)makespan;
-  return e.n;
 }
 
-// simulated makespan of the zero-bubble order (same simulation as dpipe_sched_zb), for tests / reporting
-extern "C" long long dpipe_sched_zb_makespan(int micro_batches, int stages, int tf, int tb, int tw, int max_inflight) {
-  const int M = micro_batches, S = stages;
-  if (M < 1 || S < 1 || tf < 1 || tb < 1 || tw < 1 || max_inflight < 1) return -1;
-  long long best = 0;
-  // derive it from the per-stage instruction streams: replay with dependencies
-  struct Op { int kind, m; };
-  Op** ops = new Op*[S];
-  int* cnt = new int[S];
-  for (int s = 0; s < S; ++s) {
-    const int n = dpipe_sched_zb(M, S, s, tf, tb, tw, max_inflight, nullptr, 0);
-    dpipe_instr* buf = new dpipe_instr[n];
-    dpipe_sched_zb(M, S, s, tf, tb, tw, max_inflight, buf, n);
-    ops[s] = new Op[3 * M];
-    cnt[s] = 0;
-    for (int i = 0; i < n; ++i) {
-      if (buf[i].op == DPIPE_OP_FORWARD_PASS) ops[s][cnt[s]++] = {1, buf[i].micro_batch};
-      else if (buf[i].op == DPIPE_OP_BACKWARD_INPUT) ops[s][cnt[s]++] = {2, buf[i].micro_batch};
-      else if (buf[i].op == DPIPE_OP_BACKWARD_WEIGHT) ops[s][cnt[s]++] = {3, buf[i].micro_batch};
-    }
-    delete[] buf;
-  }
+// makespan of the per-stage orders under `cost` (dependencies: F(s,m) after F(s-1,m); B(s,m) after B(s+1,m), or after
+// F(s,m) on the last stage; W(s,m) after B(s,m)).  Returns -2 if the orders deadlock (must never happen).
+long long zb_replay(int M, int S, const ZbCost* cost, const unsigned char* order) {
   const long long INF = (1LL << 60);
   long long* ff = new long long[(size_t)S * M];
   long long* fb = new long long[(size_t)S * M];
   for (size_t i = 0; i < (size_t)S * M; ++i) { ff[i] = INF; fb[i] = INF; }
   int* pos = new int[S];
+  int* cnt = new int[(size_t)S * 3];
   long long* t = new long long[S];
-  for (int s = 0; s < S; ++s) { pos[s] = 0; t[s] = 0; }
+  for (int s = 0; s < S; ++s) { pos[s] = 0; t[s] = 0; cnt[s * 3] = cnt[s * 3 + 1] = cnt[s * 3 + 2] = 0; }
   bool progress = true;
   while (progress) {
     progress = false;
     for (int s = 0; s < S; ++s) {
-      while (pos[s] < cnt[s]) {
-        const Op o = ops[s][pos[s]];
-        long long ready = 0;
-        if (o.kind == 1) ready = s == 0 ? 0 : ff[(size_t)(s - 1) * M + o.m];
-        else if (o.kind == 2) ready = s == S - 1 ? ff[(size_t)s * M + o.m] : fb[(size_t)(s + 1) * M + o.m];
-        else ready = fb[(size_t)s * M + o.m];
+      while (pos[s] < 3 * M) {
+        const int kind = order[(size_t)s * 3 * M + pos[s]];
+        const int m = cnt[s * 3 + kind - 1];
+        long long ready;
+        if (kind == ZB_F) ready = s == 0 ? 0 : ff[(size_t)(s - 1) * M + m];
+        else if (kind == ZB_B) ready = s == S - 1 ? ff[(size_t)s * M + m] : fb[(size_t)(s + 1) * M + m];
+        else ready = fb[(size_t)s * M + m];
         if (ready == INF) break;
         const long long start = ready > t[s] ? ready : t[s];
-        t[s] = start + (o.kind == 1 ? tf : o.kind == 2 ? tb : tw);
-        if (o.kind == 1) ff[(size_t)s * M + o.m] = t[s];
-        if (o.kind == 2) fb[(size_t)s * M + o.m] = t[s];
+        t[s] = start + (kind == ZB_F ? cost[s].f : kind == ZB_B ? cost[s].b : cost[s].w);
+        if (kind == ZB_F) ff[(size_t)s * M + m] = t[s];
+        if (kind == ZB_B) fb[(size_t)s * M + m] = t[s];
+        cnt[s * 3 + kind - 1]++;
         ++pos[s];
         progress = true;
       }
     }
   }
+  long long best = 0;
   bool complete = true;
-  for (int s = 0; s < S; ++s) { if (pos[s] != cnt[s]) complete = false; if (t[s] > best) best = t[s]; }
-  for (int s = 0; s < S; ++s) delete[] ops[s];
-  delete[] ops; delete[] cnt; delete[] ff; delete[] fb; delete[] pos; delete[] t;
-  return complete ? best : -2;   // -2: the per-stage orders deadlock (must never happen)
+  for (int s = 0; s < S; ++s) { if (pos[s] != 3 * M) complete = false; if (t[s] > best) best = t[s]; }
+  delete[] ff; delete[] fb; delete[] pos; delete[] cnt; delete[] t;
+  return complete ? best : -2;
+}
+
+// the candidate search described above; returns the chosen order (new[]-allocated, S * 3M kinds) and its makespan
+unsigned char* zb_best_order(int M, int S, int tf, int tb, int tw, int max_inflight, const int* stage_weight, long long* makespan) {
+  ZbCost* truth = new ZbCost[S];
+  ZbCost* model = new ZbCost[S];
+  for (int s = 0; s < S; ++s) {
+    const long long w = stage_weight ? stage_weight[s] : 1;
+    truth[s] = {tf * w, tb * w, tw * w};
+  }
+  unsigned char* best = nullptr;
+  long long best_ms = -1;
+  unsigned char* cand = new unsigned char[(size_t)S * 3 * M];
+  for (int c = 0; c < 3; ++c) {
+    for (int s = 0; s < S; ++s) {
+      if (c == 0) model[s] = truth[s];
+      else if (c == 1) model[s] = {tf, tb, tw};
+      else model[s] = {1, 1, 1};
+    }
+    zb_list_schedule(M, S, model, max_inflight, cand);
+    const long long ms = zb_replay(M, S, truth, cand);
+    if (ms >= 0 && (best_ms < 0 || ms < best_ms)) {
+      best_ms = ms;
+      if (!best) best = new unsigned char[(size_t)S * 3 * M];
+      for (size_t i = 0; i < (size_t)S * 3 * M; ++i) best[i] = cand[i];
+    }
+  }
+  delete[] cand; delete[] truth; delete[] model;
+  *makespan = best_ms;
+  return best;
+}
+
+bool zb_args_ok(int M, int S, int tf, int tb, int tw, int max_inflight, const int* stage_weight) {
+  if (M < 1 || S < 1 || tf < 1 || tb < 1 || tw < 1 || max_inflight < 1) return false;
+  if (stage_weight)
+    for (int s = 0; s < S; ++s)
+      if (stage_weight[s] < 1 || stage_weight[s] > (1 << 20)) return false;
+  return true;
+}
+
+}  // namespace
+
+extern "C" int dpipe_sched_zb_ex(int micro_batches, int stages, int stage_id, int tf, int tb, int tw, int max_inflight,
+                                 const int* stage_weight, dpipe_instr* out, int capacity) {
+  const int M = micro_batches, S = stages;
+  if (!zb_args_ok(M, S, tf, tb, tw, max_inflight, stage_weight) || stage_id < 0 || stage_id >= S || (!out && capacity > 0))
+    return dpipe::fail(DPIPE_EINVAL, "dpipe_sched_zb: bad arguments");
+  long long ms = 0;
+  unsigned char* order = zb_best_order(M, S, tf, tb, tw, max_inflight, stage_weight, &ms);
+  if (!order) return dpipe::fail(DPIPE_EINVAL, "dpipe_sched_zb: no deadlock-free order found (internal error)");
+  Emit e{out, capacity, 0, false};
+  const int s = stage_id;
+  int cnt[3] = {0, 0, 0};
+  for (int i = 0; i < 3 * M; ++i) {
+    const int kind = order[(size_t)s * 3 * M + i];
+    const int m = cnt[kind - 1]++;
+    if (kind == ZB_F) {
+      if (s == 0 || s == S - 1) e.push(DPIPE_OP_LOAD_MICRO_BATCH, m, m);
+      if (s > 0) e.push(DPIPE_OP_RECV_ACTIVATION, m, m);
+      e.push(DPIPE_OP_FORWARD_PASS, m, m);
+      if (s < S - 1) e.push(DPIPE_OP_SEND_ACTIVATION, m, m);
+    } else if (kind == ZB_B) {
+      if (s < S - 1) e.push(DPIPE_OP_RECV_GRAD, m, m);
+      e.push(DPIPE_OP_BACKWARD_INPUT, m, m);
+      if (s > 0) e.push(DPIPE_OP_SEND_GRAD, m, m);
+    } else {
+      e.push(DPIPE_OP_BACKWARD_WEIGHT, m, m);
+    }
+    e.push(DPIPE_OP_TICK_END, -1, -1);
+  }
+  delete[] order;
+  e.push(DPIPE_OP_REDUCE_TIED_GRADS, -1, -1);
+  e.push(DPIPE_OP_REDUCE_GRADS, -1, -1);
+  e.push(DPIPE_OP_OPTIMIZER_STEP, -1, -1);
+  e.push(DPIPE_OP_TICK_END, -1, -1);
+  if (e.overflow && capacity > 0) return dpipe::fail(DPIPE_EINVAL, "dpipe_sched_zb: capacity %d < %d", capacity, e.n);
+  return e.n;
+}
+
+extern "C" int dpipe_sched_zb(int micro_batches, int stages, int stage_id, int tf, int tb, int tw, int max_inflight,
+                              dpipe_instr* out, int capacity) {
+  return dpipe_sched_zb_ex(micro_batches, stages, stage_id, tf, tb, tw, max_inflight, nullptr, out, capacity);
+}
+
+// simulated makespan of the chosen order under the true costs, for tests / reporting
+extern "C" long long dpipe_sched_zb_makespan_ex(int micro_batches, int stages, int tf, int tb, int tw, int max_inflight,
+                                                const int* stage_weight) {
+  if (!zb_args_ok(micro_batches, stages, tf, tb, tw, max_inflight, stage_weight)) return -1;
+  long long ms = 0;
+  unsigned char* order = zb_best_order(micro_batches, stages, tf, tb, tw, max_inflight, stage_weight, &ms);
+  if (!order) return -2;
+  delete[] order;
+  return ms;
+}
+
+extern "C" long long dpipe_sched_zb_makespan(int micro_batches, int stages, int tf, int tb, int tw, int max_inflight) {
+  return dpipe_sched_zb_makespan_ex(micro_batches, stages, tf, tb, tw, max_inflight, nullptr);
 }

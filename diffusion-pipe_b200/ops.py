@@ -5,7 +5,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._abi import AttnArgs, AttnBwdArgs, QkBwdArgs
+from ._abi import AttnArgs, AttnBwdArgs, QkBwdArgs, WanNormBwdArgs, WanNormFwdArgs
 from ._lib import GemmArgs, QkvEpilogue, check, lib
 
 EPI_STORE = _lib.EPI_STORE
@@ -224,7 +224,11 @@ def nchunks(rows_per_batch):
     return (rows_per_batch + rc - 1) // rc
 
 
-def ln_modulate_fwd(x, scale, shift, batch, rows_per_batch, eps=1e-6, out=None, save_stats=True):
+LN_MULT_DIRECT = 1   # include/dpipe.h DPIPE_LN_MULT_DIRECT: `scale` is the multiplier itself (affine LayerNorm)
+LN_ROUND_STEPS = 2   # DPIPE_LN_ROUND_STEPS: bf16 rounding after every elementwise op (Wan modulation on bf16 tensors)
+
+
+def ln_modulate_fwd(x, scale, shift, batch, rows_per_batch, eps=1e-6, out=None, save_stats=True, flags=0):
     """out = LN(x) * bf16(1+scale[b]) + shift[b].  x: [batch*rows, D]; scale/shift: [batch, D] views (bf16)."""
     global LAUNCHES
     _req_bf16(x, 'x')
@@ -239,15 +243,15 @@ def ln_modulate_fwd(x, scale, shift, batch, rows_per_batch, eps=1e-6, out=None, 
         mean = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
         rstd = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
     _e = _prof_begin()
-    check(lib().dpipe_ln_modulate_fwd(_ptr(x), x.stride(0), _ptr(scale), _ptr(shift), scale.stride(0), _ptr(out),
-                                      out.stride(0), _ptr(mean), _ptr(rstd), batch, rows_per_batch, D, eps, _stream()),
-          'dpipe_ln_modulate_fwd')
+    check(lib().dpipe_ln_modulate_fwd_ex(_ptr(x), x.stride(0), _ptr(scale), _ptr(shift), scale.stride(0), _ptr(out),
+                                         out.stride(0), _ptr(mean), _ptr(rstd), batch, rows_per_batch, D, eps, flags,
+                                         _stream()), 'dpipe_ln_modulate_fwd')
     _prof_end(_e, 0.0, 'ln_fwd')
     LAUNCHES += 1
     return out, mean, rstd
 
 
-def ln_modulate_bwd(dxn, x, scale, mean, rstd, batch, rows_per_batch, dres=None, dx=None, partials=None):
+def ln_modulate_bwd(dxn, x, scale, mean, rstd, batch, rows_per_batch, dres=None, dx=None, partials=None, flags=0):
     """Returns (dx, partials) with partials[batch][nchunk][2][D]: slot 0 = d scale, slot 1 = d shift."""
     global LAUNCHES
     _req_bf16(dxn, 'dxn')
@@ -262,10 +266,10 @@ def ln_modulate_bwd(dxn, x, scale, mean, rstd, batch, rows_per_batch, dres=None,
     if dres is not None:
         _req_bf16(dres, 'dres')
     _e = _prof_begin()
-    check(lib().dpipe_ln_modulate_bwd(_ptr(dxn), dxn.stride(0), _ptr(x), x.stride(0), _ptr(scale), scale.stride(0),
-                                      _ptr(mean), _ptr(rstd), _ptr(dres), dres.stride(0) if dres is not None else 0,
-                                      _ptr(dx), dx.stride(0), _ptr(partials), batch, rows_per_batch, D, _stream()),
-          'dpipe_ln_modulate_bwd')
+    check(lib().dpipe_ln_modulate_bwd_ex(_ptr(dxn), dxn.stride(0), _ptr(x), x.stride(0), _ptr(scale), scale.stride(0),
+                                         _ptr(mean), _ptr(rstd), _ptr(dres), dres.stride(0) if dres is not None else 0,
+                                         _ptr(dx), dx.stride(0), _ptr(partials), batch, rows_per_batch, D, flags,
+                                         _stream()), 'dpipe_ln_modulate_bwd')
     _prof_end(_e, 0.0, 'ln_bwd')
     LAUNCHES += 1
     return dx, partials
@@ -342,6 +346,82 @@ def qknorm_rope_bwd(dq, dk, dv, qhat, khat, q_rstd, k_rstd, q_norm_w, k_norm_w, 
     check(lib().dpipe_qknorm_rope_bwd(ctypes.byref(a), _stream()), 'dpipe_qknorm_rope_bwd')
     _prof_end(_e, 0.0, 'qknorm_bwd')
     LAUNCHES += 1
+
+
+def wan_norm_rope_fwd(projs, batch, seq, heads, cos=None, sin=None, eps=1e-6):
+    """Wan q/k/v pre-processing (csrc/wan_norm.cu).  projs: up to three dicts {src [batch*seq, >=C] bf16 view, weight
+    [C] bf16 or None, rope bool}.  Returns per projection (dst [batch, heads, seq, 128], xhat [batch*seq, C] or None,
+    rstd [batch*seq] or None)."""
+    global LAUNCHES
+    a = WanNormFwdArgs()
+    C = heads * 128
+    outs = []
+    for i, pj in enumerate(projs):
+        src = pj['src']
+        _req_bf16(src, 'src')
+        dev = src.device
+        dst = torch.empty((batch, heads, seq, 128), dtype=torch.bfloat16, device=dev)
+        w = pj.get('weight')
+        xhat = rstd = None
+        if w is not None:
+            _req_bf16(w, 'weight')
+            xhat = torch.empty((batch * seq, C), dtype=torch.bfloat16, device=dev)
+            rstd = torch.empty(batch * seq, dtype=torch.float32, device=dev)
+        e = a.proj[i]
+        e.src, e.ld, e.weight, e.dst, e.xhat, e.rstd = _ptr(src), src.stride(0), _ptr(w), _ptr(dst), _ptr(xhat), _ptr(rstd)
+        e.rope = 1 if pj.get('rope') else 0
+        outs.append((dst, xhat, rstd))
+    a.nproj = len(projs)
+    if cos is not None:
+        _req_f32(cos, 'cos')
+        _req_f32(sin, 'sin')
+    a.cos, a.sin = _ptr(cos), _ptr(sin)
+    a.batch, a.seq, a.heads, a.eps = batch, seq, heads, eps
+    _e = _prof_begin()
+    check(lib().dpipe_wan_norm_rope_fwd(ctypes.byref(a), _stream()), 'dpipe_wan_norm_rope_fwd')
+    _prof_end(_e, 0.0, 'wan_norm_fwd')
+    LAUNCHES += 1
+    return outs
+
+
+def wan_norm_rope_bwd(projs, batch, seq, heads, cos=None, sin=None):
+    """Backward of wan_norm_rope_fwd.  projs: dicts {dy [batch, heads, seq, 128], dx [batch*seq, >=C] bf16 view (written),
+    weight, xhat, rstd (None for v), rope}.  Returns, per projection, the fp32 d weight [C] (or None)."""
+    global LAUNCHES
+    a = WanNormBwdArgs()
+    C = heads * 128
+    rows = batch * seq
+    nchunk = (rows + lib().dpipe_wan_norm_rows() - 1) // lib().dpipe_wan_norm_rows()
+    parts = []
+    for i, pj in enumerate(projs):
+        dy, dx = pj['dy'], pj['dx']
+        _req_bf16(dy, 'dy')
+        _req_bf16(dx, 'dx')
+        if not dy.is_contiguous():
+            raise ValueError('dy must be a contiguous [batch, heads, seq, 128] tensor')
+        w = pj.get('weight')
+        part = torch.empty((1, nchunk, 1, C), dtype=torch.float32, device=dy.device) if w is not None else None
+        e = a.proj[i]
+        e.dy, e.xhat, e.rstd, e.weight = _ptr(dy), _ptr(pj.get('xhat')), _ptr(pj.get('rstd')), _ptr(w)
+        e.dx, e.ld, e.dw_partials = _ptr(dx), dx.stride(0), _ptr(part)
+        e.rope = 1 if pj.get('rope') else 0
+        parts.append(part)
+    a.nproj = len(projs)
+    a.cos, a.sin = _ptr(cos), _ptr(sin)
+    a.batch, a.seq, a.heads = batch, seq, heads
+    _e = _prof_begin()
+    check(lib().dpipe_wan_norm_rope_bwd(ctypes.byref(a), _stream()), 'dpipe_wan_norm_rope_bwd')
+    _prof_end(_e, 0.0, 'wan_norm_bwd')
+    LAUNCHES += 1
+    dws = []
+    for part in parts:
+        if part is None:
+            dws.append(None)
+            continue
+        dw = torch.empty(C, dtype=torch.float32, device=part.device)
+        colreduce_finish(part, summed0=dw)
+        dws.append(dw)
+    return dws
 
 
 def mod_fwd(temb, weight, bias):

@@ -130,6 +130,10 @@ class PipelineEngine:
         self.pipeline_schedule = str(self.config.get('pipeline_schedule', '1f1b')).lower()
         self.zb_costs = tuple(self.config.get('zb_costs', (13, 17, 10)))
         self.zb_max_inflight = self.config.get('zb_max_inflight', None)
+        # relative work per stage for the zero-bubble planner; default: the number of layers each stage holds
+        self.zb_stage_weights = self.config.get('zb_stage_weights', None)
+        if self.zb_stage_weights is None and getattr(model, 'parts', None) is not None and len(model.parts) == self.num_stages + 1:
+            self.zb_stage_weights = [max(1, int(model.parts[i + 1] - model.parts[i])) for i in range(self.num_stages)]
         self._wgrad_queues = {}
         self.link = self._make_link()
         self.total_loss = None
@@ -182,7 +186,8 @@ class PipelineEngine:
         self.fwd_losses = []
         self._data_iter = data_iter
         if self.pipeline_schedule == 'zb':
-            sched = ZeroBubbleSchedule(self.micro_batches, self.num_stages, self.stage_id, self.zb_costs, self.zb_max_inflight)
+            sched = ZeroBubbleSchedule(self.micro_batches, self.num_stages, self.stage_id, self.zb_costs, self.zb_max_inflight,
+                                       self.zb_stage_weights)
         else:
             sched = TrainSchedule(self.micro_batches, self.num_stages, self.stage_id)
         self._reserve_buffers(sched.num_pipe_buffers())

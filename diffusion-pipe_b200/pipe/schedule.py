@@ -149,21 +149,35 @@ class ZeroBubbleSchedule(PipeSchedule):
     """Split-backward schedule from the C++ list-scheduling planner (csrc/sched.cpp: dpipe_sched_zb).  Not in the
     reference; loss-equivalent to TrainSchedule.  `costs` = relative (forward, input-grad, weight-grad) durations;
     `max_inflight` = micro-batches a stage may hold between forward and weight-grad pass, i.e. the bound on
-    activation memory (default 2 * stages: ZB-2p-like)."""
+    activation memory (default 2 * stages: ZB-2p-like); `stage_weights` = relative amount of work per stage (e.g. its
+    number of transformer blocks; default: equal) — the planner charges stage s `costs * stage_weights[s]`."""
 
-    def __init__(self, micro_batches, stages, stage_id, costs=(13, 17, 10), max_inflight=None):
+    def __init__(self, micro_batches, stages, stage_id, costs=(13, 17, 10), max_inflight=None, stage_weights=None):
         super().__init__(micro_batches, stages, stage_id)
         self.costs = tuple(int(c) for c in costs)
         self.max_inflight = int(max_inflight or 2 * stages)
+        if stage_weights is not None:
+            stage_weights = [int(w) for w in stage_weights]
+            if len(stage_weights) != stages or min(stage_weights) < 1:
+                raise ValueError(f'stage_weights must be {stages} positive integers, got {stage_weights}')
+        self.stage_weights = stage_weights
+
+    def _weights_arg(self):
+        import ctypes
+        if self.stage_weights is None:
+            return None
+        return (ctypes.c_int * self.stages)(*self.stage_weights)
 
     def steps(self):
-        return _plan('dpipe_sched_zb', self.micro_batches, self.stages, self.stage_id, (*self.costs, self.max_inflight))
+        return _plan('dpipe_sched_zb_ex', self.micro_batches, self.stages, self.stage_id,
+                     (*self.costs, self.max_inflight, self._weights_arg()))
 
     def num_pipe_buffers(self):
         return self.micro_batches     # buffers are indexed by micro-batch id
 
     def simulated_makespan(self):
-        v = _lib.lib().dpipe_sched_zb_makespan(self.micro_batches, self.stages, *self.costs, self.max_inflight)
+        v = _lib.lib().dpipe_sched_zb_makespan_ex(self.micro_batches, self.stages, *self.costs, self.max_inflight,
+                                                  self._weights_arg())
         if v < 0:
             raise _lib.DpipeError(f'dpipe_sched_zb_makespan failed ({v})')
         return v

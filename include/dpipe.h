@@ -141,6 +141,16 @@ int dpipe_row_chunk(void);
 int dpipe_ln_modulate_fwd(const void* x, int64_t ldx, const void* scale, const void* shift, int64_t mod_stride,
                           void* out, int64_t ldo, float* mean, float* rstd, int batch, int rows_per_batch, int D,
                           float eps, void* stream);
+/* flags for the _ex forms below */
+#define DPIPE_LN_MULT_DIRECT 1 /* `scale` is the multiplier itself (LayerNorm with affine weight: Wan norm3, models/wan/model.py:266-268) */
+#define DPIPE_LN_ROUND_STEPS 2 /* round x_hat and x_hat*mult to bf16 before the next op: Wan's `norm(x) * (1 + e1) + e0` on bf16 tensors (models/wan/model.py:301-302) */
+int dpipe_ln_modulate_fwd_ex(const void* x, int64_t ldx, const void* scale, const void* shift, int64_t mod_stride,
+                             void* out, int64_t ldo, float* mean, float* rstd, int batch, int rows_per_batch, int D,
+                             float eps, int flags, void* stream);
+int dpipe_ln_modulate_bwd_ex(const void* dxn, int64_t lddxn, const void* x, int64_t ldx, const void* scale,
+                             int64_t mod_stride, const float* mean, const float* rstd, const void* dres, int64_t lddres,
+                             void* dx, int64_t lddx, float* partials, int batch, int rows_per_batch, int D, int flags,
+                             void* stream);
 /* dx = LN'(dxn * bf16(1+scale)) (+ dres);  partial slot 0 = d scale, slot 1 = d shift (per sample) */
 int dpipe_ln_modulate_bwd(const void* dxn, int64_t lddxn, const void* x, int64_t ldx, const void* scale,
                           int64_t mod_stride, const float* mean, const float* rstd, const void* dres, int64_t lddres,
@@ -168,6 +178,44 @@ typedef struct dpipe_qk_bwd_args {
 } dpipe_qk_bwd_args;
 /* backward of the DPIPE_EPI_QKV_ROPE epilogue for one stream */
 int dpipe_qknorm_rope_bwd(const dpipe_qk_bwd_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Wan attention pre-processing (csrc/wan_norm.cu): RMSNorm over the full model width + RoPE +  */
+/* token-major -> head-major scatter.  Replaces WanRMSNorm / rope_apply / the .view(b, s, n, d) */
+/* of models/wan/model.py:41-68,71-87,137-156,171-183.  Up to three projections per launch.    */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct dpipe_wan_norm_proj {
+  const void* src; int64_t ld;   /* bf16 [batch*seq, ld]: projection output (bias added), width heads*128 used */
+  const void* weight;            /* bf16 [heads*128] RMSNorm scale, or NULL: no normalisation (v) */
+  void* dst;                     /* bf16 [batch, heads, seq, 128] */
+  void* xhat;                    /* bf16 [batch*seq, heads*128]: normalised rows before the scale (for backward), or NULL */
+  float* rstd;                   /* fp32 [batch*seq], or NULL */
+  int rope;                      /* rotate with the tables below */
+} dpipe_wan_norm_proj;
+typedef struct dpipe_wan_norm_fwd_args {
+  dpipe_wan_norm_proj proj[3];
+  int nproj;
+  const float* cos; const float* sin;   /* fp32 [seq, 128], every frequency repeated twice (NULL if no projection ropes) */
+  int batch, seq, heads;
+  float eps;
+} dpipe_wan_norm_fwd_args;
+int dpipe_wan_norm_rope_fwd(const dpipe_wan_norm_fwd_args* args, void* stream);
+
+typedef struct dpipe_wan_norm_bwd_proj {
+  const void* dy;                /* bf16 [batch, heads, seq, 128]: gradient of dst */
+  const void* xhat; const float* rstd; const void* weight;   /* as saved / passed in the forward (NULL for v) */
+  void* dx; int64_t ld;          /* bf16 [batch*seq, ld]: gradient of src */
+  float* dw_partials;            /* fp32 [ceil(batch*seq / dpipe_wan_norm_rows()), heads*128]; fold with dpipe_colreduce_finish */
+  int rope;
+} dpipe_wan_norm_bwd_proj;
+typedef struct dpipe_wan_norm_bwd_args {
+  dpipe_wan_norm_bwd_proj proj[3];
+  int nproj;
+  const float* cos; const float* sin;
+  int batch, seq, heads;
+} dpipe_wan_norm_bwd_args;
+int dpipe_wan_norm_rows(void);
+int dpipe_wan_norm_rope_bwd(const dpipe_wan_norm_bwd_args* args, void* stream);
 
 /* AdaLayerNorm modulation linear for a micro-batch of B <= 8 samples (HBM-bound, rank-B):
  *   out[b,:] = W * bf16(silu(temb[b,:])) + bias.   replaces nn.Linear(SiLU(temb)) of AdaLayerNormZero{,Single}/Continuous
@@ -217,11 +265,17 @@ int dpipe_sched_train(int micro_batches, int stages, int stage_id, dpipe_instr* 
 int dpipe_sched_infer(int micro_batches, int stages, int stage_id, dpipe_instr* out, int capacity);
 /* split-backward ("zero-bubble") order for one stage from a deterministic list-scheduling simulation of all stages with
  * relative costs tf / tb / tw (forward, input-gradient, weight-gradient) and at most max_inflight micro-batches held
- * per stage (forward done, weight-gradient pass pending).  Not in the reference; loss-equivalent to 1F1B.  Same calling convention as dpipe_sched_train. */
+ * per stage (forward done, weight-gradient pass pending).  Not in the reference; loss-equivalent to 1F1B.  Same calling
+ * convention as dpipe_sched_train.  The _ex form charges stage s (tf, tb, tw) * stage_weight[s] (e.g. its number of
+ * transformer blocks; NULL = all 1) and keeps, among a few candidate list schedules, the one with the smallest
+ * simulated makespan under those costs. */
 int dpipe_sched_zb(int micro_batches, int stages, int stage_id, int tf, int tb, int tw, int max_inflight,
                    dpipe_instr* out, int capacity);
-/* simulated makespan of that order in the same cost units (for tests / reporting); < 0 on error */
+int dpipe_sched_zb_ex(int micro_batches, int stages, int stage_id, int tf, int tb, int tw, int max_inflight,
+                      const int* stage_weight, dpipe_instr* out, int capacity);
 long long dpipe_sched_zb_makespan(int micro_batches, int stages, int tf, int tb, int tw, int max_inflight);
+long long dpipe_sched_zb_makespan_ex(int micro_batches, int stages, int tf, int tb, int tw, int max_inflight,
+                                      const int* stage_weight);
 /* contiguous min-max partition of n layer weights into `parts` stages; bounds has parts+1 entries
  * (replaces DeepSpeed partition_balanced behind partition_method='parameters', train.py:81-90,606) */
 int dpipe_partition_balanced(const int64_t* weights, int n, int parts, int* bounds);

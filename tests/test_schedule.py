@@ -118,3 +118,41 @@ def test_zero_bubble_beats_1f1b_in_the_cost_model():
     one_f_one_b = (m + s - 1) * sum(costs)
     assert zb < 0.85 * one_f_one_b
     assert work / zb > 0.86          # (S-1)*tf of fill is the only bubble left: 640 / (640 + 91)
+
+
+@pytest.mark.parametrize('m,s,weights', [(16, 8, [8, 7, 7, 7, 7, 7, 7, 7]), (16, 8, [7, 7, 7, 7, 7, 7, 7, 8]),
+                                         (16, 4, [15, 14, 14, 14]), (6, 3, [1, 5, 2])])
+def test_zero_bubble_with_stage_weights_is_consistent_and_bounded(m, s, weights):
+    """uneven partitions: the order stays complete, dependency-correct, memory-bounded and deadlock-free"""
+    from diffusion_pipe_b200.pipe.schedule import ZeroBubbleSchedule
+    infl = min(m, 2 * s)
+    for st in range(s):
+        sched = ZeroBubbleSchedule(m, s, st, (13, 17, 10), infl, weights)
+        seq = [(c.name, getattr(c, 'micro_batch_id', None)) for t in sched.steps() for c in t]
+        assert [mb for n, mb in seq if n == 'ForwardPass'] == list(range(m))
+        assert [mb for n, mb in seq if n == 'BackwardInput'] == list(range(m))
+        assert [mb for n, mb in seq if n == 'BackwardWeight'] == list(range(m))
+        held = peak = 0
+        for n, mb in seq:
+            held += (n == 'ForwardPass') - (n == 'BackwardWeight')
+            peak = max(peak, held)
+        assert peak <= infl                                   # forward done, weight-gradient pending
+    ms = ZeroBubbleSchedule(m, s, 0, (13, 17, 10), infl, weights).simulated_makespan()
+    assert ms >= m * 40 * max(weights)                        # no stage can beat its own work
+    with pytest.raises(ValueError):
+        ZeroBubbleSchedule(m, s, 0, (13, 17, 10), infl, weights[:-1])
+    with pytest.raises(ValueError):
+        ZeroBubbleSchedule(m, s, 0, (13, 17, 10), infl, [0] + weights[1:])
+
+
+def test_zero_bubble_prefers_the_heavier_stage_first():
+    """57 blocks over 8 stages, 16 micro-batches: the simulated speed-up over one stage (7.125 is the bound set by the
+    8-block stage) — what bench.py's flop_balanced_split relies on"""
+    from diffusion_pipe_b200.pipe.schedule import ZeroBubbleSchedule
+    work = 16 * 57 * 40
+
+    def speedup(w):
+        return work / ZeroBubbleSchedule(16, 8, 0, (13, 17, 10), 16, w).simulated_makespan()
+    first, last = speedup([8] + [7] * 7), speedup([7] * 7 + [8])
+    assert first > 7.0 and first > last + 0.5
+    assert last > 5.57 * 57 / 64                              # still better than ideal 1F1B on the same partition
