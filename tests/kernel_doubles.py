@@ -1,0 +1,244 @@
+"""TEST DOUBLES for the C-ABI kernel wrappers of diffusion-pipe_b200/ops.py — test infrastructure only.
+
+The block functions (flux_blocks.py, wan.py) are long sequences of kernel launches whose HOST logic (which buffer goes
+where, which gradient is accumulated into which parameter, what is saved for backward) can be wrong independently of the
+kernels.  These doubles implement each wrapper's documented contract with plain PyTorch on the CPU (fp32 math, bf16
+rounding where the kernel rounds), so that the `-m "not gpu"` suite can run a whole block forward + backward against the
+oracle without a GPU.  They are installed by the `kernel_doubles` fixture (monkeypatch) for the duration of one test and
+are never importable from the product package; the GPU suite exercises the real kernels.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+EPI_STORE, EPI_BIAS_GELU, EPI_GATE_RES, EPI_QKV_ROPE, EPI_MUL_GELU_GRAD = 0, 1, 2, 3, 4
+LN_MULT_DIRECT, LN_ROUND_STEPS = 1, 2
+ROW_CHUNK = 16
+
+
+def _r(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def _gelu_grad(u):
+    with torch.enable_grad():       # (called from inside autograd.Function.backward, where grad mode is off)
+        u = u.detach().clone().requires_grad_(True)
+        (g,) = torch.autograd.grad(F.gelu(u, approximate='tanh').sum(), u)
+    return g
+
+
+def gemm(a, b, *, a_mn=False, b_mn=False, out=None, epilogue=EPI_STORE, bias=None, out2=None, aux=None, gate=None,
+         rows_per_batch=None, accumulate=False, cta_group=2, qkv=None, M=None, N=None, K=None):
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    A = a.float().t() if a_mn else a.float()
+    Bm = b.float() if b_mn else b.float().t()
+    acc = A @ Bm
+    if accumulate:
+        acc = acc + out.float()
+    if bias is not None:
+        acc = acc + bias.float()[None, :]
+    Mr = acc.shape[0]
+    if epilogue == EPI_STORE:
+        res = acc
+    elif epilogue == EPI_BIAS_GELU:
+        u = _r(acc)
+        if out2 is not None:
+            out2.copy_(u)
+        res = F.gelu(u, approximate='tanh')
+    elif epilogue == EPI_GATE_RES:
+        y = _r(acc)
+        if out2 is not None:
+            out2.copy_(y)
+        rpb = rows_per_batch or Mr
+        g = gate.float()[torch.arange(Mr) // rpb]
+        res = aux.float() + _r(g * y)
+    elif epilogue == EPI_MUL_GELU_GRAD:
+        res = acc * _gelu_grad(aux.float())
+    else:
+        raise NotImplementedError(epilogue)
+    if out is None:
+        out = torch.empty(res.shape, dtype=torch.bfloat16)
+    out.copy_(res)
+    return out
+
+
+def _heads(t):       # [B,H,L,128] -> fp32
+    return t.float()
+
+
+def attn_fwd(q, k, v, out=None, lse=None, scale=None):
+    B, H, Lq, _ = q.shape
+    s = torch.matmul(_heads(q), _heads(k).transpose(-1, -2)) * (scale or 128 ** -0.5)
+    m = s.amax(-1, keepdim=True)
+    p = torch.exp(s - m)
+    l = p.sum(-1, keepdim=True)
+    o = torch.matmul(_r(p), _heads(v)) / l
+    res = o.permute(0, 2, 1, 3).reshape(B * Lq, H * 128)
+    if out is None:
+        out = torch.empty((B * Lq, H * 128), dtype=torch.bfloat16)
+    out[:, :H * 128].copy_(res)
+    lse_v = ((m + torch.log(l)) * math.log2(math.e)).squeeze(-1)
+    return out, lse_v
+
+
+def attn_bwd(q, k, v, o, d_o, lse, scale=None, dq=None, dk=None, dv=None, delta=None):
+    B, H, Lq, _ = q.shape
+    g = d_o[:, :H * 128].float().view(B, Lq, H, 128).permute(0, 2, 1, 3)
+    with torch.enable_grad():
+        qq, kk, vv = (t.detach().float().clone().requires_grad_(True) for t in (q, k, v))
+        s = torch.matmul(qq, kk.transpose(-1, -2)) * (scale or 128 ** -0.5)
+        out = torch.matmul(torch.softmax(s, dim=-1), vv)
+        out.backward(g)
+    return qq.grad.to(torch.bfloat16), kk.grad.to(torch.bfloat16), vv.grad.to(torch.bfloat16)
+
+
+def nchunks(rows_per_batch):
+    return (rows_per_batch + ROW_CHUNK - 1) // ROW_CHUNK
+
+
+def _mult(scale, flags):
+    return scale.float() if flags & LN_MULT_DIRECT else _r(1.0 + scale.float())
+
+
+def ln_modulate_fwd(x, scale, shift, batch, rows_per_batch, eps=1e-6, out=None, save_stats=True, flags=0):
+    D = x.shape[1]
+    xf = x.float().view(batch, rows_per_batch, D)
+    mean = xf.mean(-1, keepdim=True)
+    var = (xf - mean).pow(2).mean(-1, keepdim=True)
+    rstd = torch.rsqrt(var + eps)
+    xh = (xf - mean) * rstd
+    m = _mult(scale, flags)[:, None, :]
+    sh = shift.float()[:, None, :]
+    res = _r(_r(xh) * m) + sh if flags & LN_ROUND_STEPS else xh * m + sh
+    if out is None:
+        out = torch.empty((batch * rows_per_batch, D), dtype=torch.bfloat16)
+    out.copy_(res.reshape(-1, D))
+    if save_stats:
+        return out, mean.reshape(-1).clone(), rstd.reshape(-1).clone()
+    return out, None, None
+
+
+def ln_modulate_bwd(dxn, x, scale, mean, rstd, batch, rows_per_batch, dres=None, dx=None, partials=None, flags=0):
+    D = x.shape[1]
+    xh = ((x.float() - mean[:, None]) * rstd[:, None]).view(batch, rows_per_batch, D)
+    d = dxn.float().view(batch, rows_per_batch, D)
+    g = d * _mult(scale, flags)[:, None, :]
+    res = rstd.view(batch, rows_per_batch, 1) * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+    if dres is not None:
+        res = res + dres.float().view(batch, rows_per_batch, D)
+    if dx is None:
+        dx = torch.empty((batch * rows_per_batch, D), dtype=torch.bfloat16)
+    dx.copy_(res.reshape(-1, D))
+    partials = torch.zeros((batch, nchunks(rows_per_batch), 2, D), dtype=torch.float32)
+    partials[:, 0, 0] = (d * xh).sum(1)
+    partials[:, 0, 1] = d.sum(1)
+    return dx, partials
+
+
+def gate_bwd(dx, y, gate, batch, rows_per_batch, dy=None, partials=None):
+    D = y.shape[1]
+    d = dx.float().view(batch, rows_per_batch, D)
+    res = _r(gate.float()[:, None, :] * d)
+    if dy is None:
+        dy = torch.empty((batch * rows_per_batch, D), dtype=torch.bfloat16)
+    dy.copy_(res.reshape(-1, D))
+    partials = torch.zeros((batch, nchunks(rows_per_batch), 2, D), dtype=torch.float32)
+    partials[:, 0, 0] = (d * y.float().view(batch, rows_per_batch, D)).sum(1)
+    partials[:, 0, 1] = res.sum(1)
+    return dy, partials
+
+
+def colreduce_finish(partials, per_sample0=None, per_sample1=None, summed0=None, summed1=None):
+    tot = partials.sum(1)                     # [batch, nslot, D]
+    for s, (ps, sm) in enumerate(((per_sample0, summed0), (per_sample1, summed1))):
+        if s >= tot.shape[1]:
+            break
+        if ps is not None:
+            ps.copy_(tot[:, s])
+        if sm is not None:
+            sm.copy_(tot[:, s].sum(0))
+
+
+def colsum(x, out=None):
+    res = x.float().sum(0)
+    if out is None:
+        return res
+    out.copy_(res)
+    return out
+
+
+def _rope(y, cos, sin, transpose=False):
+    # y [..., L, 128] head-major, tables [L, 128]
+    a, b = y[..., 0::2], y[..., 1::2]
+    c, s = cos[:, 0::2], sin[:, 0::2]
+    if transpose:
+        s = -s
+    return torch.stack([a * c - b * s, b * c + a * s], dim=-1).flatten(-2)
+
+
+def wan_norm_rope_fwd(projs, batch, seq, heads, cos=None, sin=None, eps=1e-6):
+    C = heads * 128
+    outs = []
+    for pj in projs:
+        x = pj['src'][:, :C].float()
+        w = pj.get('weight')
+        xhat = rstd = None
+        if w is not None:
+            rs = torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps)
+            xh = _r(x * rs)
+            y = _r(xh * w.float())
+            xhat, rstd = xh.to(torch.bfloat16), rs.reshape(-1).clone()
+        else:
+            y = x
+        y = y.view(batch, seq, heads, 128).permute(0, 2, 1, 3)
+        if pj.get('rope'):
+            y = _rope(y, cos, sin)
+        outs.append((y.to(torch.bfloat16).contiguous(), xhat, rstd))
+    return outs
+
+
+def wan_norm_rope_bwd(projs, batch, seq, heads, cos=None, sin=None):
+    C = heads * 128
+    dws = []
+    for pj in projs:
+        g = pj['dy'].float()
+        if pj.get('rope'):
+            g = _rope(g, cos, sin, transpose=True)
+        g = g.permute(0, 2, 1, 3).reshape(batch * seq, C)
+        w = pj.get('weight')
+        if w is not None:
+            xh = pj['xhat'].float()
+            dws.append((g * xh).sum(0))
+            dxh = g * w.float()
+            res = pj['rstd'][:, None] * (dxh - xh * (dxh * xh).mean(-1, keepdim=True))
+        else:
+            dws.append(None)
+            res = g
+        pj['dx'].copy_(res)
+    return dws
+
+
+def mod_fwd(temb, weight, bias):
+    s = _r(F.silu(temb.float()))
+    return (s @ weight.float().t() + (bias.float() if bias is not None else 0)).to(torch.bfloat16)
+
+
+def mod_bwd(dmod32, temb, weight, wgrad, accumulate, dtemb32):
+    d = _r(dmod32)
+    s = _r(F.silu(temb.float()))
+    if wgrad is not None:
+        g = d.t() @ s
+        wgrad.copy_(g + wgrad.float() if accumulate else g)
+    with torch.enable_grad():
+        t = temb.detach().float().clone().requires_grad_(True)
+        (sg,) = torch.autograd.grad(F.silu(t).sum(), t)
+    dtemb32.add_(_r(d @ weight.float()) * sg)
+    return d.sum(0)
+
+
+def install(monkeypatch, ops):
+    """replaces the kernel wrappers of `ops` (diffusion_pipe_b200.ops) by the doubles above"""
+    for name in ('gemm', 'attn_fwd', 'attn_bwd', 'nchunks', 'ln_modulate_fwd', 'ln_modulate_bwd', 'gate_bwd', 'colreduce_finish',
+                 'colsum', 'wan_norm_rope_fwd', 'wan_norm_rope_bwd', 'mod_fwd', 'mod_bwd'):
+        monkeypatch.setattr(ops, name, globals()[name])
