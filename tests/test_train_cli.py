@@ -72,3 +72,30 @@ betas = [0.9, 0.99]
     assert run_dir2 == run_dir
     lines = [json.loads(l) for l in open(os.path.join(run_dir, 'metrics.jsonl'))]
     assert [l['x'] for l in lines if l['tag'] == 'train/loss'] == [1, 2, 3]
+
+
+@pytest.mark.parametrize('kind,example', [('flux', 'flux_synthetic.toml'), ('qwen_image', 'qwen_image_synthetic.toml'),
+                                          ('wan', 'wan_synthetic.toml')])
+def test_model_registry_and_synthetic_examples_feed_prepare_inputs(kind, example):
+    """every model family with an sm_100a path is reachable from the TOML surface, and its synthetic cached examples have
+    the keys / shapes its prepare_inputs consumes (CPU: lazy layers, no kernels)"""
+    from diffusion_pipe_b200 import data_feed
+    cfg = T.set_config_defaults(T.load_toml(os.path.join(ROOT, 'examples', example)))
+    assert cfg['model']['type'] == kind and kind in T.MODEL_TYPES
+    cfg['model']['lazy_layers'] = True
+    import importlib
+    mod, cls = T.MODEL_TYPES[kind]
+    model = getattr(importlib.import_module(mod), cls)(cfg, device='cpu')
+    syn = {'model': kind, 'num_examples': 4, 'resolution': 128, 'frames': 9, 'text_len': 16, 't5_dim': 64, 'clip_dim': 32,
+           'text_dim': 64}
+    exs = T.synthetic_examples(syn)
+    assert len(exs) == 4
+    batch = data_feed.BatchedDataset.collate(exs[:2])
+    feats, (target, mask) = model.prepare_inputs(batch)
+    assert mask is None and target.shape[0] == 2
+    micro = data_feed.split_batch((feats, (target, mask)), 2)
+    assert len(micro) == 2 and all(torch.is_tensor(t) for t in micro[0][0])      # None fields became empty tensors
+    specs = model.to_layers()
+    assert len(specs) == {'flux': 59, 'qwen_image': 62, 'wan': 42}[kind]
+    with pytest.raises(NotImplementedError):
+        T.make_model({'model': {'type': 'sdxl'}})

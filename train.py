@@ -138,16 +138,53 @@ class CachedExamples:
         return ex
 
 
+MODEL_TYPES = {   # config['model']['type'] -> (module, class): the model families with an sm_100a path (train.py:431-535)
+    'flux': ('diffusion_pipe_b200.flux', 'FluxPipeline'),
+    'qwen_image': ('diffusion_pipe_b200.qwen_image', 'QwenImagePipeline'),
+    'wan': ('diffusion_pipe_b200.wan', 'WanPipeline'),
+}
+
+
+def make_model(config):
+    import importlib
+    model_type = config['model']['type']
+    if model_type not in MODEL_TYPES:
+        raise NotImplementedError(f"model type '{model_type}': the sm_100a path covers {sorted(MODEL_TYPES)} "
+                                  '(SURVEY.md section 8); the other model definitions of the reference are out of scope')
+    mod, cls = MODEL_TYPES[model_type]
+    return getattr(importlib.import_module(mod), cls)(config)
+
+
+def synthetic_examples(syn):
+    """random cached examples with the keys and shapes the reference's caching step produces for each model family
+    (models/flux.py:312-321, models/qwen_image.py:302-318,385-392, models/wan/wan.py:262-330)"""
+    n, res = syn.get('num_examples', 16), syn.get('resolution', 1024)
+    kind = syn.get('model', 'flux')
+    g = torch.Generator().manual_seed(syn.get('seed', 0))
+    h = w = res // 8
+    if kind == 'flux':
+        return [{'latents': torch.randn(16, h, w, generator=g),
+                 't5_embed': torch.randn(syn.get('text_len', 512), syn.get('t5_dim', 4096), generator=g).bfloat16(),
+                 'clip_embed': torch.randn(syn.get('clip_dim', 768), generator=g).bfloat16(), 'mask': None} for _ in range(n)]
+    if kind == 'qwen_image':
+        return [{'latents': torch.randn(16, 1, h, w, generator=g),
+                 'prompt_embeds': torch.randn(syn.get('text_len', 256), syn.get('text_dim', 3584), generator=g).bfloat16(),
+                 'mask': None} for _ in range(n)]
+    if kind == 'wan':
+        frames = (syn.get('frames', 33) - 1) // 4 + 1            # VAE temporal stride 4 (models/wan/configs.py:63)
+        tl = syn.get('text_len', 512)
+        return [{'latents': torch.randn(16, frames, h, w, generator=g),
+                 'text_embeddings': torch.randn(tl, syn.get('text_dim', 4096), generator=g).bfloat16(),
+                 'seq_lens': torch.tensor(syn.get('prompt_len', tl)), 'mask': None} for _ in range(n)]
+    raise ValueError(f"[synthetic] model = '{kind}': expected one of flux, qwen_image, wan")
+
+
 def load_size_buckets(dataset_config):
     out = []
     if syn := dataset_config.get('synthetic', None):
-        n, res = syn.get('num_examples', 16), syn.get('resolution', 1024)
-        g = torch.Generator().manual_seed(syn.get('seed', 0))
-        exs = [{'latents': torch.randn(16, res // 8, res // 8, generator=g),
-                't5_embed': torch.randn(syn.get('text_len', 512), syn.get('t5_dim', 4096), generator=g).bfloat16(),
-                'clip_embed': torch.randn(syn.get('clip_dim', 768), generator=g).bfloat16(), 'mask': None}
-               for _ in range(n)]
-        out.append(CachedExamples(exs, (1.0, res, res, 1), syn.get('num_repeats', 1)))
+        res = syn.get('resolution', 1024)
+        frames = syn.get('frames', 33) if syn.get('model', 'flux') == 'wan' else 1
+        out.append(CachedExamples(synthetic_examples(syn), (1.0, res, res, frames), syn.get('num_repeats', 1)))
     for d in dataset_config.get('directory', []):
         exs = torch.load(d['path'], map_location='cpu', weights_only=False)
         by_shape = {}
@@ -244,12 +281,7 @@ def main(argv=None):
         dist.init_distributed()
     is_main = dist.get_rank() == 0
 
-    model_type = config['model']['type']
-    if model_type != 'flux':
-        raise NotImplementedError(f"model type '{model_type}': only 'flux' has an sm_100a path in this round "
-                                  '(SURVEY.md section 8: Wan / Qwen-Image are the next rows)')
-    from diffusion_pipe_b200 import flux
-    model = flux.FluxPipeline(config)
+    model = make_model(config)
 
     dataset_config = load_toml(config['dataset'])
     ds_config, micro_batch_size_per_gpu = make_ds_config(config)
