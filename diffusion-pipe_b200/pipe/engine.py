@@ -135,11 +135,27 @@ class PipelineEngine:
         if self.zb_stage_weights is None and getattr(model, 'parts', None) is not None and len(model.parts) == self.num_stages + 1:
             self.zb_stage_weights = [max(1, int(model.parts[i + 1] - model.parts[i])) for i in range(self.num_stages)]
         self._wgrad_queues = {}
+        self._broadcast_model()
         self.link = self._make_link()
         self.total_loss = None
         self.fwd_losses = []
         self._data_iter = None
         self._busy_ms = 0.0
+
+    def _broadcast_model(self):
+        """utils/patches.py:163-172 (installed over DeepSpeedEngine._broadcast_model): at engine construction every
+        data-parallel replica takes the TRAINABLE parameters of the first replica of its stage (frozen ones are loaded
+        identically from disk and are not sent).  Parameters that alias one fused allocation are sent once."""
+        if not self.is_data_parallel:
+            return
+        group = self.grid.get_data_parallel_group()
+        src = self.grid.dp_group[0]
+        seen = set()
+        for p in self.module.parameters():
+            if not p.requires_grad or p.data_ptr() in seen:
+                continue
+            seen.add(p.data_ptr())
+            dist.broadcast(p.data, src, group=group)
 
     # ------------------------------------------------------------------ DeepSpeed-compatible accessors
     def is_first_stage(self):

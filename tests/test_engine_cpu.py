@@ -27,7 +27,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, stages, outdir, partition, schedule='1f1b'):
+def _worker(rank, world, port, stages, outdir, partition, schedule='1f1b', perturb=False):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
@@ -36,6 +36,12 @@ def _worker(rank, world, port, stages, outdir, partition, schedule='1f1b'):
     torch.set_num_threads(1)
     dist.init_distributed('gloo')
     layers = toy_model.make_layers()
+    if perturb and rank > 0:      # a replica that was initialised differently: the engine must overwrite it (E11)
+        with torch.no_grad():
+            for l in layers:
+                for p in (l.parameters() if hasattr(l, 'parameters') else []):
+                    if p.requires_grad:
+                        p.add_(0.37)
     pm = ManualPipelineModule(layers=layers, num_stages=stages, partition_method=partition,
                               manual_partition_split=[3] if partition == 'manual' else None, loss_fn=toy_model.loss_fn,
                               dynamic_shape=True, device=torch.device('cpu'))
@@ -80,7 +86,7 @@ def _reference(dp_world):
     return losses, norms, ev, sd
 
 
-def _run(world, stages, partition='uniform', schedule='1f1b'):
+def _run(world, stages, partition='uniform', schedule='1f1b', perturb=False):
     with tempfile.TemporaryDirectory() as d:
         port = _free_port()
         if world == 1:
@@ -89,7 +95,7 @@ def _run(world, stages, partition='uniform', schedule='1f1b'):
             if tdist.is_initialized():
                 tdist.destroy_process_group()
         else:
-            mp.spawn(_worker, args=(world, port, stages, d, partition, schedule), nprocs=world, join=True)
+            mp.spawn(_worker, args=(world, port, stages, d, partition, schedule, perturb), nprocs=world, join=True)
         return [torch.load(os.path.join(d, f'rank{r}.pt'), weights_only=False) for r in range(world)]
 
 
@@ -125,6 +131,12 @@ def test_two_stages_parameter_partition():
 def test_data_parallel_world_2():
     res = _run(2, 1)
     assert [r['dp'] for r in res] == [0, 1]
+    _check(res, 2)
+
+
+def test_engine_broadcasts_trainable_parameters_over_the_dp_group():
+    """utils/patches.py:163-172: replica 1 starts from different weights and must end up training rank 0's model"""
+    res = _run(2, 1, 'uniform', '1f1b', perturb=True)
     _check(res, 2)
 
 
