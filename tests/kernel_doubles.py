@@ -55,12 +55,67 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, epilogue=EPI_STORE, bias=Non
         res = aux.float() + _r(g * y)
     elif epilogue == EPI_MUL_GELU_GRAD:
         res = acc * _gelu_grad(aux.float())
+    elif epilogue == EPI_QKV_ROPE:
+        return _qkv_rope_epilogue(acc, qkv, rows_per_batch or Mr, out, out2)
     else:
         raise NotImplementedError(epilogue)
     if out is None:
         out = torch.empty(res.shape, dtype=torch.bfloat16)
     out.copy_(res)
     return out
+
+
+def make_qkv_epilogue(q, k, v, q_norm_w, k_norm_w, rope_cos, rope_sin, heads, seq_total, seq_offset, qhat=None, khat=None,
+                      q_rstd=None, k_rstd=None, eps=1e-6):
+    return dict(q=q, k=k, v=v, wq=q_norm_w, wk=k_norm_w, cos=rope_cos, sin=rope_sin, heads=heads, seq_total=seq_total,
+                seq_offset=seq_offset, qhat=qhat, khat=khat, q_rstd=q_rstd, k_rstd=k_rstd, eps=eps)
+
+
+def _qkv_rope_epilogue(acc, e, rows_per_batch, out, out2):
+    """columns [0, 3C): bias added -> bf16 -> per-head RMSNorm (q, k) -> RoPE -> head-major scatter at seq_offset;
+    columns >= 3C (single block): pre-activation to out2, GELU(tanh) to out"""
+    H = e['heads']
+    C = H * 128
+    M = acc.shape[0]
+    B = M // rows_per_batch
+    L, off = rows_per_batch, e['seq_offset']
+    y = _r(acc[:, :3 * C]).view(B, L, 3, H, 128).permute(2, 0, 3, 1, 4)          # [3, B, H, L, 128]
+    cos, sin = e['cos'][off:off + L], e['sin'][off:off + L]
+    for i, (dst, w, hat, rstd) in enumerate(((e['q'], e['wq'], e['qhat'], e['q_rstd']), (e['k'], e['wk'], e['khat'], e['k_rstd']))):
+        rs = torch.rsqrt(y[i].pow(2).mean(-1, keepdim=True) + e['eps'])
+        xh = _r(y[i] * rs)
+        val = _rope(_r(xh * w.float()), cos, sin)
+        dst[:, :, off:off + L] = val.to(torch.bfloat16)
+        if hat is not None:
+            hat[:, :, off:off + L] = xh.to(torch.bfloat16)
+        if rstd is not None:
+            rstd[:, :, off:off + L] = rs.squeeze(-1)
+    e['v'][:, :, off:off + L] = y[2].to(torch.bfloat16)
+    if acc.shape[1] > 3 * C:
+        u = _r(acc[:, 3 * C:])
+        if out2 is not None:
+            out2.copy_(u)
+        out.copy_(F.gelu(u, approximate='tanh'))
+    return out
+
+
+def qknorm_rope_bwd(dq, dk, dv, qhat, khat, q_rstd, k_rstd, q_norm_w, k_norm_w, rope_cos, rope_sin, dqkv, dbias, dw,
+                    batch, heads, seq_total, seq_offset, rows_per_batch):
+    L, off, H = rows_per_batch, seq_offset, heads
+    C = H * 128
+    cos, sin = rope_cos[off:off + L], rope_sin[off:off + L]
+    cols = []
+    for i, (g, hat, rstd, w) in enumerate(((dq, qhat, q_rstd, q_norm_w), (dk, khat, k_rstd, k_norm_w))):
+        dy = _rope(g[:, :, off:off + L].float(), cos, sin, transpose=True)
+        xh = hat[:, :, off:off + L].float()
+        dw[i] += (dy * xh).sum((0, 1, 2))
+        dxh = dy * w.float()
+        res = rstd[:, :, off:off + L, None] * (dxh - xh * (dxh * xh).mean(-1, keepdim=True))
+        cols.append(res.permute(0, 2, 1, 3).reshape(batch * L, C))
+    cols.append(dv[:, :, off:off + L].float().permute(0, 2, 1, 3).reshape(batch * L, C))
+    full = torch.cat(cols, dim=1)
+    dqkv[:, :3 * C].copy_(full)
+    dbias[:3 * C] += full.sum(0)
 
 
 def _heads(t):       # [B,H,L,128] -> fp32
@@ -237,8 +292,17 @@ def mod_bwd(dmod32, temb, weight, wgrad, accumulate, dtemb32):
     return d.sum(0)
 
 
+def mse_loss(out, target, mask=None, want_grad=True):
+    d = out.float() - target.float()
+    w = mask.float().expand_as(d) if mask is not None else torch.ones_like(d)
+    loss = (d * d * w).mean()
+    dout = (2.0 * d * w / d.numel()).to(torch.bfloat16) if want_grad else None
+    return loss, dout
+
+
 def install(monkeypatch, ops):
     """replaces the kernel wrappers of `ops` (diffusion_pipe_b200.ops) by the doubles above"""
-    for name in ('gemm', 'attn_fwd', 'attn_bwd', 'nchunks', 'ln_modulate_fwd', 'ln_modulate_bwd', 'gate_bwd', 'colreduce_finish',
-                 'colsum', 'wan_norm_rope_fwd', 'wan_norm_rope_bwd', 'mod_fwd', 'mod_bwd'):
+    for name in ('gemm', 'make_qkv_epilogue', 'qknorm_rope_bwd', 'attn_fwd', 'attn_bwd', 'nchunks', 'ln_modulate_fwd',
+                 'ln_modulate_bwd', 'gate_bwd', 'colreduce_finish', 'colsum', 'wan_norm_rope_fwd', 'wan_norm_rope_bwd', 'mod_fwd',
+                 'mod_bwd', 'mse_loss'):
         monkeypatch.setattr(ops, name, globals()[name])
