@@ -162,6 +162,15 @@ def run_reference_arm(a):
 # ---------------------------------------------------------------------------------------------------------------------
 # the GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
+def gemm_traffic_from_profile():
+    """dram bytes (read + write) per launch of the dominant GEMM shape, from the committed ncu --set full capture"""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_gemm_traffic.json')) as f:
+            return json.load(f)['dram_bytes_total']
+    except Exception:
+        return None
+
+
 def flop_balanced_split(n_double, n_single, stages):
     """Stage boundaries over [embed, double..., single..., out]: every block costs the same FLOPs, the
     embedding rides with the first block and the output layer with the last.  When the block count does not divide, the
@@ -361,7 +370,7 @@ def main():
         achieved = gemm_fl / gemm_ms / 1e9 if gemm_ms > 0 else 0.0
         roof = {'bound': 'tensor', 'kernel': 'gemm_bf16_kernel (tcgen05, all epilogues/layouts)', 'achieved': achieved,
                 'peak': peak, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PF sustained',
-                'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+                'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': gemm_traffic_from_profile(),
                 'launches_timed': n_gemm, 'avg_launch_ms': gemm_ms / max(1, n_gemm),
                 'share_of_step': gemm_ms / (ms_dev if ms_dev else 1),
                 'attention': {'achieved': attn_fl / attn_ms / 1e9 if attn_ms > 0 else None, 'unit': 'TFLOP/s (algorithmic: 4LqLkD fwd, 2.5x bwd)',
