@@ -119,15 +119,18 @@ __global__ void ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, int6
 
 // backward: g = dxn * bf16(1+scale);  dx = rstd * (g - mean(g) - xhat * mean(g*xhat)) (+ dres)
 // partial column sums: slot 0 = sum_rows dxn * xhat (dscale), slot 1 = sum_rows dxn (dshift)
-// grid (nchunk, batch), block D/8 threads
-__global__ void ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, int64_t lddxn,
+// grid (nchunk, batch), block D/8 threads.  RGT rows are processed together; MAXT bounds the block size so that the
+// register file holds it: <4, 512> (128 registers, D <= 4096: Flux / Qwen 3072) and <2, 1024> (64 registers, D <= 8192:
+// Wan 5120 = 640 threads, which 128 registers per thread do not fit).
+template <int RGT, int MAXT>
+__global__ void __launch_bounds__(MAXT) ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, int64_t lddxn,
                                        const __nv_bfloat16* __restrict__ x, int64_t ldx,
                                        const __nv_bfloat16* __restrict__ scale, int64_t mod_stride,
                                        const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                        const __nv_bfloat16* __restrict__ dres, int64_t lddres,
                                        __nv_bfloat16* __restrict__ dx, int64_t lddx, float* __restrict__ partials,
                                        int rows_per_batch, int D, int flags) {
-  __shared__ float red[32 * 2 * RG];
+  __shared__ float red[32 * 2 * RGT];
   const int b = blockIdx.y;
   const int col = threadIdx.x * 8;
   float sc[8];
@@ -140,11 +143,11 @@ __global__ void ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, in
 #pragma unroll
   for (int j = 0; j < 8; ++j) { acc_scale[j] = 0.f; acc_shift[j] = 0.f; }
   const int rbeg = blockIdx.x * ROW_CHUNK;
-  for (int r0 = rbeg; r0 < rbeg + ROW_CHUNK; r0 += RG) {
-    float g[RG][8], xh[RG][8], rs[RG];
-    float sums[2 * RG];
+  for (int r0 = rbeg; r0 < rbeg + ROW_CHUNK; r0 += RGT) {
+    float g[RGT][8], xh[RGT][8], rs[RGT];
+    float sums[2 * RGT];
 #pragma unroll
-    for (int i = 0; i < RG; ++i) {
+    for (int i = 0; i < RGT; ++i) {
       const int r = r0 + i;
       sums[2 * i] = 0.f; sums[2 * i + 1] = 0.f;
       if (r < rows_per_batch) {
@@ -169,9 +172,9 @@ __global__ void ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, in
         for (int j = 0; j < 8; ++j) { g[i][j] = 0.f; xh[i][j] = 0.f; }
       }
     }
-    block_sum<2 * RG>(sums, red);
+    block_sum<2 * RGT>(sums, red);
 #pragma unroll
-    for (int i = 0; i < RG; ++i) {
+    for (int i = 0; i < RGT; ++i) {
       const int r = r0 + i;
       if (r >= rows_per_batch) continue;
       const int64_t row = (int64_t)b * rows_per_batch + r;
@@ -454,6 +457,7 @@ extern "C" int dpipe_ln_modulate_fwd_ex(const void* x, int64_t ldx, const void* 
   if (rc) return rc;
   if (!x || !scale || !shift || !out) return fail(DPIPE_EINVAL, "dpipe_ln_modulate_fwd: null pointer");
   if (ldx % 8 || ldo % 8 || mod_stride % 8) return fail(DPIPE_EINVAL, "dpipe_ln_modulate_fwd: strides must be multiples of 8");
+  if (D > 6144) return fail(DPIPE_EINVAL, "dpipe_ln_modulate_fwd: D=%d > 6144 (one CTA of D/8 threads at 79 registers must fit the register file)", D);
   dim3 grid((rows_per_batch + RG - 1) / RG, batch);
   ln_modulate_fwd_kernel<<<grid, D / 8, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)scale, (const bf16*)shift,
                                                                     mod_stride, (bf16*)out, ldo, mean, rstd, rows_per_batch, D, eps, flags);
@@ -477,9 +481,14 @@ extern "C" int dpipe_ln_modulate_bwd_ex(const void* dxn, int64_t lddxn, const vo
   if (rc) return rc;
   if (!dxn || !x || !scale || !mean || !rstd || !dx || !partials) return fail(DPIPE_EINVAL, "dpipe_ln_modulate_bwd: null pointer");
   dim3 grid((rows_per_batch + ROW_CHUNK - 1) / ROW_CHUNK, batch);
-  ln_modulate_bwd_kernel<<<grid, D / 8, 0, (cudaStream_t)stream>>>((const bf16*)dxn, lddxn, (const bf16*)x, ldx, (const bf16*)scale,
-                                                                    mod_stride, mean, rstd, (const bf16*)dres, lddres, (bf16*)dx,
-                                                                    lddx, partials, rows_per_batch, D, flags);
+  if (D <= 4096)
+    ln_modulate_bwd_kernel<4, 512><<<grid, D / 8, 0, (cudaStream_t)stream>>>(
+        (const bf16*)dxn, lddxn, (const bf16*)x, ldx, (const bf16*)scale, mod_stride, mean, rstd, (const bf16*)dres, lddres,
+        (bf16*)dx, lddx, partials, rows_per_batch, D, flags);
+  else
+    ln_modulate_bwd_kernel<2, 1024><<<grid, D / 8, 0, (cudaStream_t)stream>>>(
+        (const bf16*)dxn, lddxn, (const bf16*)x, ldx, (const bf16*)scale, mod_stride, mean, rstd, (const bf16*)dres, lddres,
+        (bf16*)dx, lddx, partials, rows_per_batch, D, flags);
   DPIPE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

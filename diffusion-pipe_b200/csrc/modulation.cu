@@ -175,6 +175,8 @@ extern "C" int dpipe_mod_bwd(const float* dmod, int64_t ldd, const void* temb, c
                              float* dbias, float* partials, float* dtemb, int B, int N, int K, void* stream) {
   if (!dmod || !temb || !W || !partials || !dtemb || B < 1 || B > MOD_MAX_B || K % 256 || K / 8 > 1024)
     return fail(DPIPE_EINVAL, "dpipe_mod_bwd: bad arguments (B=%d N=%d K=%d)", B, N, K);
+  if (B > 4 && K > 3328)   // mod_bwd_kernel<8>: 155 registers x K/8 threads must fit the register file
+    return fail(DPIPE_EINVAL, "dpipe_mod_bwd: batch %d with K=%d is not supported (batch <= 4 for K > 3328)", B, K);
   const int nchunk = dpipe_mod_bwd_chunks(N);
   cudaStream_t s = (cudaStream_t)stream;
   if (B <= 2)

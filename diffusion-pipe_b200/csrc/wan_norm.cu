@@ -194,8 +194,8 @@ __global__ void wan_norm_rope_bwd_kernel(const WanNormBwdParams p) {
 using namespace dpipe;
 
 static int wn_check(const char* fn, int B, int L, int H, int nproj) {
-  if (B < 1 || L < 1 || H < 1 || H * 128 / 8 > 1024 || (H * 128) % 256 || nproj < 1 || nproj > 3)
-    return fail(DPIPE_EINVAL, "%s: bad geometry B=%d L=%d H=%d nproj=%d (width H*128 must be a multiple of 256, <= 8192)", fn, B, L, H, nproj);
+  if (B < 1 || L < 1 || H < 1 || H > 56 || (H * 128) % 256 || nproj < 1 || nproj > 3)   // 16 H threads x 72 registers per CTA
+    return fail(DPIPE_EINVAL, "%s: bad geometry B=%d L=%d H=%d nproj=%d (width H*128 must be a multiple of 256, <= 7168)", fn, B, L, H, nproj);
   return 0;
 }
 

@@ -117,9 +117,10 @@ def test_attention_rescale_path(ops):
     _check(lse * math.log(2.0), lseref, 1e-3)
 
 
-def test_ln_modulate_and_gate_backward(ops):
+@pytest.mark.parametrize('D', [512, 5120])      # 5120 = Wan-14B width: 640-thread CTAs take the <2, 1024> backward variant
+def test_ln_modulate_and_gate_backward(ops, D):
     torch.manual_seed(5)
-    B, L, D = 2, 50, 512
+    B, L = 2, 50
     x = torch.randn(B * L, D, device='cuda').bfloat16()
     mod = (0.3 * torch.randn(B, 3 * D, device='cuda')).bfloat16()
     scale, shift, gate = mod[:, D:2 * D], mod[:, :D], mod[:, 2 * D:]
