@@ -319,6 +319,7 @@ class FluxPipeline:
         self.dtype, self.device = dtype, device
         self.pipeline_model = None
         self.model_engine = None
+        self.adapter_config = None
         if self.model_config.get('lazy_layers', False):
             # Stage-local construction: to_layers() hands the engine LayerSpecs and only the layers of this rank's
             # stage are ever materialised (12 B parameters do not fit eight times on the host, and need not).
@@ -349,21 +350,21 @@ class FluxPipeline:
                                  CombinedTimestepGuidanceTextProjEmbeddings(dim, cfg['pooled_projection_dim'], dtype, d,
                                                                             cfg.get('guidance_embeds', True)),
                                  _plain(dim, cfg['joint_attention_dim'], dtype, d), tuple(cfg['axes_dims_rope']))
-            return name_params(w, {'x_embedder.': 'x_embedder.', 'time_text_embed.': 'time_text_embed.',
-                                   'context_embedder.': 'context_embedder.'})
+            return self._adapt(name_params(w, {'x_embedder.': 'x_embedder.', 'time_text_embed.': 'time_text_embed.',
+                                               'context_embedder.': 'context_embedder.'}), dev)
 
         def build_double(i, dev=None):
             w = TransformerWrapper(FluxTransformerBlock(dim, heads, 4, dtype, dev or device), i)
-            return name_params(w, {'block.': f'transformer_blocks.{i}.'})
+            return self._adapt(name_params(w, {'block.': f'transformer_blocks.{i}.'}), dev)
 
         def build_single(i, dev=None):
             w = SingleTransformerWrapper(FluxSingleTransformerBlock(dim, heads, 4, dtype, dev or device), i)
-            return name_params(w, {'block.': f'single_transformer_blocks.{i}.'})
+            return self._adapt(name_params(w, {'block.': f'single_transformer_blocks.{i}.'}), dev)
 
         def build_out(dev=None):
             d = dev or device
             w = OutputWrapper(_AdaNorm(dim, 2, dtype, d), _plain(cfg['in_channels'], dim, dtype, d))
-            return name_params(w, {'norm_out.': 'norm_out.', 'proj_out.': 'proj_out.'})
+            return self._adapt(name_params(w, {'norm_out.': 'norm_out.', 'proj_out.': 'proj_out.'}), dev)
 
         def count(fn, *a):
             return sum(p.numel() for p in fn(*a, dev='meta').parameters())
@@ -399,6 +400,41 @@ class FluxPipeline:
 
     def load_diffusion_model(self):
         pass
+
+    # ---- adapters (models/base.py:263-303, train.py:531-535) ----
+    def configure_adapter(self, adapter_config):
+        """LoRA on every Linear of the transformer blocks, everything else frozen (lora.py).  Call before to_layers() /
+        the engine is built, as the reference does (train.py:531 precedes :597)."""
+        if adapter_config.get('type', 'lora') != 'lora':
+            raise NotImplementedError(f"adapter type {adapter_config.get('type')!r}: only 'lora' is built for the sm_100a path")
+        if adapter_config.get('dropout', 0.0):
+            raise NotImplementedError('lora dropout > 0 is not supported on the sm_100a path')
+        self.adapter_config = dict(adapter_config)
+        if self.transformer is not None:
+            self._adapt(self.transformer, None)
+
+    def _adapt(self, module, dev):
+        """freezes `module` and attaches the configured adapters to the blocks inside it (no-op without an adapter or on
+        the meta device used for parameter counting)"""
+        if self.adapter_config is None or dev == 'meta':
+            return module
+        from . import lora
+        for p in module.parameters():
+            p.requires_grad_(False)
+        dtype = self.adapter_config.get('dtype', torch.bfloat16)
+        if isinstance(dtype, str):
+            dtype = {'bfloat16': torch.bfloat16, 'float32': torch.float32}[dtype]
+        if dtype != torch.bfloat16:
+            raise NotImplementedError('adapter dtype must be bfloat16 on the sm_100a path')
+        lora.attach(module, int(self.adapter_config['rank']), dtype)
+        return module
+
+    def save_adapter(self, save_dir, peft_state_dict):
+        """models/flux.py:290-296: ComfyUI-style keys are produced by the caller; this writes them as safetensors"""
+        from safetensors.torch import save_file
+        os.makedirs(save_dir, exist_ok=True)
+        save_file({k: v.contiguous() for k, v in peft_state_dict.items()}, os.path.join(save_dir, 'adapter_model.safetensors'),
+                  metadata={'format': 'pt'})
 
     def get_param_groups(self, parameters):
         return [{'params': parameters}]

@@ -341,6 +341,10 @@ class FluxTransformerBlock(nn.Module):
 
     def forward(self, hidden_states, encoder_hidden_states, temb, image_rotary_emb, joint_attention_kwargs=None):
         cos, sin = image_rotary_emb
+        if 'lora' in self.__dict__:          # adapters attached (lora.py): frozen base, K-extended GEMMs
+            from .lora import FluxDoubleBlockLoraFn
+            h, e = FluxDoubleBlockLoraFn.apply(self, hidden_states, encoder_hidden_states, temb, cos, sin)
+            return e, h
         h, e = FluxDoubleBlockFn.apply(self, hidden_states, encoder_hidden_states, temb, cos, sin)
         return e, h
 
@@ -461,5 +465,9 @@ class FluxSingleTransformerBlock(nn.Module):
 
     def forward(self, hidden_states, encoder_hidden_states, temb, image_rotary_emb, joint_attention_kwargs=None):
         cos, sin = image_rotary_emb
+        if 'lora' in self.__dict__:
+            from .lora import FluxSingleBlockLoraFn
+            h, e = FluxSingleBlockLoraFn.apply(self, hidden_states, encoder_hidden_states, temb, cos, sin)
+            return e, h
         h, e = FluxSingleBlockFn.apply(self, hidden_states, encoder_hidden_states, temb, cos, sin)
         return e, h

@@ -1,0 +1,503 @@
+"""LoRA on the fused Flux / Qwen-Image blocks — the adapter path of the reference (models/base.py:263-303:
+`peft.LoraConfig(r=rank, lora_alpha=rank, lora_dropout=dropout, bias='none', target_modules=<every nn.Linear inside the
+blocks named in adapter_target_modules>)`; train.py:115-133 forces alpha = rank, i.e. scaling 1).
+
+    y = x W^T + b + (x A^T) B^T          W, b frozen;  A [r, K], B [N, r] trained
+
+**LoRA as a K-extension.**  Both terms are contractions feeding one accumulator, so the adapter rides the SAME tcgen05
+GEMM — and therefore every fused epilogue (QKV->RMSNorm->RoPE scatter, bias+GELU, gate*y+residual, x GELU') — instead
+of a second GEMM plus an elementwise add:
+
+    forward   [x | t] . [W | B]^T        t = x A^T   (r extra K columns; one small GEMM produces t in place)
+    backward  [dy | dt] . [W ; A]        dt = dy B   (r extra reduction rows; same epilogues as the dense dgrad)
+    grads     dB = dy^T t,  dA = dt^T x  (two skinny GEMMs, queued with the other weight-gradient work)
+
+Each site owns ONE buffer `[(N + R) x (K + R)]` holding `[[W | B], [A | 0]]`: the forward operand is its first N rows,
+the dgrad operand its first K columns, so W is stored once and no transposes or copies of W exist.  Projections that the
+kernels consume fused (q, k, v of a stream) keep per-projection adapters: A's are stacked, B's are block-diagonal.
+The trained factors are ordinary contiguous Parameters (`<linear>.lora_A.weight`, `<linear>.lora_B.weight`, PEFT's
+state-dict names); they are copied into the site buffer when their version counter moves (after an optimizer step).
+The frozen base produces no weight gradient: a LoRA step runs 2/3 of the dense-training FLOPs.
+
+Supported: rank % 8 == 0 (16-byte rows for TMA), dropout 0, Flux double / single blocks and Qwen-Image blocks.
+Modulation linears (AdaLayerNormZero.linear, batch-row) get their adapter through a [batch, r] torch matmul.
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import ops
+from .flux_blocks import HD, _acc_vec, _grad_buf, _mod_bwd, _mod_fwd
+
+
+class _LoraW(nn.Module):
+    def __init__(self, weight):
+        super().__init__()
+        self.weight = weight
+
+
+def _kaiming_a(r, k, dtype, device):
+    w = torch.empty(r, k, dtype=torch.float32, device=device)
+    nn.init.kaiming_uniform_(w, a=math.sqrt(5))              # peft LoraLayer.reset_lora_parameters (default init)
+    return nn.Parameter(w.to(dtype))
+
+
+class LoraSite:
+    """One GEMM site = one or several nn.Linear-like holders (weight [n_i, K], bias) that the kernels consume as one
+    [N, K] matrix, plus their LoRA factors.  See the module docstring for the buffer layout."""
+
+    def __init__(self, lins, rank, dtype=torch.bfloat16):
+        if rank % 8:
+            raise ValueError(f'LoRA rank must be a multiple of 8 on the sm_100a path (got {rank})')
+        self.lins, self.r = list(lins), rank
+        w0 = self.lins[0].weight
+        dev = w0.device
+        self.K = w0.shape[1]
+        self.sizes = [l.weight.shape[0] for l in self.lins]
+        self.N = sum(self.sizes)
+        self.R = rank * len(self.lins)
+        self.buf = torch.zeros((self.N + self.R, self.K + self.R), dtype=w0.dtype, device=dev)
+        self.bias = torch.zeros(self.N, dtype=w0.dtype, device=dev)
+        row = 0
+        self.A, self.B = [], []
+        for i, l in enumerate(self.lins):
+            n = self.sizes[i]
+            self.buf[row:row + n, :self.K].copy_(l.weight.detach())
+            if l.bias is not None:
+                self.bias[row:row + n].copy_(l.bias.detach())
+            # the base parameters now live inside the site buffer (frozen): checkpoints load straight into it
+            l.weight.data = self.buf[row:row + n, :self.K]
+            l.weight.requires_grad_(False)
+            if l.bias is not None:
+                l.bias.data = self.bias[row:row + n]
+                l.bias.requires_grad_(False)
+            a = _kaiming_a(rank, self.K, dtype, dev)
+            b = nn.Parameter(torch.zeros(n, rank, dtype=dtype, device=dev))
+            l.lora_A, l.lora_B = _LoraW(a), _LoraW(b)
+            self.A.append(a)
+            self.B.append(b)
+            row += n
+        self._versions = None
+        self.refresh()
+
+    # ---- operand views -------------------------------------------------------------------------------------------
+    @property
+    def w_fwd(self):        # [N, K + R]   ([W | B]),  K-major B operand of the forward GEMM
+        return self.buf[:self.N]
+
+    @property
+    def w_dgrad(self):      # [N + R, K]   ([W ; A]),  MN-major (b_mn) operand of the input-gradient GEMM
+        return self.buf[:, :self.K]
+
+    @property
+    def a_all(self):        # [R, K]       stacked A's
+        return self.buf[self.N:, :self.K]
+
+    @property
+    def b_blk(self):        # [N, R]       block-diagonal B's
+        return self.buf[:self.N, self.K:]
+
+    def refresh(self):
+        """copies the trained factors into the site buffer if an optimizer step (or a load) changed them"""
+        v = tuple(p._version for p in self.A + self.B)
+        if v == self._versions:
+            return
+        row = 0
+        with torch.no_grad():
+            for i, (a, b) in enumerate(zip(self.A, self.B)):
+                n = self.sizes[i]
+                self.buf[self.N + i * self.r:self.N + (i + 1) * self.r, :self.K].copy_(a)
+                self.buf[row:row + n, self.K + i * self.r:self.K + (i + 1) * self.r].copy_(b)
+                row += n
+        self._versions = tuple(p._version for p in self.A + self.B)
+
+    # ---- the three small GEMMs ---------------------------------------------------------------------------------------
+    def alloc_in(self, rows, device):
+        """[rows, K + R] activation buffer: the producing kernel writes x into [:, :K], project() fills the tail"""
+        return torch.empty((rows, self.K + self.R), dtype=torch.bfloat16, device=device)
+
+    def alloc_dy(self, rows, device):
+        return torch.empty((rows, self.N + self.R), dtype=torch.bfloat16, device=device)
+
+    def project(self, xa):
+        """t = x A^T into the tail columns of xa (rows of xa may be a slice of a larger buffer)"""
+        ops.gemm(xa[:, :self.K], self.a_all, out=xa[:, self.K:])
+
+    def backproject(self, dya):
+        """dt = dy B into the tail columns of dya"""
+        ops.gemm(dya[:, :self.N], self.b_blk, b_mn=True, out=dya[:, self.N:])
+
+    def queue_grads(self, xa, dya):
+        """dA_i = dt_i^T x,  dB_i = dy_i^T t_i   (weight-gradient work: deferred in the zero-bubble order)"""
+        def wgrad(self=self, xa=xa, dya=dya):
+            K, N, r = self.K, self.N, self.r
+            row = 0
+            for i, (a, b) in enumerate(zip(self.A, self.B)):
+                n = self.sizes[i]
+                if a.requires_grad:
+                    g, acc = _grad_buf(a)
+                    ops.gemm(dya[:, N + i * r:N + (i + 1) * r], xa[:, :K], a_mn=True, b_mn=True, out=g, accumulate=acc)
+                if b.requires_grad:
+                    g, acc = _grad_buf(b)
+                    ops.gemm(dya[:, row:row + n], xa[:, K + i * r:K + (i + 1) * r], a_mn=True, b_mn=True, out=g, accumulate=acc)
+                row += n
+        ops.defer(wgrad)
+
+
+class ModLora:
+    """adapter of a batch-row modulation linear (AdaLayerNormZero.linear): mod += (silu(temb) A^T) B^T on [batch, r]"""
+
+    def __init__(self, lin, rank, dtype=torch.bfloat16):
+        self.lin = lin
+        dev = lin.weight.device
+        lin.weight.requires_grad_(False)
+        if lin.bias is not None:
+            lin.bias.requires_grad_(False)
+        self.a = _kaiming_a(rank, lin.weight.shape[1], dtype, dev)
+        self.b = nn.Parameter(torch.zeros(lin.weight.shape[0], rank, dtype=dtype, device=dev))
+        lin.lora_A, lin.lora_B = _LoraW(self.a), _LoraW(self.b)
+
+    def fwd(self, temb):
+        s = torch.nn.functional.silu(temb.float()).to(torch.bfloat16)
+        t = (s.float() @ self.a.float().t()).to(torch.bfloat16)                    # lora_A output (bf16)
+        mod = _mod_fwd(temb, self.lin)
+        return (mod.float() + (t.float() @ self.b.float().t()).to(torch.bfloat16).float()).to(torch.bfloat16), (s, t)
+
+    def bwd(self, dmod32, temb, saved, d_temb32):
+        """accumulates d temb (fp32) and the factor gradients"""
+        s, t = saved
+        d = dmod32.to(torch.bfloat16).float()
+        _mod_bwd(dmod32, temb, self.lin, d_temb32)                                # frozen base: only the d temb part
+        dt = d @ self.b.float()
+        _acc_vec(self.b, d.t() @ t.float())
+        _acc_vec(self.a, dt.t() @ s.float())
+        ds = dt @ self.a.float()
+        tf = temb.float()
+        sg = torch.sigmoid(tf)
+        d_temb32.add_(ds.to(torch.bfloat16).float() * (sg * (1 + tf * (1 - sg))))
+
+
+def _needs(p):
+    return p is not None and p.requires_grad
+
+
+# =====================================================================================================================
+# double-stream block (Flux, Qwen-Image)
+# =====================================================================================================================
+class FluxDoubleBlockLoraFn(torch.autograd.Function):
+    """FluxDoubleBlockFn (flux_blocks.py) with every Linear of the block carrying a LoRA adapter and the base frozen."""
+
+    @staticmethod
+    def forward(ctx, blk, hidden, enc, temb, cos, sin):
+        lo = blk.lora
+        B, Li, D = hidden.shape
+        Lt = enc.shape[1]
+        Ltot = Li + Lt
+        H = blk.heads
+        dev = hidden.device
+        bf = torch.bfloat16
+        for s in lo['sites']:
+            s.refresh()
+        shp = (B, H, Ltot, HD)
+        q, k, v, qhat, khat = (torch.empty(shp, dtype=bf, device=dev) for _ in range(5))
+        q_rstd = torch.empty((B, H, Ltot), dtype=torch.float32, device=dev)
+        k_rstd = torch.empty((B, H, Ltot), dtype=torch.float32, device=dev)
+        spec = ((hidden, Li, Lt, lo['mod'], lo['qkv'], blk.attn.norm_q, blk.attn.norm_k),
+                (enc, Lt, 0, lo['mod_c'], lo['add_qkv'], blk.attn.norm_added_q, blk.attn.norm_added_k))
+        streams = []
+        for x3, L, off, ml, sq, nq, nk in spec:
+            st = {'L': L, 'off': off, 'x': x3.reshape(B * L, D)}
+            st['mod'], st['mod_saved'] = ml.fwd(temb)
+            m = st['mod']
+            xa = sq.alloc_in(B * L, dev)
+            _, st['mean1'], st['rstd1'] = ops.ln_modulate_fwd(st['x'], m[:, D:2 * D], m[:, 0:D], B, L, out=xa[:, :D])
+            sq.project(xa)
+            e = ops.make_qkv_epilogue(q, k, v, nq.weight, nk.weight, cos, sin, H, Ltot, off, qhat, khat, q_rstd, k_rstd)
+            ops.gemm(xa, sq.w_fwd, bias=sq.bias, epilogue=ops.EPI_QKV_ROPE, out=xa, rows_per_batch=L, qkv=e)
+            st['t_qkv'] = xa[:, D:].clone()          # [rows, R]: what the factor gradients need (x itself is recomputed)
+            streams.append(st)
+        so, sao = lo['to_out'], lo['to_add_out']
+        assert so.R == sao.R
+        oa = torch.empty((B * Ltot, H * HD + so.R), dtype=bf, device=dev)      # attention output + adapter columns
+        _, lse = ops.attn_fwd(q, k, v, out=oa)
+        oa3 = oa.view(B, Ltot, H * HD + so.R)
+        outs = []
+        tail = ((so, lo['ff1'], lo['ff2']), (sao, lo['ffc1'], lo['ffc2']))
+        for st, (swo, s1, s2) in zip(streams, tail):
+            L, off, m = st['L'], st['off'], st['mod']
+            st['y_attn'] = torch.empty((B * L, D), dtype=bf, device=dev)
+            st['x1'] = torch.empty((B * L, D), dtype=bf, device=dev)
+            for b in range(B):
+                rs = slice(b * L, (b + 1) * L)
+                rows = oa3[b, off:off + L]
+                swo.project(rows)
+                ops.gemm(rows, swo.w_fwd, bias=swo.bias, epilogue=ops.EPI_GATE_RES, aux=st['x'][rs], gate=m[b:b + 1, 2 * D:3 * D],
+                         out=st['x1'][rs], out2=st['y_attn'][rs], rows_per_batch=L)
+            x2a = s1.alloc_in(B * L, dev)
+            _, st['mean2'], st['rstd2'] = ops.ln_modulate_fwd(st['x1'], m[:, 4 * D:5 * D], m[:, 3 * D:4 * D], B, L, out=x2a[:, :D])
+            s1.project(x2a)
+            st['t_ff1'] = x2a[:, D:].clone()
+            st['u'] = torch.empty((B * L, s1.N), dtype=bf, device=dev)
+            ha = s2.alloc_in(B * L, dev)
+            ops.gemm(x2a, s1.w_fwd, bias=s1.bias, epilogue=ops.EPI_BIAS_GELU, out=ha[:, :s1.N], out2=st['u'])
+            s2.project(ha)
+            st['ha'] = ha
+            st['y_mlp'] = torch.empty((B * L, D), dtype=bf, device=dev)
+            x2 = ops.gemm(ha, s2.w_fwd, bias=s2.bias, epilogue=ops.EPI_GATE_RES, aux=st['x1'], gate=m[:, 5 * D:6 * D],
+                          out2=st['y_mlp'], rows_per_batch=L)
+            outs.append(x2.view(B, L, D))
+        ctx.blk = blk
+        ctx.streams = streams
+        ctx.attn = (q, k, v, qhat, khat, q_rstd, k_rstd, oa, lse)
+        ctx.save_for_backward(temb, cos, sin)
+        ctx.dims = (B, Li, Lt, D, H)
+        return outs[0], outs[1]
+
+    @staticmethod
+    def backward(ctx, d_hidden, d_enc):
+        blk = ctx.blk
+        lo = blk.lora
+        temb, cos, sin = ctx.saved_tensors
+        B, Li, Lt, D, H = ctx.dims
+        Ltot = Li + Lt
+        C = H * HD
+        dev = temb.device
+        bf = torch.bfloat16
+        q, k, v, qhat, khat, q_rstd, k_rstd, oa, lse = ctx.attn
+        so, sao = lo['to_out'], lo['to_add_out']
+        oa3 = oa.view(B, Ltot, C + so.R)
+        d_o = torch.empty((B * Ltot, C), dtype=bf, device=dev)
+        d_o3 = d_o.view(B, Ltot, C)
+        tail = ((so, lo['ff1'], lo['ff2']), (sao, lo['ffc1'], lo['ffc2']))
+        dmods, dx1s = [], []
+        for st, (swo, s1, s2), dxo in zip(ctx.streams, tail, (d_hidden, d_enc)):
+            L, off, m = st['L'], st['off'], st['mod']
+            dx2 = dxo.reshape(B * L, D)
+            if dx2.dtype != bf:
+                dx2 = dx2.to(bf)
+            dmod = torch.empty((B, 6 * D), dtype=torch.float32, device=dev)
+            # ---- MLP branch ----
+            dy2a = s2.alloc_dy(B * L, dev)
+            _, part = ops.gate_bwd(dx2, st['y_mlp'], m[:, 5 * D:6 * D], B, L, dy=dy2a[:, :D])
+            ops.colreduce_finish(part, per_sample0=dmod[:, 5 * D:6 * D])
+            s2.backproject(dy2a)
+            s2.queue_grads(st['ha'], dy2a)
+            dua = s1.alloc_dy(B * L, dev)
+            ops.gemm(dy2a, s2.w_dgrad, b_mn=True, epilogue=ops.EPI_MUL_GELU_GRAD, aux=st['u'], out=dua[:, :s1.N])
+            s1.backproject(dua)
+            x2a = s1.alloc_in(B * L, dev)
+            ops.ln_modulate_fwd(st['x1'], m[:, 4 * D:5 * D], m[:, 3 * D:4 * D], B, L, out=x2a[:, :D], save_stats=False)
+            x2a[:, D:].copy_(st['t_ff1'])
+            s1.queue_grads(x2a, dua)
+            dxn2 = ops.gemm(dua, s1.w_dgrad, b_mn=True)
+            dx1, part = ops.ln_modulate_bwd(dxn2, st['x1'], m[:, 4 * D:5 * D], st['mean2'], st['rstd2'], B, L, dres=dx2)
+            ops.colreduce_finish(part, per_sample0=dmod[:, 4 * D:5 * D], per_sample1=dmod[:, 3 * D:4 * D])
+            # ---- attention branch ----
+            dy1a = swo.alloc_dy(B * L, dev)
+            _, part = ops.gate_bwd(dx1, st['y_attn'], m[:, 2 * D:3 * D], B, L, dy=dy1a[:, :D])
+            ops.colreduce_finish(part, per_sample0=dmod[:, 2 * D:3 * D])
+            swo.backproject(dy1a)
+            for b in range(B):
+                rs = slice(b * L, (b + 1) * L)
+                ops.gemm(dy1a[rs], swo.w_dgrad, b_mn=True, out=d_o3[b, off:off + L])
+                swo.queue_grads(oa3[b, off:off + L], dy1a[rs])
+            dmods.append(dmod)
+            dx1s.append(dx1)
+        dq, dk, dv = ops.attn_bwd(q, k, v, oa, d_o, lse)
+        d_temb = torch.zeros_like(temb, dtype=torch.float32)
+        grads = []
+        spec = ((lo['mod'], lo['qkv'], blk.attn.norm_q, blk.attn.norm_k), (lo['mod_c'], lo['add_qkv'], blk.attn.norm_added_q, blk.attn.norm_added_k))
+        for st, dmod, dx1, (ml, sq, nq, nk) in zip(ctx.streams, dmods, dx1s, spec):
+            L, off, m = st['L'], st['off'], st['mod']
+            dqa = sq.alloc_dy(B * L, dev)
+            dbias = torch.zeros(3 * C, dtype=torch.float32, device=dev)
+            dw = torch.zeros((2, HD), dtype=torch.float32, device=dev)
+            ops.qknorm_rope_bwd(dq, dk, dv, qhat, khat, q_rstd, k_rstd, nq.weight, nk.weight, cos, sin, dqa, dbias, dw,
+                                B, H, Ltot, off, L)
+            if _needs(nq.weight):
+                _acc_vec(nq.weight, dw[0])
+                _acc_vec(nk.weight, dw[1])
+            sq.backproject(dqa)
+            xa = sq.alloc_in(B * L, dev)
+            ops.ln_modulate_fwd(st['x'], m[:, D:2 * D], m[:, 0:D], B, L, out=xa[:, :D], save_stats=False)
+            xa[:, D:].copy_(st['t_qkv'])
+            sq.queue_grads(xa, dqa)
+            dxn = ops.gemm(dqa, sq.w_dgrad, b_mn=True)
+            dx, part = ops.ln_modulate_bwd(dxn, st['x'], m[:, D:2 * D], st['mean1'], st['rstd1'], B, L, dres=dx1)
+            ops.colreduce_finish(part, per_sample0=dmod[:, D:2 * D], per_sample1=dmod[:, 0:D])
+            ml.bwd(dmod, temb, st['mod_saved'], d_temb)
+            grads.append(dx.view(B, L, D))
+        ctx.streams = None
+        ctx.attn = None
+        return None, grads[0], grads[1], d_temb.to(temb.dtype), None, None
+
+
+# =====================================================================================================================
+# single-stream block (Flux)
+# =====================================================================================================================
+class FluxSingleBlockLoraFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, blk, hidden, enc, temb, cos, sin):
+        lo = blk.lora
+        B, Li, D = hidden.shape
+        Lt = enc.shape[1]
+        L = Li + Lt
+        H = blk.heads
+        dev = hidden.device
+        bf = torch.bfloat16
+        for s in lo['sites']:
+            s.refresh()
+        s1, s2 = lo['lin1'], lo['proj_out']
+        inner = blk.mlp_dim
+        x = torch.cat([enc, hidden], dim=1).reshape(B * L, D)
+        mod, mod_saved = lo['mod'].fwd(temb)
+        xa = s1.alloc_in(B * L, dev)
+        _, mean, rstd = ops.ln_modulate_fwd(x, mod[:, D:2 * D], mod[:, 0:D], B, L, out=xa[:, :D])
+        s1.project(xa)
+        t1 = xa[:, D:].clone()
+        shp = (B, H, L, HD)
+        q, k, v, qhat, khat = (torch.empty(shp, dtype=bf, device=dev) for _ in range(5))
+        q_rstd = torch.empty((B, H, L), dtype=torch.float32, device=dev)
+        k_rstd = torch.empty((B, H, L), dtype=torch.float32, device=dev)
+        cata = s2.alloc_in(B * L, dev)              # [attn | gelu(mlp) | adapter columns]: the operand of proj_out
+        u = torch.empty((B * L, inner), dtype=bf, device=dev)
+        e = ops.make_qkv_epilogue(q, k, v, blk.attn.norm_q.weight, blk.attn.norm_k.weight, cos, sin, H, L, 0, qhat, khat,
+                                  q_rstd, k_rstd)
+        ops.gemm(xa, s1.w_fwd, bias=s1.bias, epilogue=ops.EPI_QKV_ROPE, out=cata[:, D:D + inner], out2=u, rows_per_batch=L, qkv=e)
+        _, lse = ops.attn_fwd(q, k, v, out=cata)
+        s2.project(cata)
+        y = torch.empty((B * L, D), dtype=bf, device=dev)
+        xo = ops.gemm(cata, s2.w_fwd, bias=s2.bias, epilogue=ops.EPI_GATE_RES, aux=x, gate=mod[:, 2 * D:3 * D], out2=y,
+                      rows_per_batch=L)
+        xo3 = xo.view(B, L, D)
+        ctx.blk = blk
+        ctx.saved = (x, mod, mod_saved, mean, rstd, t1, q, k, v, qhat, khat, q_rstd, k_rstd, cata, u, lse, y)
+        ctx.save_for_backward(temb, cos, sin)
+        ctx.dims = (B, Li, Lt, D, H)
+        return xo3[:, Lt:], xo3[:, :Lt]
+
+    @staticmethod
+    def backward(ctx, d_hidden, d_enc):
+        blk = ctx.blk
+        lo = blk.lora
+        temb, cos, sin = ctx.saved_tensors
+        B, Li, Lt, D, H = ctx.dims
+        L = Li + Lt
+        C = H * HD
+        dev = temb.device
+        bf = torch.bfloat16
+        x, mod, mod_saved, mean, rstd, t1, q, k, v, qhat, khat, q_rstd, k_rstd, cata, u, lse, y = ctx.saved
+        s1, s2 = lo['lin1'], lo['proj_out']
+        inner = blk.mlp_dim
+        dxo = torch.cat([d_enc, d_hidden], dim=1).reshape(B * L, D)
+        if dxo.dtype != bf:
+            dxo = dxo.to(bf)
+        dmod = torch.empty((B, 3 * D), dtype=torch.float32, device=dev)
+        dya = s2.alloc_dy(B * L, dev)
+        _, part = ops.gate_bwd(dxo, y, mod[:, 2 * D:3 * D], B, L, dy=dya[:, :D])
+        ops.colreduce_finish(part, per_sample0=dmod[:, 2 * D:3 * D])
+        s2.backproject(dya)
+        s2.queue_grads(cata, dya)
+        dl1a = s1.alloc_dy(B * L, dev)                                   # [dq | dk | dv | d mlp_pre | adapter columns]
+        d_o = torch.empty((B * L, D), dtype=bf, device=dev)
+        wd = s2.w_dgrad                                                  # [D + R, D + inner]
+        ops.gemm(dya, wd[:, :D], b_mn=True, out=d_o)
+        ops.gemm(dya, wd[:, D:], b_mn=True, epilogue=ops.EPI_MUL_GELU_GRAD, aux=u, out=dl1a[:, 3 * C:3 * C + inner])
+        dq, dk, dv = ops.attn_bwd(q, k, v, cata, d_o, lse)
+        dbias = torch.zeros(3 * C, dtype=torch.float32, device=dev)
+        dw = torch.zeros((2, HD), dtype=torch.float32, device=dev)
+        ops.qknorm_rope_bwd(dq, dk, dv, qhat, khat, q_rstd, k_rstd, blk.attn.norm_q.weight, blk.attn.norm_k.weight, cos, sin,
+                            dl1a, dbias, dw, B, H, L, 0, L)
+        if _needs(blk.attn.norm_q.weight):
+            _acc_vec(blk.attn.norm_q.weight, dw[0])
+            _acc_vec(blk.attn.norm_k.weight, dw[1])
+        s1.backproject(dl1a)
+        xa = s1.alloc_in(B * L, dev)
+        ops.ln_modulate_fwd(x, mod[:, D:2 * D], mod[:, 0:D], B, L, out=xa[:, :D], save_stats=False)
+        xa[:, D:].copy_(t1)
+        s1.queue_grads(xa, dl1a)
+        dxn = ops.gemm(dl1a, s1.w_dgrad, b_mn=True)
+        dx, part = ops.ln_modulate_bwd(dxn, x, mod[:, D:2 * D], mean, rstd, B, L, dres=dxo)
+        ops.colreduce_finish(part, per_sample0=dmod[:, D:2 * D], per_sample1=dmod[:, 0:D])
+        d_temb = torch.zeros((B, D), dtype=torch.float32, device=dev)
+        lo['mod'].bwd(dmod, temb, mod_saved, d_temb)
+        dx3 = dx.view(B, L, D)
+        ctx.saved = None
+        return None, dx3[:, Lt:], dx3[:, :Lt], d_temb.to(temb.dtype), None, None
+
+
+# =====================================================================================================================
+# attaching adapters
+# =====================================================================================================================
+def _name_factors(blk):
+    """original_name of a new factor = the block's prefix (taken from an already named parameter) + its local name"""
+    prefix = None
+    for n, p in blk.named_parameters():
+        on = getattr(p, 'original_name', None)
+        if on is not None and on.endswith(n):
+            prefix = on[:len(on) - len(n)]
+            break
+    if prefix is None:
+        return
+    for n, p in blk.named_parameters():
+        if '.lora_A.' in n or '.lora_B.' in n:
+            p.original_name = prefix + n
+
+
+def attach(module, rank, dtype=torch.bfloat16):
+    """attaches adapters to every supported block found under `module`; returns the number of blocks adapted"""
+    n = 0
+    for m in module.modules():
+        if 'lora' in m.__dict__:
+            continue
+        cls = type(m).__name__
+        if cls in ('FluxTransformerBlock', 'QwenImageTransformerBlock'):
+            attach_double_block(m, rank, dtype)
+            n += 1
+        elif cls == 'FluxSingleTransformerBlock':
+            attach_single_block(m, rank, dtype)
+            n += 1
+    return n
+
+
+def attach_double_block(blk, rank, dtype=torch.bfloat16):
+    """every nn.Linear of a FluxTransformerBlock / QwenImageTransformerBlock gets an adapter (models/base.py:263-271)"""
+    a = blk.attn
+    lo = {
+        'mod': ModLora(blk.norm1.linear, rank, dtype), 'mod_c': ModLora(blk.norm1_context.linear, rank, dtype),
+        'qkv': LoraSite([a.to_q, a.to_k, a.to_v], rank, dtype),
+        'add_qkv': LoraSite([a.add_q_proj, a.add_k_proj, a.add_v_proj], rank, dtype),
+        'to_out': LoraSite([a.to_out[0]], rank, dtype), 'to_add_out': LoraSite([a.to_add_out], rank, dtype),
+        'ff1': LoraSite([blk.ff.net[0].proj], rank, dtype), 'ff2': LoraSite([blk.ff.net[2]], rank, dtype),
+        'ffc1': LoraSite([blk.ff_context.net[0].proj], rank, dtype), 'ffc2': LoraSite([blk.ff_context.net[2]], rank, dtype),
+    }
+    lo['sites'] = [v for v in lo.values() if isinstance(v, LoraSite)]
+    for n in (a.norm_q, a.norm_k, a.norm_added_q, a.norm_added_k):
+        n.weight.requires_grad_(False)                       # bias='none', no modules_to_save: only the factors train
+    for fp, site in ((blk.qkv, lo['qkv']), (blk.add_qkv, lo['add_qkv'])):
+        fp.weight, fp.bias = site.buf[:site.N, :site.K], site.bias   # drop the old fused storage (the site buffer owns W now)
+    blk.__dict__['lora'] = lo
+    _name_factors(blk)
+    return lo
+
+
+def attach_single_block(blk, rank, dtype=torch.bfloat16):
+    a = blk.attn
+    lo = {
+        'mod': ModLora(blk.norm.linear, rank, dtype),
+        'lin1': LoraSite([a.to_q, a.to_k, a.to_v, blk.proj_mlp], rank, dtype),
+        'proj_out': LoraSite([blk.proj_out], rank, dtype),
+    }
+    lo['sites'] = [v for v in lo.values() if isinstance(v, LoraSite)]
+    for n in (a.norm_q, a.norm_k):
+        n.weight.requires_grad_(False)
+    blk.lin1.weight, blk.lin1.bias = lo['lin1'].buf[:lo['lin1'].N, :lo['lin1'].K], lo['lin1'].bias
+    blk.__dict__['lora'] = lo
+    _name_factors(blk)
+    return lo
+
+
+def lora_state_dict(module):
+    """{original_name: tensor} of the adapter factors only (what the reference's save_adapter receives)"""
+    return {n: p.detach() for n, p in module.named_parameters() if '.lora_A.' in n or '.lora_B.' in n}

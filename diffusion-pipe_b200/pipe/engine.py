@@ -502,7 +502,8 @@ class PipelineEngine:
         missing = []
         for k, p in by_name.items():
             if k in state['module']:
-                p.data.copy_(state['module'][k])
+                with torch.no_grad():
+                    p.copy_(state['module'][k])      # in place on the parameter itself: bumps its version counter (lora.py watches it)
             elif p.requires_grad:
                 missing.append(k)
         if load_module_strict and missing:

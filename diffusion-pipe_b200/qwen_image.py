@@ -75,6 +75,10 @@ class QwenImageTransformerBlock(nn.Module):
     def forward(self, hidden_states, encoder_hidden_states, temb, image_rotary_emb, encoder_hidden_states_mask=None,
                 joint_attention_kwargs=None):
         cos, sin = image_rotary_emb            # joint [text; image] tables, fp32 [L, 128]
+        if 'lora' in self.__dict__:
+            from .lora import FluxDoubleBlockLoraFn
+            h, e = FluxDoubleBlockLoraFn.apply(self, hidden_states, encoder_hidden_states, temb, cos, sin)
+            return e, h
         h, e = FluxDoubleBlockFn.apply(self, hidden_states, encoder_hidden_states, temb, cos, sin)
         return e, h
 
@@ -256,6 +260,7 @@ class QwenImagePipeline:
         self.dtype, self.device = dtype, device
         self.pipeline_model = None
         self.model_engine = None
+        self.adapter_config = None
         self.transformer = None
         if not self.model_config.get('lazy_layers', False):
             self.transformer = QwenImageTransformer2DModel(tcfg, dtype=dtype, device=device)
@@ -269,6 +274,19 @@ class QwenImagePipeline:
 
     def load_diffusion_model(self):
         pass
+
+    def configure_adapter(self, adapter_config):
+        from .flux import FluxPipeline
+        FluxPipeline.configure_adapter(self, adapter_config)
+
+    def _adapt(self, module, dev):
+        from .flux import FluxPipeline
+        return FluxPipeline._adapt(self, module, dev)
+
+    def save_adapter(self, save_dir, peft_state_dict):
+        """models/qwen_image.py:290-294 (ComfyUI format: keys prefixed with diffusion_model.)"""
+        from .flux import FluxPipeline
+        FluxPipeline.save_adapter(self, save_dir, {'diffusion_model.' + k: v for k, v in peft_state_dict.items()})
 
     def get_param_groups(self, parameters):
         return [{'params': parameters}]
@@ -362,16 +380,16 @@ class QwenImagePipeline:
             w = InitialLayer(_plain(dim, cfg['in_channels'], dtype, d), _RMSNormW(cfg['joint_attention_dim'], dtype, d),
                              _plain(dim, cfg['joint_attention_dim'], dtype, d), QwenTimestepProjEmbeddings(dim, dtype, d),
                              tuple(cfg['axes_dims_rope']))
-            return name_params(w, {'': ''})
+            return self._adapt(name_params(w, {'': ''}), dev)
 
         def build_block(i, dev=None):
             w = TransformerLayer(QwenImageTransformerBlock(dim, heads, 4, dtype, dev or device), i)
-            return name_params(w, {'block.': f'transformer_blocks.{i}.'})
+            return self._adapt(name_params(w, {'block.': f'transformer_blocks.{i}.'}), dev)
 
         def build_last(dev=None):
             d = dev or device
             w = FinalLayer(_AdaNorm(dim, 2, dtype, d), _plain(cfg['patch_size'] ** 2 * cfg['out_channels'], dim, dtype, d))
-            return name_params(w, {'': ''})
+            return self._adapt(name_params(w, {'': ''}), dev)
 
         def count(fn, *a):
             return sum(p.numel() for p in fn(*a, dev='meta').parameters())
