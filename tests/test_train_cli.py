@@ -32,8 +32,12 @@ def test_config_defaults_and_batch_tables():
     assert T.batch_size_table(None, {None: 3}) == {None: 3}
     with pytest.raises(AssertionError):
         T.set_config_defaults({'model': {'dtype': 'bfloat16'}})          # save_every_n_* is mandatory (train.py:95)
+    c = T.set_config_defaults({'save_every_n_epochs': 1, 'model': {'dtype': 'bfloat16'}, 'adapter': {'type': 'lora', 'rank': 16}})
+    assert c['adapter'] == {'type': 'lora', 'rank': 16, 'alpha': 16, 'dtype': torch.bfloat16, 'dropout': 0.0}   # train.py:115-133
+    with pytest.raises(NotImplementedError):      # alpha is forced to rank
+        T.set_config_defaults({'save_every_n_epochs': 1, 'model': {'dtype': 'bfloat16'}, 'adapter': {'type': 'lora', 'rank': 8, 'alpha': 4}})
     with pytest.raises(NotImplementedError):
-        T.set_config_defaults({'save_every_n_epochs': 1, 'model': {'dtype': 'bfloat16'}, 'adapter': {'type': 'lora', 'rank': 8}})
+        T.set_config_defaults({'save_every_n_epochs': 1, 'model': {'dtype': 'bfloat16'}, 'adapter': {'type': 'lokr', 'rank': 8}})
 
 
 @pytest.mark.gpu

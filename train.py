@@ -84,9 +84,15 @@ def set_config_defaults(config):
         if v := mc.get(k, None):
             mc[k] = DTYPE_MAP[v]
     mc.setdefault('guidance', 1.0)
-    if 'adapter' in config:
-        raise NotImplementedError('LoRA / LoKr adapters are not built for the sm_100a path yet (SURVEY.md 8f item 3): '
-                                  'remove the [adapter] table for full fine-tuning')
+    if 'adapter' in config:                     # train.py:115-133
+        ac = config['adapter']
+        if 'alpha' in ac:
+            raise NotImplementedError('alpha is forced to rank (as in the reference): remove alpha from the [adapter] table')
+        if ac['type'] != 'lora':
+            raise NotImplementedError(f"adapter type '{ac['type']}': only 'lora' is built for the sm_100a path")
+        ac['alpha'] = ac['rank']
+        ac['dtype'] = DTYPE_MAP[ac['dtype']] if 'dtype' in ac else mc['dtype']
+        ac.setdefault('dropout', 0.0)
     config.setdefault('logging_steps', 1)
     config.setdefault('eval_datasets', [])
     config.setdefault('eval_gradient_accumulation_steps', 1)
@@ -282,6 +288,12 @@ def main(argv=None):
     is_main = dist.get_rank() == 0
 
     model = make_model(config)
+    is_adapter = False
+    if adapter_config := config.get('adapter', None):          # train.py:531-535 (before the layers are built)
+        if not hasattr(model, 'configure_adapter'):
+            raise NotImplementedError(f"[adapter] is not available for model type '{config['model']['type']}' yet")
+        model.configure_adapter(adapter_config)
+        is_adapter = True
 
     dataset_config = load_toml(config['dataset'])
     ds_config, micro_batch_size_per_gpu = make_ds_config(config)
