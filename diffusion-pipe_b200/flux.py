@@ -316,6 +316,7 @@ class FluxPipeline:
             with open(tcfg) as f:
                 tcfg = json.load(f)
         self.tcfg = dict(FLUX_DEV_CONFIG, **(tcfg or {}))
+        device = self.model_config.get("device", device)      # (tests: "cpu" with the kernel test doubles)
         self.dtype, self.device = dtype, device
         self.pipeline_model = None
         self.model_engine = None
@@ -429,8 +430,16 @@ class FluxPipeline:
         lora.attach(module, int(self.adapter_config['rank']), dtype)
         return module
 
+    def save_model(self, save_dir, state_dict):
+        """full-model export in the diffusers layout this engine trains in (the reference re-lays Flux out to BFL names
+        on top of this, models/flux.py:257-288 — outside the hot path)"""
+        from safetensors.torch import save_file
+        os.makedirs(save_dir, exist_ok=True)
+        save_file({k: v.contiguous() for k, v in state_dict.items()}, os.path.join(save_dir, 'model.safetensors'),
+                  metadata={'format': 'pt'})
+
     def save_adapter(self, save_dir, peft_state_dict):
-        """models/flux.py:290-296: ComfyUI-style keys are produced by the caller; this writes them as safetensors"""
+        """models/flux.py:231-236: the adapter factors as safetensors (PEFT state-dict names)"""
         from safetensors.torch import save_file
         os.makedirs(save_dir, exist_ok=True)
         save_file({k: v.contiguous() for k, v in peft_state_dict.items()}, os.path.join(save_dir, 'adapter_model.safetensors'),

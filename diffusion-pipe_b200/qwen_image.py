@@ -257,6 +257,7 @@ class QwenImagePipeline:
             with open(tcfg) as f:
                 tcfg = json.load(f)
         self.tcfg = dict(QWEN_IMAGE_CONFIG, **(tcfg or {}))
+        device = self.model_config.get("device", device)      # (tests: "cpu" with the kernel test doubles)
         self.dtype, self.device = dtype, device
         self.pipeline_model = None
         self.model_engine = None
@@ -274,6 +275,11 @@ class QwenImagePipeline:
 
     def load_diffusion_model(self):
         pass
+
+    def save_model(self, save_dir, state_dict):
+        """models/qwen_image.py:296-297"""
+        from .flux import FluxPipeline
+        FluxPipeline.save_model(self, save_dir, state_dict)
 
     def configure_adapter(self, adapter_config):
         from .flux import FluxPipeline

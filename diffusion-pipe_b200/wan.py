@@ -588,6 +588,7 @@ class WanPipeline:
                 tcfg = json.load(f)
         self.tcfg = dict(WAN_T2V_14B_CONFIG, **(tcfg or {}))
         self.model_type = self.tcfg['model_type']
+        device = self.model_config.get("device", device)      # (tests: "cpu" with the kernel test doubles)
         self.dtype, self.device = dtype, device
         self.t_dist = get_t_distribution(self.model_config)
         self.pipeline_model = None
@@ -605,6 +606,11 @@ class WanPipeline:
 
     def load_diffusion_model(self):
         pass
+
+    def save_model(self, save_dir, state_dict):
+        """models/wan/wan.py:264-265"""
+        from .flux import FluxPipeline
+        FluxPipeline.save_model(self, save_dir, state_dict)
 
     def get_param_groups(self, parameters):
         return [{'params': parameters}]

@@ -409,58 +409,51 @@ def main(argv=None):
             with open(os.path.join(run_dir, 'metrics.jsonl'), 'a') as f:
                 f.write(json.dumps(metrics[-1]) + '\n')
 
-    def save_checkpoint(step, examples):
-        model_engine.save_checkpoint(run_dir, client_state={'step': step, 'examples': examples,
-                                                            'custom_loader': train_dataloader.state_dict()},
-                                     save_latest=True, exclude_frozen_parameters=True)
+    from diffusion_pipe_b200.saver import Saver
+    saver = Saver(args, config, is_adapter, run_dir, model, train_dataloader, model_engine, pipeline_model)
 
     if config['eval_before_first_step'] and not resume:
         evaluate(model_engine, eval_dataloaders, 0, config['eval_gradient_accumulation_steps'], log)
 
     epoch = train_dataloader.epoch
     epoch_loss, num_steps = 0.0, 0
-    last_checkpoint_time = time.time()
-    while True:
+    checkpointed = saved = False
+    final_model_name = None
+    while True:                                                          # train.py:915-965
         model_engine.reset_activation_shape()
         iterator = data_feed.get_data_iterator_for_step(train_dataloader, model_engine)
         loss = model_engine.train_batch(iterator).item()
         epoch_loss += loss
         num_steps += 1
         train_dataloader.sync_epoch()
-        new_epoch = train_dataloader.epoch
+        new_epoch, checkpointed, saved = saver.process_epoch(epoch, step, examples)
         finished_epoch = new_epoch != epoch
         x_axis = examples if config['x_axis_examples'] else step
         if step % config['logging_steps'] == 0:
             log('train/loss', loss, x_axis)
             if model_engine._grad_norm is not None:
                 log('train/grad_norm', float(model_engine._grad_norm), x_axis)
-        checkpointed = False
         if (config['eval_every_n_steps'] and step % config['eval_every_n_steps'] == 0) or \
                 (finished_epoch and config['eval_every_n_epochs'] and epoch % config['eval_every_n_epochs'] == 0):
             evaluate(model_engine, eval_dataloaders, x_axis, config['eval_gradient_accumulation_steps'], log)
         if finished_epoch:
             log('train/epoch_loss', epoch_loss / num_steps, epoch)
             epoch_loss, num_steps = 0.0, 0
-            if ce := config.get('checkpoint_every_n_epochs', None):
-                if epoch % ce == 0:
-                    save_checkpoint(step, examples)
-                    checkpointed = True
-            if new_epoch > config.get('epochs', 1 << 30):
+            if new_epoch is None:
+                final_model_name = f'epoch{epoch}'
                 break
             epoch = new_epoch
-        if (n := config.get('save_every_n_steps', None)) and step % n == 0:
-            save_checkpoint(step, examples)
-            checkpointed = True
-        if (m := config.get('checkpoint_every_n_minutes', None)) and time.time() - last_checkpoint_time > m * 60:
-            save_checkpoint(step, examples)
-            checkpointed = True
-            last_checkpoint_time = time.time()
+        checkpointed, saved = saver.process_step(step, examples)
         if 'max_steps' in config and step >= config['max_steps']:
+            final_model_name = f'step{step}'
             break
         step += 1
         examples += global_batch_size
+    # final training state and model, unless they were just written
     if not checkpointed:
-        save_checkpoint(step, examples)
+        saver.save_checkpoint(step, examples)
+    if not saved:
+        saver.save_model(final_model_name)
     if is_main:
         print('TRAINING COMPLETE!')
     return run_dir
