@@ -458,6 +458,9 @@ def attach(module, rank, dtype=torch.bfloat16):
         elif cls == 'FluxSingleTransformerBlock':
             attach_single_block(m, rank, dtype)
             n += 1
+        elif cls == 'WanAttentionBlock':
+            attach_wan_block(m, rank, dtype)
+            n += 1
     return n
 
 
@@ -501,3 +504,186 @@ def attach_single_block(blk, rank, dtype=torch.bfloat16):
 def lora_state_dict(module):
     """{original_name: tensor} of the adapter factors only (what the reference's save_adapter receives)"""
     return {n: p.detach() for n, p in module.named_parameters() if '.lora_A.' in n or '.lora_B.' in n}
+
+
+# =====================================================================================================================
+# Wan attention block (adapter_target_modules = ['WanAttentionBlock'], models/wan/wan.py:71: its ten nn.Linear)
+# =====================================================================================================================
+class WanBlockLoraFn(torch.autograd.Function):
+    """WanBlockFn (wan.py) with adapters on q/k/v/o of both attentions and on the two FFN linears; base, norms and the
+    modulation table frozen."""
+
+    @staticmethod
+    def forward(ctx, blk, x, e0, context, cos, sin):
+        lo = blk.lora
+        B, L, D = x.shape
+        Lc = context.shape[1]
+        H = blk.num_heads
+        dev = x.device
+        bf = torch.bfloat16
+        for s in lo['sites']:
+            s.refresh()
+        LN_STEPS, LN_MULT = ops.LN_ROUND_STEPS, ops.LN_MULT_DIRECT
+        x2 = x.reshape(B * L, D)
+        mod = (blk.modulation.unsqueeze(0) + e0).reshape(B, 6, D)
+        sa, ca = blk.self_attn, blk.cross_attn
+        s_qkv, s_o, s_cq, s_ckv, s_co, s_f1, s_f2 = (lo[k] for k in ('sa_qkv', 'sa_o', 'ca_q', 'ca_kv', 'ca_o', 'ffn1', 'ffn2'))
+        # ---- self-attention ----
+        xa = s_qkv.alloc_in(B * L, dev)
+        _, mean1, rstd1 = ops.ln_modulate_fwd(x2, mod[:, 1], mod[:, 0], B, L, eps=blk.eps, out=xa[:, :D], flags=LN_STEPS)
+        s_qkv.project(xa)
+        t_qkv = xa[:, D:].clone()
+        qkv = ops.gemm(xa, s_qkv.w_fwd, bias=s_qkv.bias)
+        (q, xhq, rq), (k, xhk, rk), (v, _, _) = ops.wan_norm_rope_fwd(
+            [{'src': qkv[:, 0:D], 'weight': sa.norm_q.weight, 'rope': True},
+             {'src': qkv[:, D:2 * D], 'weight': sa.norm_k.weight, 'rope': True},
+             {'src': qkv[:, 2 * D:3 * D]}], B, L, H, cos, sin, eps=blk.eps)
+        del qkv, xa
+        oa = s_o.alloc_in(B * L, dev)
+        _, lse = ops.attn_fwd(q, k, v, out=oa)
+        s_o.project(oa)
+        y_attn = torch.empty((B * L, D), dtype=bf, device=dev)
+        x1 = ops.gemm(oa, s_o.w_fwd, bias=s_o.bias, epilogue=ops.EPI_GATE_RES, aux=x2, gate=mod[:, 2], out2=y_attn, rows_per_batch=L)
+        # ---- cross-attention ----
+        n3w = blk.norm3.weight.view(1, D).expand(B, D)
+        n3b = blk.norm3.bias.view(1, D).expand(B, D)
+        x3a = s_cq.alloc_in(B * L, dev)
+        _, mean3, rstd3 = ops.ln_modulate_fwd(x1, n3w, n3b, B, L, eps=blk.eps, out=x3a[:, :D], flags=LN_MULT)
+        s_cq.project(x3a)
+        t_cq = x3a[:, D:].clone()
+        qc_lin = ops.gemm(x3a, s_cq.w_fwd, bias=s_cq.bias)
+        ((qc, xhqc, rqc),) = ops.wan_norm_rope_fwd([{'src': qc_lin, 'weight': ca.norm_q.weight}], B, L, H, eps=blk.eps)
+        del qc_lin, x3a
+        ca_in = s_ckv.alloc_in(B * Lc, dev)
+        ca_in[:, :D].copy_(context.reshape(B * Lc, D))
+        s_ckv.project(ca_in)
+        kv_lin = ops.gemm(ca_in, s_ckv.w_fwd, bias=s_ckv.bias)
+        (kc, xhkc, rkc), (vc, _, _) = ops.wan_norm_rope_fwd(
+            [{'src': kv_lin[:, 0:D], 'weight': ca.norm_k.weight}, {'src': kv_lin[:, D:2 * D]}], B, Lc, H, eps=blk.eps)
+        del kv_lin
+        oca = s_co.alloc_in(B * L, dev)
+        _, lse_c = ops.attn_fwd(qc, kc, vc, out=oca)
+        s_co.project(oca)
+        x2_ = ops.gemm(oca, s_co.w_fwd, bias=s_co.bias, epilogue=ops.EPI_GATE_RES, aux=x1, gate=blk._ones(B, D, dev), rows_per_batch=L)
+        # ---- feed-forward ----
+        x2a = s_f1.alloc_in(B * L, dev)
+        _, mean2, rstd2 = ops.ln_modulate_fwd(x2_, mod[:, 4], mod[:, 3], B, L, eps=blk.eps, out=x2a[:, :D], flags=LN_STEPS)
+        s_f1.project(x2a)
+        t_f1 = x2a[:, D:].clone()
+        F = s_f1.N
+        u = torch.empty((B * L, F), dtype=bf, device=dev)
+        ha = s_f2.alloc_in(B * L, dev)
+        ops.gemm(x2a, s_f1.w_fwd, bias=s_f1.bias, epilogue=ops.EPI_BIAS_GELU, out=ha[:, :F], out2=u)
+        del x2a
+        s_f2.project(ha)
+        y_mlp = torch.empty((B * L, D), dtype=bf, device=dev)
+        x3 = ops.gemm(ha, s_f2.w_fwd, bias=s_f2.bias, epilogue=ops.EPI_GATE_RES, aux=x2_, gate=mod[:, 5], out2=y_mlp, rows_per_batch=L)
+        ctx.blk = blk
+        ctx.saved = (x2, mod, mean1, rstd1, t_qkv, q, k, v, xhq, rq, xhk, rk, oa, lse, y_attn, x1, mean3, rstd3, t_cq, qc, xhqc,
+                     rqc, ca_in, kc, xhkc, rkc, vc, oca, lse_c, x2_, mean2, rstd2, t_f1, u, ha, y_mlp)
+        ctx.save_for_backward(cos, sin)
+        ctx.dims = (B, L, Lc, D, H)
+        ctx.in_dtypes = (x.dtype, e0.dtype, context.dtype)
+        return x3.view(B, L, D)
+
+    @staticmethod
+    def backward(ctx, dx3):
+        blk = ctx.blk
+        lo = blk.lora
+        cos, sin = ctx.saved_tensors
+        B, L, Lc, D, H = ctx.dims
+        (x2, mod, mean1, rstd1, t_qkv, q, k, v, xhq, rq, xhk, rk, oa, lse, y_attn, x1, mean3, rstd3, t_cq, qc, xhqc,
+         rqc, ca_in, kc, xhkc, rkc, vc, oca, lse_c, x2_, mean2, rstd2, t_f1, u, ha, y_mlp) = ctx.saved
+        ctx.saved = None
+        dev = x2.device
+        bf = torch.bfloat16
+        LN_STEPS, LN_MULT = ops.LN_ROUND_STEPS, ops.LN_MULT_DIRECT
+        sa, ca = blk.self_attn, blk.cross_attn
+        s_qkv, s_o, s_cq, s_ckv, s_co, s_f1, s_f2 = (lo[k] for k in ('sa_qkv', 'sa_o', 'ca_q', 'ca_kv', 'ca_o', 'ffn1', 'ffn2'))
+        F = s_f1.N
+        dmod = torch.zeros((B, 6, D), dtype=torch.float32, device=dev)
+        d3 = dx3.reshape(B * L, D)
+        if d3.dtype != bf:
+            d3 = d3.to(bf)
+        d3 = d3.contiguous()
+        # ---- feed-forward ----
+        dy2a = s_f2.alloc_dy(B * L, dev)
+        _, part = ops.gate_bwd(d3, y_mlp, mod[:, 5], B, L, dy=dy2a[:, :D])
+        ops.colreduce_finish(part, per_sample0=dmod[:, 5])
+        s_f2.backproject(dy2a)
+        s_f2.queue_grads(ha, dy2a)
+        dua = s_f1.alloc_dy(B * L, dev)
+        ops.gemm(dy2a, s_f2.w_dgrad, b_mn=True, epilogue=ops.EPI_MUL_GELU_GRAD, aux=u, out=dua[:, :F])
+        s_f1.backproject(dua)
+        x2a = s_f1.alloc_in(B * L, dev)
+        ops.ln_modulate_fwd(x2_, mod[:, 4], mod[:, 3], B, L, eps=blk.eps, out=x2a[:, :D], save_stats=False, flags=LN_STEPS)
+        x2a[:, D:].copy_(t_f1)
+        s_f1.queue_grads(x2a, dua)
+        dxn2 = ops.gemm(dua, s_f1.w_dgrad, b_mn=True)
+        # d x2 lands directly in the dy operand of the cross-attention output projection (x2 = x1 + o_c W^T: no gate)
+        dca = s_co.alloc_dy(B * L, dev)
+        _, part = ops.ln_modulate_bwd(dxn2, x2_, mod[:, 4], mean2, rstd2, B, L, dres=d3, dx=dca[:, :D], flags=LN_STEPS)
+        ops.colreduce_finish(part, per_sample0=dmod[:, 4], per_sample1=dmod[:, 3])
+        dx2 = dca[:, :D]
+        # ---- cross-attention ----
+        s_co.backproject(dca)
+        s_co.queue_grads(oca, dca)
+        d_oc = ops.gemm(dca, s_co.w_dgrad, b_mn=True)
+        dqc, dkc, dvc = ops.attn_bwd(qc, kc, vc, oca, d_oc, lse_c)
+        dqca = s_cq.alloc_dy(B * L, dev)
+        ops.wan_norm_rope_bwd([{'dy': dqc, 'dx': dqca[:, :D], 'weight': ca.norm_q.weight, 'xhat': xhqc, 'rstd': rqc}], B, L, H)
+        s_cq.backproject(dqca)
+        dkva = s_ckv.alloc_dy(B * Lc, dev)
+        ops.wan_norm_rope_bwd([{'dy': dkc, 'dx': dkva[:, 0:D], 'weight': ca.norm_k.weight, 'xhat': xhkc, 'rstd': rkc},
+                               {'dy': dvc, 'dx': dkva[:, D:2 * D]}], B, Lc, H)
+        s_ckv.backproject(dkva)
+        s_ckv.queue_grads(ca_in, dkva)
+        n3w = blk.norm3.weight.view(1, D).expand(B, D)
+        n3b = blk.norm3.bias.view(1, D).expand(B, D)
+        x3a = s_cq.alloc_in(B * L, dev)
+        ops.ln_modulate_fwd(x1, n3w, n3b, B, L, eps=blk.eps, out=x3a[:, :D], save_stats=False, flags=LN_MULT)
+        x3a[:, D:].copy_(t_cq)
+        s_cq.queue_grads(x3a, dqca)
+        d_ctx = ops.gemm(dkva, s_ckv.w_dgrad, b_mn=True)
+        dxn3 = ops.gemm(dqca, s_cq.w_dgrad, b_mn=True)
+        dx1, _ = ops.ln_modulate_bwd(dxn3, x1, n3w, mean3, rstd3, B, L, dres=dx2, flags=LN_MULT)      # norm3 is frozen
+        # ---- self-attention ----
+        dy1a = s_o.alloc_dy(B * L, dev)
+        _, part = ops.gate_bwd(dx1, y_attn, mod[:, 2], B, L, dy=dy1a[:, :D])
+        ops.colreduce_finish(part, per_sample0=dmod[:, 2])
+        s_o.backproject(dy1a)
+        s_o.queue_grads(oa, dy1a)
+        d_o = ops.gemm(dy1a, s_o.w_dgrad, b_mn=True)
+        dq, dk, dv = ops.attn_bwd(q, k, v, oa, d_o, lse)
+        dqkva = s_qkv.alloc_dy(B * L, dev)
+        ops.wan_norm_rope_bwd(
+            [{'dy': dq, 'dx': dqkva[:, 0:D], 'weight': sa.norm_q.weight, 'xhat': xhq, 'rstd': rq, 'rope': True},
+             {'dy': dk, 'dx': dqkva[:, D:2 * D], 'weight': sa.norm_k.weight, 'xhat': xhk, 'rstd': rk, 'rope': True},
+             {'dy': dv, 'dx': dqkva[:, 2 * D:3 * D]}], B, L, H, cos, sin)
+        s_qkv.backproject(dqkva)
+        xa = s_qkv.alloc_in(B * L, dev)
+        ops.ln_modulate_fwd(x2, mod[:, 1], mod[:, 0], B, L, eps=blk.eps, out=xa[:, :D], save_stats=False, flags=LN_STEPS)
+        xa[:, D:].copy_(t_qkv)
+        s_qkv.queue_grads(xa, dqkva)
+        dxn1 = ops.gemm(dqkva, s_qkv.w_dgrad, b_mn=True)
+        dx, part = ops.ln_modulate_bwd(dxn1, x2, mod[:, 1], mean1, rstd1, B, L, dres=dx1, flags=LN_STEPS)
+        ops.colreduce_finish(part, per_sample0=dmod[:, 1], per_sample1=dmod[:, 0])
+        xdt, edt, cdt = ctx.in_dtypes
+        return (None, dx.view(B, L, D).to(xdt), dmod.view(B, 1, 6, D).to(edt), d_ctx.view(B, Lc, D).to(cdt), None, None)
+
+
+def attach_wan_block(blk, rank, dtype=torch.bfloat16):
+    sa, ca = blk.self_attn, blk.cross_attn
+    lo = {
+        'sa_qkv': LoraSite([sa.q, sa.k, sa.v], rank, dtype), 'sa_o': LoraSite([sa.o], rank, dtype),
+        'ca_q': LoraSite([ca.q], rank, dtype), 'ca_kv': LoraSite([ca.k, ca.v], rank, dtype), 'ca_o': LoraSite([ca.o], rank, dtype),
+        'ffn1': LoraSite([blk.ffn[0]], rank, dtype), 'ffn2': LoraSite([blk.ffn[2]], rank, dtype),
+    }
+    lo['sites'] = [v for v in lo.values() if isinstance(v, LoraSite)]
+    for p in (sa.norm_q.weight, sa.norm_k.weight, ca.norm_q.weight, ca.norm_k.weight, blk.norm3.weight, blk.norm3.bias, blk.modulation):
+        p.requires_grad_(False)
+    sa.qkv.weight, sa.qkv.bias = lo['sa_qkv'].buf[:lo['sa_qkv'].N, :lo['sa_qkv'].K], lo['sa_qkv'].bias
+    ca.kv.weight, ca.kv.bias = lo['ca_kv'].buf[:lo['ca_kv'].N, :lo['ca_kv'].K], lo['ca_kv'].bias
+    blk.__dict__['lora'] = lo
+    _name_factors(blk)
+    return lo

@@ -364,6 +364,9 @@ class WanAttentionBlock(nn.Module):
 
     def forward(self, x, e, seq_lens, grid_sizes, freqs, context, context_lens=None):
         assert context_lens is None, 'the reference passes context_lens=None (models/wan/wan.py:526)'
+        if 'lora' in self.__dict__:          # adapters attached (lora.py): frozen base, K-extended GEMMs
+            from .lora import WanBlockLoraFn
+            return WanBlockLoraFn.apply(self, x, e, context, freqs[0], freqs[1])
         return WanBlockFn.apply(self, x, e, context, freqs[0], freqs[1])
 
 
@@ -593,6 +596,7 @@ class WanPipeline:
         self.t_dist = get_t_distribution(self.model_config)
         self.pipeline_model = None
         self.model_engine = None
+        self.adapter_config = None
         self.transformer = None
         if not self.model_config.get('lazy_layers', False):
             self.transformer = WanModel(self.tcfg, dtype=dtype, device=device)
@@ -611,6 +615,19 @@ class WanPipeline:
         """models/wan/wan.py:264-265"""
         from .flux import FluxPipeline
         FluxPipeline.save_model(self, save_dir, state_dict)
+
+    def configure_adapter(self, adapter_config):
+        from .flux import FluxPipeline
+        FluxPipeline.configure_adapter(self, adapter_config)
+
+    def _adapt(self, module, dev):
+        from .flux import FluxPipeline
+        return FluxPipeline._adapt(self, module, dev)
+
+    def save_adapter(self, save_dir, peft_state_dict):
+        """models/wan/wan.py:258-262 (ComfyUI format: keys prefixed with diffusion_model.)"""
+        from .flux import FluxPipeline
+        FluxPipeline.save_adapter(self, save_dir, {'diffusion_model.' + k: v for k, v in peft_state_dict.items()})
 
     def get_param_groups(self, parameters):
         return [{'params': parameters}]
@@ -676,15 +693,15 @@ class WanPipeline:
             w = InitialLayer(pe, _Seq([_plain(dim, cfg['freq_dim'], dtype, d), nn.Identity(), _plain(dim, dim, dtype, d)]),
                              _Seq([_plain(dim, cfg['text_dim'], dtype, d), nn.Identity(), _plain(dim, dim, dtype, d)]),
                              _Seq([nn.Identity(), _plain(dim * 6, dim, dtype, d)]), cfg)
-            return name_params(w, {'': ''})
+            return self._adapt(name_params(w, {'': ''}), dev)
 
         def build_block(i, dev=None):
             w = TransformerLayer(WanAttentionBlock(dim, cfg['ffn_dim'], cfg['num_heads'], cfg['eps'], dtype, dev or device), i)
-            return name_params(w, {'block.': f'blocks.{i}.'})
+            return self._adapt(name_params(w, {'block.': f'blocks.{i}.'}), dev)
 
         def build_last(dev=None):
             w = FinalLayer(WanHead(dim, cfg['out_dim'], cfg['patch_size'], cfg['eps'], dtype, dev or device), cfg['patch_size'], cfg['out_dim'])
-            return name_params(w, {'': ''})
+            return self._adapt(name_params(w, {'': ''}), dev)
 
         def count(fn, *a):
             return sum(p.numel() for p in fn(*a, dev='meta').parameters())

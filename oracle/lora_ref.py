@@ -1,4 +1,4 @@
-"""ORACLE — test infrastructure only.  LoRA adapters on the restated Flux / Qwen-Image blocks, as the reference
+"""ORACLE — test infrastructure only.  LoRA adapters on the restated Flux / Qwen-Image / Wan blocks, as the reference
 configures them through PEFT (models/base.py:263-303):
 
     peft.LoraConfig(r=rank, lora_alpha=rank, lora_dropout=0, bias='none',
@@ -20,7 +20,8 @@ from torch import nn
 
 from .flux_ref import RefLinear, _r
 
-TARGET_BLOCKS = ('RefFluxTransformerBlock', 'RefFluxSingleTransformerBlock', 'RefQwenImageTransformerBlock')
+TARGET_BLOCKS = ('RefFluxTransformerBlock', 'RefFluxSingleTransformerBlock', 'RefQwenImageTransformerBlock',
+                 'RefWanAttentionBlock')
 
 
 class RefLoraLinear(nn.Module):

@@ -126,3 +126,13 @@ def test_forward_matches_the_references_own_model(golden_dir):
             out = layer(out)
     err = (out.float().cpu() - g['out']).norm() / g['out'].norm()
     assert err <= 2e-2, err.item()
+
+
+def test_wan_lora_matches_oracle():
+    """LoRA on the ten Linear layers of every Wan block (K-extended GEMM operands) with the real kernels vs the oracle
+    with PEFT-style adapters; host logic of the same function is covered on CPU by tests/test_lora_wan_host_logic.py"""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import test_lora_wan_host_logic as H
+    model, ref = H.make_pair(device='cuda')
+    loss, rloss = H.run_both(model, ref, *H.make_batch(), dev='cuda')
+    H.check(model, ref, loss, rloss)
