@@ -296,8 +296,9 @@ class PipelineEngine:
         self._wgrad_queues[cmd.micro_batch_id] = q
 
     def _exec_backward_weight(self, cmd, train):
-        for fn in self._wgrad_queues.pop(cmd.micro_batch_id, ()):
-            fn()
+        with torch.no_grad():          # the queued closures are the tail of a backward pass: never recorded by autograd
+            for fn in self._wgrad_queues.pop(cmd.micro_batch_id, ()):
+                fn()
 
     def _exec_backward_pass(self, cmd, train):
         b = cmd.buffer_id

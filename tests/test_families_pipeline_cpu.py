@@ -1,0 +1,122 @@
+"""CPU / gloo: the Qwen-Image and Wan layer tuple protocols (bool key mask, int32 shape tensors, fp32 rope tables, empty
+`None` placeholders, text context) through the pipeline engine — 2 stages x {1F1B, zero-bubble} against 1 stage — with
+the kernel wrappers replaced by the PyTorch test doubles (the arithmetic is identical in both runs, so losses agree to
+rounding of the boundary dtype)."""
+import os
+import socket
+import sys
+import tempfile
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE, os.path.join(HERE, 'golden')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GAS = 4
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+class _Patch:
+    def setattr(self, obj, name, value):
+        setattr(obj, name, value)
+
+
+def _make(kind):
+    from synth import fill_parameters
+    if kind == 'qwen_image':
+        from diffusion_pipe_b200.qwen_image import QwenImagePipeline
+        from oracle import qwen_ref as Q
+        model = QwenImagePipeline({'model': {'dtype': 'bfloat16', 'device': 'cpu',
+                                             'transformer_config': {'num_attention_heads': 2, 'num_layers': 2, 'joint_attention_dim': 64}}})
+        ref = fill_parameters(Q.RefQwenImageTransformer(dim=256, heads=2, num_layers=2, joint_dim=64))
+    else:
+        from diffusion_pipe_b200.wan import WanPipeline
+        from oracle import wan_ref as W
+        cfg = {'dim': 256, 'ffn_dim': 512, 'num_heads': 2, 'num_layers': 2, 'text_dim': 64, 'text_len': 16}
+        model = WanPipeline({'model': {'dtype': 'bfloat16', 'device': 'cpu', 'transformer_config': cfg}})
+        ref = fill_parameters(W.RefWanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, text_len=16))
+    sd = ref.state_dict()
+    with torch.no_grad():
+        for n, p in model.transformer.named_parameters():
+            p.copy_(sd[n].to(p.dtype))
+    return model
+
+
+def _micro_batches(kind, model, n, seed):
+    from diffusion_pipe_b200 import data_feed
+    g = torch.Generator().manual_seed(seed)
+    if kind == 'qwen_image':
+        batch = {'latents': torch.randn(n, 16, 1, 8, 8, generator=g), 'prompt_embeds': [torch.randn(7, 64, generator=g).bfloat16() for _ in range(n)],
+                 'mask': None}
+    else:
+        batch = {'latents': torch.randn(n, 16, 2, 8, 8, generator=g), 'text_embeddings': torch.randn(n, 16, 64, generator=g).bfloat16(),
+                 'seq_lens': torch.full((n,), 12), 'mask': None}
+    torch.manual_seed(seed)
+    feats, label = model.prepare_inputs(batch)
+    return data_feed.split_batch((feats, label), n)
+
+
+def _worker(rank, world, port, kind, stages, schedule, outdir):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    import kernel_doubles
+    from diffusion_pipe_b200 import ops
+    from diffusion_pipe_b200.pipe import ManualPipelineModule, dist, initialize
+    kernel_doubles.install(_Patch(), ops)
+    torch.set_num_threads(1)
+    if world > 1:
+        dist.init_distributed('gloo')
+    model = _make(kind)
+    pm = ManualPipelineModule(layers=model.to_layers(), num_stages=stages, partition_method='uniform', manual_partition_split=None,
+                              loss_fn=model.get_loss_fn(), dynamic_shape=True, device=torch.device('cpu'))
+    engine, _, _, _ = initialize(model=pm, config={'train_micro_batch_size_per_gpu': 1, 'gradient_accumulation_steps': GAS,
+                                                   'gradient_clipping': 1.0, 'steps_per_print': 0, 'stage_link': 'dist',
+                                                   'pipeline_schedule': schedule})
+    params = [p for p in pm.parameters() if p.requires_grad]
+    engine._configure_optimizer(lambda ps: torch.optim.SGD(ps, lr=0.05) if ps else None, params)
+    losses = []
+    for step in range(2):
+        engine.reset_activation_shape()
+        mbs = _micro_batches(kind, model, GAS, 100 + step)
+        it = iter(mbs) if (engine.is_first_stage() or engine.is_last_stage()) else None
+        losses.append(float(engine.train_batch(it)))
+    ev_it = iter(_micro_batches(kind, model, 2, 999)) if (engine.is_first_stage() or engine.is_last_stage()) else None
+    ev = float(engine.eval_batch(ev_it, num_micro_batches=2))
+    torch.save({'losses': losses, 'eval': ev, 'norm': float(engine._grad_norm)}, os.path.join(outdir, f'rank{rank}.pt'))
+    if world > 1:
+        dist.barrier()
+
+
+def _run(kind, stages, schedule):
+    with tempfile.TemporaryDirectory() as d:
+        port = _free_port()
+        if stages == 1:
+            _worker(0, 1, port, kind, 1, schedule, d)
+            import torch.distributed as tdist
+            if tdist.is_initialized():
+                tdist.destroy_process_group()
+        else:
+            mp.spawn(_worker, args=(stages, port, kind, stages, schedule, d), nprocs=stages, join=True)
+        return [torch.load(os.path.join(d, f'rank{r}.pt'), weights_only=False) for r in range(stages)]
+
+
+@pytest.mark.parametrize('kind', ['qwen_image', 'wan'])
+def test_two_stage_pipeline_matches_single_stage(kind):
+    base = _run(kind, 1, '1f1b')[0]
+    assert all(v == v and 0 < v < 100 for v in base['losses'])
+    for schedule in ('1f1b', 'zb'):
+        for r in _run(kind, 2, schedule):
+            assert r['losses'] == pytest.approx(base['losses'], rel=2e-3), (kind, schedule, r['losses'], base['losses'])
+            assert r['eval'] == pytest.approx(base['eval'], rel=2e-3)
+            assert r['norm'] == pytest.approx(base['norm'], rel=2e-2)
