@@ -37,3 +37,55 @@ def test_bad_arguments_fail_loudly_without_a_gpu():
     rc = lib.dpipe_gemm_bf16(None, None)
     assert rc < 0 and b'null' in lib.dpipe_last_error()
     assert lib.dpipe_sched_train(0, 1, 0, None, 0) < 0
+
+
+def test_struct_sizes_of_the_wan_and_qk_entry_points_match_c_layout():
+    # sizes printed by gcc for include/dpipe.h (LP64): dpipe_wan_norm_proj, _fwd_args, _bwd_proj, _bwd_args, dpipe_qk_bwd_args
+    assert ctypes.sizeof(_abi.WanNormProj) == 56 and ctypes.sizeof(_abi.WanNormFwdArgs) == 208
+    assert ctypes.sizeof(_abi.WanNormBwdProj) == 64 and ctypes.sizeof(_abi.WanNormBwdArgs) == 232
+    assert ctypes.sizeof(_abi.QkBwdArgs) == 144
+
+
+def test_header_compiles_as_plain_c():
+    """include/dpipe.h is the boundary a C (not C++) caller binds: it must compile with gcc and agree on the struct sizes"""
+    import os
+    import shutil
+    import subprocess
+    import tempfile
+    if shutil.which('gcc') is None:
+        import pytest
+        pytest.skip('gcc not available')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, 'sz.c')
+        with open(src, 'w') as f:
+            f.write('#include <stdio.h>\n#include "dpipe.h"\nint main(void){ printf("%zu %zu %zu %zu\\n", sizeof(dpipe_wan_norm_fwd_args), '
+                    'sizeof(dpipe_wan_norm_bwd_args), sizeof(dpipe_qk_bwd_args), sizeof(dpipe_instr)); return 0; }\n')
+        exe = os.path.join(d, 'sz')
+        subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(root, 'include'), src, '-o', exe], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+    assert [int(x) for x in out] == [ctypes.sizeof(_abi.WanNormFwdArgs), ctypes.sizeof(_abi.WanNormBwdArgs),
+                                    ctypes.sizeof(_abi.QkBwdArgs), 12]
+
+
+def test_new_entry_points_validate_their_arguments_without_a_gpu():
+    lib = _lib.lib()
+    assert lib.dpipe_wan_norm_rope_fwd(None, None) < 0 and b'null' in lib.dpipe_last_error()
+    a = _abi.WanNormFwdArgs()
+    a.nproj, a.batch, a.seq, a.heads = 1, 1, 8, 57                   # 57 heads: 912-thread CTAs do not fit the register file
+    assert lib.dpipe_wan_norm_rope_fwd(ctypes.byref(a), None) < 0 and b'geometry' in lib.dpipe_last_error()
+    a.heads = 3                                                     # 384 columns: not a multiple of 256
+    assert lib.dpipe_wan_norm_rope_fwd(ctypes.byref(a), None) < 0
+    assert lib.dpipe_wan_norm_rope_bwd(None, None) < 0
+    # LayerNorm width rules (whole warps, one CTA per row group)
+    buf = ctypes.c_void_p(8)
+    assert lib.dpipe_ln_modulate_fwd_ex(buf, 100, buf, buf, 0, buf, 100, None, None, 1, 1, 100, 1e-6, 0, None) < 0
+    assert b'multiple of 256' in lib.dpipe_last_error()
+    assert lib.dpipe_ln_modulate_fwd_ex(buf, 8192, buf, buf, 0, buf, 8192, None, None, 1, 1, 8192, 1e-6, 0, None) < 0
+    # zero-bubble planner: weights must be positive and one per stage
+    w = (ctypes.c_int * 2)(3, 0)
+    assert lib.dpipe_sched_zb_ex(4, 2, 0, 13, 17, 10, 4, w, None, 0) < 0
+    assert lib.dpipe_sched_zb_makespan_ex(4, 2, 13, 17, 10, 4, w) < 0
+    # the batch-row modulation backward refuses what its register budget cannot hold
+    assert lib.dpipe_mod_bwd(buf, 0, buf, buf, buf, 0, buf, buf, buf, 8, 1024, 5120, None) < 0
+    assert b'not supported' in lib.dpipe_last_error()

@@ -144,3 +144,18 @@ def test_zero_bubble_schedule_single_and_two_stages():
     """the split-backward order changes when things run, not what is computed"""
     _check(_run(1, 1, 'uniform', 'zb'), 1)
     _check(_run(2, 2, 'manual', 'zb'), 1)
+
+
+@pytest.mark.parametrize('schedule', ['1f1b', 'zb'])
+def test_two_stages_times_two_replicas_world_4(schedule):
+    """BASELINE.json configs[4] shape (pipeline x data parallel): rank = stage * dp + dp_rank, per-stage DP groups for the
+    gradient all-reduce, per-replica pipe groups for the boundary traffic, the norm and the loss"""
+    res = _run(4, 2, 'uniform', schedule)
+    assert sorted((r['stage'], r['dp']) for r in res) == [(0, 0), (0, 1), (1, 0), (1, 1)]
+    assert [(r['stage'], r['dp']) for r in res] == [(0, 0), (0, 1), (1, 0), (1, 1)]      # pipe is the outer axis
+    losses, norms, ev, sd = _reference(2)
+    for r in res:
+        assert r['losses'] == pytest.approx(losses, rel=1e-5, abs=1e-7), (r['losses'], losses)
+        assert r['norms'] == pytest.approx(norms, rel=1e-5)
+        for k, v in r['params'].items():
+            assert torch.allclose(v, sd[k], rtol=1e-5, atol=1e-6), k
