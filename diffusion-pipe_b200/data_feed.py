@@ -18,6 +18,7 @@ Pinned by tests/golden/datafeed_traces.json, produced by executing the reference
 (tests/golden/make_golden_datafeed.py).
 """
 import math
+import os
 import random
 from collections import defaultdict
 
@@ -197,6 +198,7 @@ class PipelineDataLoader:
         self.num_batches_pulled = 0
         self.next_micro_batch = None
         self.recreate_dataloader = False
+        self._epoch0, self._consumed0, self._steps = 1, 0, 0     # for the communication-free epoch agreement (sync_epoch)
         self._create_dataloader()
         self.data = self._micro_batches()
 
@@ -204,6 +206,7 @@ class PipelineDataLoader:
         self.epoch = 1
         self.num_batches_pulled = 0
         self.next_micro_batch = None
+        self._epoch0, self._consumed0, self._steps = 1, 0, 0
         self.data = self._micro_batches()
 
     def set_eval_quantile(self, q):
@@ -264,12 +267,24 @@ class PipelineDataLoader:
         return target
 
     def sync_epoch(self):
-        """Middle stages never touch the dataloader: everyone adopts the largest epoch seen (train.py:921)."""
-        if dist.get_world_size() == 1:
-            return
-        seen = [None] * dist.get_world_size()
-        dist.all_gather_object(seen, self.epoch)
-        self.epoch = max(seen)
+        """Call once per step on every rank (train.py:921).  Middle stages never touch the dataloader; the reference makes
+        everyone adopt the largest epoch seen with an `all_gather_object` per step (utils/dataset.py:1410-1417) — a host
+        round trip over every rank.  The epoch is a pure function of the number of steps taken: every step consumes exactly
+        one item of the dataset (`gradient_accumulation_steps` micro-batches), and `epoch` advances during the step that
+        hands out the last one.  So every rank counts steps and computes the same value locally; the ranks that do pull
+        data check it against what they observed.  DPIPE_CHECK_EPOCH_SYNC=1 additionally runs the reference's all-gather
+        and asserts agreement."""
+        self._steps += 1
+        expected = self._epoch0 + (self._consumed0 + self._steps) // len(self.dataset)
+        pulls = self.model_engine.is_first_stage() or self.model_engine.is_last_stage()
+        if pulls and self.iter_called and expected != self.epoch:
+            raise RuntimeError(f'epoch bookkeeping diverged: counted {expected}, dataloader says {self.epoch} '
+                               f'(sync_epoch must be called exactly once per step)')
+        self.epoch = expected
+        if os.environ.get('DPIPE_CHECK_EPOCH_SYNC') == '1' and dist.get_world_size() > 1:
+            seen = [None] * dist.get_world_size()
+            dist.all_gather_object(seen, self.epoch)
+            assert len(set(seen)) == 1, f'ranks disagree on the epoch: {seen}'
 
     def state_dict(self):
         return {'epoch': self.epoch, 'num_batches_pulled': self.num_batches_pulled}
@@ -279,6 +294,7 @@ class PipelineDataLoader:
         self.epoch = state['epoch']
         # one batch is always pre-pulled, so one fewer has actually been consumed
         self.num_batches_pulled = state['num_batches_pulled'] - 1
+        self._epoch0, self._consumed0, self._steps = self.epoch, self.num_batches_pulled, 0
         self._create_dataloader(skip_first_n_batches=self.num_batches_pulled)
         self.data = self._micro_batches()
         self.recreate_dataloader = True   # skip only on the first pass

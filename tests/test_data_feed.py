@@ -139,3 +139,52 @@ def test_empty_and_dropped_buckets():
     assert len(ds) == 0
     with pytest.raises(RuntimeError):
         DF.PipelineDataLoader(ds, Engine(), 2, Model(), num_dataloader_workers=0)
+
+
+def test_sync_epoch_is_a_pure_function_of_the_step_count(golden):
+    """every rank — including middle stages that never see data — computes the epoch the pulling ranks observe, across
+    epoch boundaries, after reset() and after a resume, without communication (utils/dataset.py:1410-1417 replaced)"""
+    class Mid(Engine):
+        def is_first_stage(self):
+            return False
+
+        def is_last_stage(self):
+            return False
+    for key in golden['loader']:
+        lname, gas = key.split('|')
+        gas = int(gas)
+
+        def mk(engine):
+            ds = make(LAYOUTS[lname], with_mask=True)
+            ds.post_init(0, 1, {None: 2}, gas, {None: 2})
+            return DF.PipelineDataLoader(ds, engine, gas, Model(), num_dataloader_workers=0)
+        puller, middle = mk(Engine()), mk(Mid())
+        n = len(puller.dataset)
+        saved, saved_at = None, n + 1
+        for step in range(1, 3 * n + 2):
+            it = DF.get_data_iterator_for_step(puller, puller.model_engine, num_micro_batches=gas)
+            assert len(list(it)) == gas
+            assert DF.get_data_iterator_for_step(middle, middle.model_engine, num_micro_batches=gas) is None
+            puller.sync_epoch()                      # raises if the count and the dataloader disagree
+            middle.sync_epoch()
+            assert middle.epoch == puller.epoch == 1 + step // n, (key, step)
+            if step == saved_at:
+                saved = (puller.state_dict(), middle.state_dict(), puller.epoch)
+        # resume both from the saved state and keep going
+        p2, m2 = mk(Engine()), mk(Mid())
+        p2.load_state_dict(saved[0])
+        m2.load_state_dict(saved[0])                 # every rank loads the same client_state (train.py:870-875)
+        for step in range(saved_at + 1, saved_at + 2 * n):
+            list(DF.get_data_iterator_for_step(p2, p2.model_engine, num_micro_batches=gas))
+            p2.sync_epoch()
+            m2.sync_epoch()
+            assert m2.epoch == p2.epoch, (key, step)
+        # reset() (evaluation loops) restarts the count
+        puller.reset()
+        middle.reset()
+        for step in range(1, n + 1):
+            list(DF.get_data_iterator_for_step(puller, puller.model_engine, num_micro_batches=gas))
+            puller.sync_epoch()
+            middle.sync_epoch()
+            assert middle.epoch == puller.epoch
+        assert puller.epoch == 2
