@@ -103,3 +103,50 @@ def test_qwen_model_forward_backward_matches_oracle(doubles, control):
     feats2, _ = Q.prepare_inputs(latents, [pe[0][:5], pe[1]], t, noise)
     with pytest.raises(NotImplementedError):
         model.to_layers()[0](tuple(f.clone() for f in feats2))
+
+
+def test_activation_checkpointing_of_fused_blocks_is_equivalent(doubles):
+    """train.py:588-603 (`activation_checkpointing = true`): torch.utils.checkpoint around every block layer — the fused
+    autograd functions are recomputed in backward and give the same loss and gradients, also in the zero-bubble order"""
+    from functools import partial
+    from diffusion_pipe_b200.flux import FluxPipeline
+    from diffusion_pipe_b200.pipe import ManualPipelineModule, initialize
+    from oracle import flux_ref as R
+    cfg = {'num_attention_heads': 2, 'num_layers': 1, 'num_single_layers': 1, 'joint_attention_dim': 64, 'pooled_projection_dim': 32}
+    g = torch.Generator().manual_seed(1)
+    bs = 1
+    mbs = []
+    for _ in range(2):
+        latents, noise = torch.randn(bs, 16, 8, 8, generator=g), torch.randn(bs, 16, 8, 8, generator=g)
+        t5 = torch.randn(bs, 12, 64, generator=g).bfloat16()
+        clip = torch.randn(bs, 32, generator=g).bfloat16()
+        t = torch.sigmoid(torch.randn(bs, generator=g))
+        feats, (target, _) = R.prepare_inputs(latents, t5, clip, t, noise)
+        mbs.append((feats, (target, torch.tensor([]))))
+    results = []
+    for ckpt, schedule in ((False, '1f1b'), (True, '1f1b'), (True, 'zb')):
+        torch.manual_seed(0)
+        model = FluxPipeline({'model': {'dtype': 'bfloat16', 'guidance': 1.0, 'device': 'cpu', 'transformer_config': cfg}})
+        extra = {}
+        if ckpt:
+            extra = {'activation_checkpoint_interval': 1, 'checkpointable_layers': model.checkpointable_layers,
+                     'activation_checkpoint_func': partial(torch.utils.checkpoint.checkpoint, use_reentrant=False)}
+        pm = ManualPipelineModule(layers=model.to_layers(), num_stages=1, partition_method='uniform', manual_partition_split=None,
+                                  loss_fn=model.get_loss_fn(), dynamic_shape=True, device=torch.device('cpu'), **extra)
+        engine, _, _, _ = initialize(model=pm, config={'train_micro_batch_size_per_gpu': 1, 'gradient_accumulation_steps': 2,
+                                                       'gradient_clipping': 0.0, 'steps_per_print': 0, 'pipeline_schedule': schedule})
+        captured = {}
+
+        class Capture(torch.optim.SGD):
+            def step(self, closure=None):
+                captured.update({p.original_name: p.grad.detach().float().clone() for gr in self.param_groups for p in gr['params']})
+        params = [p for p in pm.parameters() if p.requires_grad]
+        engine._configure_optimizer(lambda ps: Capture(ps, lr=0.0), params)
+        loss = float(engine.train_batch(iter([(tuple(f.clone() for f in fe), la) for fe, la in mbs])))
+        results.append((loss, captured))
+    base_loss, base = results[0]
+    for loss, grads in results[1:]:
+        assert loss == pytest.approx(base_loss, rel=1e-6)
+        assert grads.keys() == base.keys()
+        for k in base:
+            torch.testing.assert_close(grads[k], base[k], rtol=1e-5, atol=1e-6, msg=k)
