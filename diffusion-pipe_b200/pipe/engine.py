@@ -285,7 +285,10 @@ class PipelineEngine:
                 self.link.release_activations(b, cmd.micro_batch_id)
 
     def _exec_backward_input(self, cmd, train):
-        """split backward: weight-gradient work of the layers that support it is queued instead of launched"""
+        """split backward: weight-gradient work of the layers that support it is queued instead of launched.
+        Contract for the queued closures (ops.defer): they may capture tensors the block produced, never tensors RECEIVED
+        from another stage — a received tensor is a view of a stage-link mailbox slot that is released to the sender as
+        soon as this pass (and its SendGrad) is enqueued.  wan.py clones the one boundary tensor it needs (`context`)."""
         from .. import ops
         q = []
         ops.WGRAD_DEFER = q

@@ -241,6 +241,11 @@ class WanBlockFn(torch.autograd.Function):
         if ca.q.weight.requires_grad:
             dbq_c = ops.colsum(dqc_lin)
             dbkv_c = ops.colsum(dkv_lin)
+            if ops.deferring():
+                # `context` arrives from the previous stage as a view of a stage-link mailbox slot, which is handed back
+                # to the sender once this input-gradient pass has been enqueued: a weight-gradient closure that runs
+                # later must own its copy (5 MB).  Nothing else a closure captures is a boundary tensor.
+                c2 = c2.clone()
 
             def wgrad_cq(ca=ca, dqc_lin=dqc_lin, xn3=xn3, dbq_c=dbq_c, dkv_lin=dkv_lin, c2=c2, dbkv_c=dbkv_c, dw_nqc=dw_nqc, dw_nkc=dw_nkc):
                 g, acc = _grad_buf(ca.q.weight)

@@ -113,3 +113,74 @@ def test_gradients_accumulate_over_micro_batches_and_deferral_is_equivalent(doub
     for n, p in ref.named_parameters():
         rel = ((want[n] - p.grad).norm() / (p.grad.norm() + 1e-12)).item()
         assert rel <= 6e-2, (n, rel)
+
+
+@pytest.mark.parametrize('family', ['wan', 'flux_double', 'flux_single'])
+def test_deferred_weight_gradients_do_not_read_boundary_tensors(doubles, family):
+    """zero-bubble contract (pipe/engine.py:_exec_backward_input): block inputs received from another stage are views of
+    a mailbox slot that is handed back right after the input-gradient pass; emulate the sender overwriting the slot
+    (NaN-poison every input in place) before the queued weight-gradient closures run"""
+    ops = doubles
+    torch.manual_seed(0)
+    if family == 'wan':
+        from diffusion_pipe_b200.wan import WanAttentionBlock, wan_rope_tables
+        mk = lambda: WanAttentionBlock(256, 512, 2, 1e-6, torch.bfloat16, 'cpu')
+        freqs = wan_rope_tables((2, 4, 4), 128)
+        ins = lambda: [(0.5 * torch.randn(2, 32, 256)).bfloat16().requires_grad_(True), (0.1 * torch.randn(2, 1, 6, 256)).bfloat16().requires_grad_(True),
+                       (0.5 * torch.randn(2, 16, 256)).bfloat16().requires_grad_(True)]
+        call = lambda blk, t: blk(t[0], t[1], None, None, freqs, t[2], None)
+    else:
+        from diffusion_pipe_b200.flux_blocks import FluxSingleTransformerBlock, FluxTransformerBlock
+        from oracle.flux_ref import flux_rope_tables
+        cls = FluxTransformerBlock if family == 'flux_double' else FluxSingleTransformerBlock
+        mk = lambda: cls(256, 2, 2, torch.bfloat16, 'cpu')
+        ids = torch.zeros(24, 3)
+        ids[8:, 1] = torch.arange(16) // 4
+        ids[8:, 2] = torch.arange(16) % 4
+        cos, sin = flux_rope_tables(ids)
+        ins = lambda: [(0.5 * torch.randn(2, 16, 256)).bfloat16().requires_grad_(True), (0.5 * torch.randn(2, 8, 256)).bfloat16().requires_grad_(True),
+                       (0.5 * torch.randn(2, 256)).bfloat16().requires_grad_(True)]
+
+        def call(blk, t):
+            e, h = blk(t[0], t[1], t[2], (cos, sin))
+            return torch.cat([e, h], dim=1)
+    torch.manual_seed(1)
+    blk = mk()
+    with torch.no_grad():
+        for p in blk.parameters():
+            if p.ndim == 1:
+                p.add_(0.05 * torch.randn_like(p.float()).to(p.dtype))
+    state = {k: v.clone() for k, v in blk.state_dict().items()}
+    torch.manual_seed(2)
+    t = ins()
+    gout = None
+
+    def run(poison):
+        nonlocal gout
+        b = mk()
+        b.load_state_dict(state)
+        torch.manual_seed(2)
+        tt = ins()
+        y = call(b, tt)
+        if gout is None:
+            gout = torch.randn_like(y.float()).to(y.dtype)
+        q = []
+        if poison:
+            ops.WGRAD_DEFER = q
+        try:
+            y.backward(gout)
+        finally:
+            ops.WGRAD_DEFER = None
+        if poison:
+            assert q
+            with torch.no_grad():
+                for x in tt:
+                    x.fill_(float('nan'))                 # the previous stage reuses the slot
+                for fn in q:
+                    fn()
+        return {n: p.grad.float().clone() for n, p in b.named_parameters() if p.grad is not None}
+    base, deferred = run(False), run(True)
+    assert base.keys() == deferred.keys() and base
+    for n in base:
+        assert torch.isfinite(deferred[n]).all(), n
+        torch.testing.assert_close(deferred[n], base[n], rtol=1e-5, atol=1e-6, msg=n)
