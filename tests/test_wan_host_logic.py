@@ -115,13 +115,14 @@ def test_gradients_accumulate_over_micro_batches_and_deferral_is_equivalent(doub
         assert rel <= 6e-2, (n, rel)
 
 
-@pytest.mark.parametrize('family', ['wan', 'flux_double', 'flux_single'])
+@pytest.mark.parametrize('family', ['wan', 'flux_double', 'flux_single', 'wan+lora', 'flux_double+lora', 'flux_single+lora'])
 def test_deferred_weight_gradients_do_not_read_boundary_tensors(doubles, family):
     """zero-bubble contract (pipe/engine.py:_exec_backward_input): block inputs received from another stage are views of
     a mailbox slot that is handed back right after the input-gradient pass; emulate the sender overwriting the slot
     (NaN-poison every input in place) before the queued weight-gradient closures run"""
     ops = doubles
     torch.manual_seed(0)
+    family, _, adapter = family.partition('+')
     if family == 'wan':
         from diffusion_pipe_b200.wan import WanAttentionBlock, wan_rope_tables
         mk = lambda: WanAttentionBlock(256, 512, 2, 1e-6, torch.bfloat16, 'cpu')
@@ -159,6 +160,14 @@ def test_deferred_weight_gradients_do_not_read_boundary_tensors(doubles, family)
         nonlocal gout
         b = mk()
         b.load_state_dict(state)
+        if adapter:
+            from diffusion_pipe_b200 import lora
+            assert lora.attach(b, 16) == 1
+            gl = torch.Generator().manual_seed(7)
+            with torch.no_grad():
+                for n, p in b.named_parameters():
+                    if '.lora_' in n:
+                        p.copy_((0.05 * torch.randn(p.shape, generator=gl)).bfloat16())
         torch.manual_seed(2)
         tt = ins()
         y = call(b, tt)
