@@ -332,9 +332,11 @@ def main():
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): algorithmic 2MNK per launch / CUDA-event duration ----
     roof = None
+    busy_local = 0.0
     if prof:
         torch.cuda.synchronize()
         tot_ms = sum(s.elapsed_time(e) for s, e, _, _, _ in prof)
+        busy_local = tot_ms / ms_dev if ms_dev else 0.0
         tot_fl = sum(f for _, _, f, _, _ in prof)
         gemm_ms = sum(s.elapsed_time(e) for s, e, _, k, _ in prof if k == 'gemm')
         gemm_fl = sum(f for _, _, f, k, _ in prof if k == 'gemm')
@@ -378,6 +380,13 @@ def main():
                 'kernels_share_of_step': tot_ms / (ms_dev if ms_dev else 1), 'share_by_kernel': kind_share,
                 'step_tflops': TRAIN_TFLOP_PER_SAMPLE * (n_double + n_single) / 57.0 * value / max(1, world)}
 
+    # kernel-busy fraction of every stage (instrumented kernels / step time): separates pipeline bubbles from imbalance
+    busy_t = torch.zeros(world, device=device, dtype=torch.float64)
+    busy_t[rank] = busy_local
+    if world > 1:
+        tdist.all_reduce(busy_t)
+    stage_busy = [round(float(x), 4) for x in busy_t.tolist()]
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         del dev_batches, host_batches
@@ -403,6 +412,7 @@ def main():
             'gpu_launches': int(lt.item()),
             'loss': loss_dev,
             'peak_mem_gib_max_rank': round(float(mem_t.item()), 1),
+            'stage_kernel_busy_frac': stage_busy,
             'clocks': clk,
         }
         if roof:
