@@ -243,8 +243,12 @@ class IpcLink:
         self.device = engine.device
         assert self.device.type == 'cuda'
         grid = engine.grid
-        # 1F1B keeps at most `stages` micro-batches in flight on a stage; the zero-bubble order may hold 2x as many
-        self.nslots = max(2, engine.num_stages) * (2 if engine.pipeline_schedule == 'zb' else 1)
+        # 1F1B keeps at most `stages` micro-batches in flight on a stage; the zero-bubble order holds up to
+        # `zb_max_inflight` (default 2 x stages).  A receiver that may hold n un-released activations needs n slots:
+        # with fewer, the sender would wait for a slot whose release is ordered AFTER the forward pass it is feeding.
+        self.nslots = max(2, engine.num_stages)
+        if engine.pipeline_schedule == 'zb':
+            self.nslots = max(2 * self.nslots, int(engine.zb_max_inflight or 2 * engine.num_stages))
         self.copy_stream = torch.cuda.Stream(device=self.device)
         # host control plane: one gloo group per pipeline (every rank creates all of them, in the same order)
         self.ctrl_group = None
