@@ -33,19 +33,19 @@ class _Patch:
         setattr(obj, name, value)
 
 
-def _make(kind):
+def _make(kind, device='cpu'):
     from synth import fill_parameters
     if kind == 'qwen_image':
         from diffusion_pipe_b200.qwen_image import QwenImagePipeline
         from oracle import qwen_ref as Q
-        model = QwenImagePipeline({'model': {'dtype': 'bfloat16', 'device': 'cpu',
+        model = QwenImagePipeline({'model': {'dtype': 'bfloat16', 'device': device,
                                              'transformer_config': {'num_attention_heads': 2, 'num_layers': 2, 'joint_attention_dim': 64}}})
         ref = fill_parameters(Q.RefQwenImageTransformer(dim=256, heads=2, num_layers=2, joint_dim=64))
     else:
         from diffusion_pipe_b200.wan import WanPipeline
         from oracle import wan_ref as W
         cfg = {'dim': 256, 'ffn_dim': 512, 'num_heads': 2, 'num_layers': 2, 'text_dim': 64, 'text_len': 16}
-        model = WanPipeline({'model': {'dtype': 'bfloat16', 'device': 'cpu', 'transformer_config': cfg}})
+        model = WanPipeline({'model': {'dtype': 'bfloat16', 'device': device, 'transformer_config': cfg}})
         ref = fill_parameters(W.RefWanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, text_len=16))
     sd = ref.state_dict()
     with torch.no_grad():
@@ -68,20 +68,29 @@ def _micro_batches(kind, model, n, seed):
     return data_feed.split_batch((feats, label), n)
 
 
-def _worker(rank, world, port, kind, stages, schedule, outdir):
-    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
-    import kernel_doubles
+def _worker(rank, world, port, kind, stages, schedule, outdir, gpu=False, link='dist'):
+    """gpu=False: CPU + gloo + kernel test doubles;  gpu=True (tests/test_pipeline_multigpu.py): one GPU per rank, NCCL,
+    the real kernels and the requested stage link"""
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     from diffusion_pipe_b200 import ops
     from diffusion_pipe_b200.pipe import ManualPipelineModule, dist, initialize
-    kernel_doubles.install(_Patch(), ops)
-    torch.set_num_threads(1)
-    if world > 1:
-        dist.init_distributed('gloo')
-    model = _make(kind)
+    if gpu:
+        torch.cuda.set_device(rank)
+        device = torch.device('cuda', rank)
+        if world > 1:
+            dist.init_distributed('nccl')
+    else:
+        import kernel_doubles
+        kernel_doubles.install(_Patch(), ops)
+        torch.set_num_threads(1)
+        device = torch.device('cpu')
+        if world > 1:
+            dist.init_distributed('gloo')
+    model = _make(kind, device)
     pm = ManualPipelineModule(layers=model.to_layers(), num_stages=stages, partition_method='uniform', manual_partition_split=None,
-                              loss_fn=model.get_loss_fn(), dynamic_shape=True, device=torch.device('cpu'))
+                              loss_fn=model.get_loss_fn(), dynamic_shape=True, device=device)
     engine, _, _, _ = initialize(model=pm, config={'train_micro_batch_size_per_gpu': 1, 'gradient_accumulation_steps': GAS,
-                                                   'gradient_clipping': 1.0, 'steps_per_print': 0, 'stage_link': 'dist',
+                                                   'gradient_clipping': 1.0, 'steps_per_print': 0, 'stage_link': link,
                                                    'pipeline_schedule': schedule})
     params = [p for p in pm.parameters() if p.requires_grad]
     engine._configure_optimizer(lambda ps: torch.optim.SGD(ps, lr=0.05) if ps else None, params)
@@ -98,16 +107,16 @@ def _worker(rank, world, port, kind, stages, schedule, outdir):
         dist.barrier()
 
 
-def _run(kind, stages, schedule):
+def _run(kind, stages, schedule, gpu=False, link='dist'):
     with tempfile.TemporaryDirectory() as d:
         port = _free_port()
-        if stages == 1:
+        if stages == 1 and not gpu:
             _worker(0, 1, port, kind, 1, schedule, d)
             import torch.distributed as tdist
             if tdist.is_initialized():
                 tdist.destroy_process_group()
         else:
-            mp.spawn(_worker, args=(stages, port, kind, stages, schedule, d), nprocs=stages, join=True)
+            mp.spawn(_worker, args=(stages, port, kind, stages, schedule, d, gpu, link), nprocs=stages, join=True)
         return [torch.load(os.path.join(d, f'rank{r}.pt'), weights_only=False) for r in range(stages)]
 
 

@@ -99,3 +99,17 @@ def test_zero_bubble_schedule_matches_single_stage(link):
     for r in res:
         assert r['losses'] == pytest.approx(base['losses'], rel=2e-3), (r['losses'], base['losses'])
         assert r['eval'] == pytest.approx(base['eval'], rel=2e-3)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+@pytest.mark.parametrize('kind', ['qwen_image', 'wan'])
+def test_qwen_and_wan_tuples_cross_the_ipc_link(kind):
+    """the other families' boundary tuples (bool key mask, int32 / int64 shape tensors, fp32 rope tables, text context)
+    over CUDA-IPC mailboxes, 1F1B and zero-bubble, against one stage (CPU twin: tests/test_families_pipeline_cpu.py)"""
+    sys.path.insert(0, HERE)
+    import test_families_pipeline_cpu as F
+    base = F._run(kind, 1, '1f1b', gpu=True)[0]
+    for schedule in ('1f1b', 'zb'):
+        for r in F._run(kind, 2, schedule, gpu=True, link='ipc'):
+            assert r['losses'] == pytest.approx(base['losses'], rel=2e-3), (kind, schedule, r['losses'], base['losses'])
+            assert r['eval'] == pytest.approx(base['eval'], rel=2e-3)
