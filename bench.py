@@ -45,6 +45,8 @@ def parse():
     ap.add_argument('--layers', type=str, default='19,38', help='double,single block counts (default = Flux-dev)')
     ap.add_argument('--no-optimizer', action='store_true', help='diagnostic: skip the optimizer step (INVALID as a bench value)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-library-baseline', action='store_true',
+                    help='skip the cuBLAS + SDPA timing of the restated reference blocks on the GPU (context only, N=1)')
     ap.add_argument('--schedule', default='auto', choices=['auto', '1f1b', 'zb'],
                     help="pipeline order: the reference's 1F1B or the split-backward zero-bubble order (auto: zb when stages > 1)")
     ap.add_argument('--profile-kernels', action='store_true', default=True)
@@ -128,6 +130,59 @@ def cpu_reference_sample(res, text_len, n_double, n_single, reps=1):
     desc = (f'oracle/flux_ref.py blocks, fp32, torch CPU, {cores} threads: 1 double ({times["double"]:.2f}s) + 1 single '
             f'({times["single"]:.2f}s) block fwd+bwd at L={Li + Lt}, D=3072, extrapolated x{n_double}/x{n_single}')
     return 1.0 / per_sample, desc, cores
+
+
+def gpu_library_sample(res, text_len, n_double, n_single, device, iters=3):
+    """what the reference's blocks would dispatch on this GPU — the restated blocks (oracle/flux_ref.py) under
+    torch.autocast(bf16), i.e. cuBLAS GEMMs, ATen elementwise kernels and torch SDPA (flash) — one double + one single
+    block forward+backward at the full shape, CUDA events, extrapolated to the whole model.  No activation checkpointing
+    (the reference adds a forward recompute on top when `activation_checkpointing = true`).  Context for the bench line, not
+    part of it; any failure here is reported as a string and never takes the bench line down."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import flux_ref as R
+    D, H = 3072, 24
+    Li, Lt = (res // 16) ** 2, text_len
+    ids = torch.zeros(Lt + Li, 3, device=device)
+    ids[Lt:, 1] = torch.arange(Li, device=device) // (res // 16)
+    ids[Lt:, 2] = torch.arange(Li, device=device) % (res // 16)
+    cos, sin = R.flux_rope_tables(ids)
+
+    def library_sdpa(q, k, v, emulate):
+        o = F.scaled_dot_product_attention(q.permute(0, 2, 1, 3).to(torch.bfloat16), k.permute(0, 2, 1, 3).to(torch.bfloat16),
+                                           v.permute(0, 2, 1, 3).to(torch.bfloat16))
+        return o.permute(0, 2, 1, 3)
+    saved = R.sdpa
+    R.sdpa = library_sdpa
+    times = {}
+    try:
+        for kind, cls in (('double', R.RefFluxTransformerBlock), ('single', R.RefFluxSingleTransformerBlock)):
+            blk = cls(D, H).to(device)
+            hid = torch.randn(1, Li, D, device=device, requires_grad=True)
+            enc = torch.randn(1, Lt, D, device=device, requires_grad=True)
+            temb = torch.randn(1, D, device=device, requires_grad=True)
+
+            def once():
+                with torch.autocast('cuda', dtype=torch.bfloat16):
+                    e, h = blk(hid, enc, temb, (cos, sin))
+                (h.float().sum() + e.float().sum()).backward()
+            once()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                once()
+            e1.record()
+            torch.cuda.synchronize()
+            times[kind] = e0.elapsed_time(e1) / iters / 1000.0
+            del blk, hid, enc, temb
+    finally:
+        R.sdpa = saved
+    per_sample = n_double * times['double'] + n_single * times['single']
+    return {'value': 1.0 / per_sample, 'unit': 'samples/s (blocks only, extrapolated)',
+            'kind': 'restated reference blocks on the GPU: cuBLAS + ATen + torch SDPA under autocast(bf16), no recompute',
+            'sample': f'1 double ({times["double"] * 1e3:.1f} ms) + 1 single ({times["single"] * 1e3:.1f} ms) block fwd+bwd at L={Li + Lt}, '
+                      f'extrapolated x{n_double}/x{n_single}'}
 
 
 def run_reference_arm(a):
@@ -398,6 +453,18 @@ def main():
         v, desc, cores = cpu_reference_sample(a.res, a.text_len, n_double, n_single)
         cpu = {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': desc}
 
+    link_name, schedule_name = type(engine.link).__name__, engine.pipeline_schedule
+    library = None
+    if rank == 0 and world == 1 and not a.no_library_baseline:
+        try:
+            del engine, pm, model, layers, params
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            library = gpu_library_sample(a.res, a.text_len, n_double, n_single, device)
+        except Exception as exc:      # context only: never lose the bench line over it
+            library = {'error': repr(exc)[:300]}
+
     if rank == 0:
         h2d = int(h2d_t.item())
         out = {
@@ -411,7 +478,7 @@ def main():
                        'activation_recompute': False, 'train_tflop_per_sample': TRAIN_TFLOP_PER_SAMPLE,
                        'optimizer': 'none (diagnostic)' if a.no_optimizer else 'torch.optim.AdamW(fused) bf16, clip 1.0',
                        'l2_flush': 'working set (>=24 GB of weights+grads per step) is far larger than the 126 MB L2',
-                       'stage_link': type(engine.link).__name__, 'pipeline_schedule': engine.pipeline_schedule},
+                       'stage_link': link_name, 'pipeline_schedule': schedule_name},
             'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                     'ms_per_step': ms_e2e / a.steps},
             'gpu_launches': int(lt.item()),
@@ -424,6 +491,8 @@ def main():
             out['roofline'] = roof
         if cpu:
             out['cpu_baseline'] = cpu
+        if library:
+            out['gpu_library_baseline'] = library
         print(json.dumps(out), flush=True)
     if world > 1:
         tdist.barrier()
