@@ -454,16 +454,6 @@ def main():
         cpu = {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': desc}
 
     link_name, schedule_name = type(engine.link).__name__, engine.pipeline_schedule
-    library = None
-    if rank == 0 and world == 1 and not a.no_library_baseline:
-        try:
-            del engine, pm, model, layers, params
-            import gc
-            gc.collect()
-            torch.cuda.empty_cache()
-            library = gpu_library_sample(a.res, a.text_len, n_double, n_single, device)
-        except Exception as exc:      # context only: never lose the bench line over it
-            library = {'error': repr(exc)[:300]}
 
     if rank == 0:
         h2d = int(h2d_t.item())
@@ -491,6 +481,17 @@ def main():
             out['roofline'] = roof
         if cpu:
             out['cpu_baseline'] = cpu
+        # every value of `out` is a plain Python number by now: whatever the context measurement below does, the line prints
+        library = None
+        if world == 1 and not a.no_library_baseline:
+            try:
+                del engine, pm, model, layers, params
+                import gc
+                gc.collect()
+                torch.cuda.empty_cache()
+                library = gpu_library_sample(a.res, a.text_len, n_double, n_single, device)
+            except Exception as exc:      # context only: never lose the bench line over it
+                library = {'error': repr(exc)[:300]}
         if library:
             out['gpu_library_baseline'] = library
         print(json.dumps(out), flush=True)
