@@ -150,3 +150,43 @@ def test_activation_checkpointing_of_fused_blocks_is_equivalent(doubles):
         assert grads.keys() == base.keys()
         for k in base:
             torch.testing.assert_close(grads[k], base[k], rtol=1e-5, atol=1e-6, msg=k)
+
+
+def test_flux_kontext_control_latents_match_oracle(doubles):
+    """Flux Kontext (models/flux.py:381-392): control latents are appended on the sequence axis with id[..., 0] = 1 and the
+    prediction keeps only the first img_seq_len tokens.  The reference slices inside OutputWrapper with a host sync
+    (:545-546); here the loss slices by the target's length — same loss, same gradients."""
+    from diffusion_pipe_b200.flux import FluxPipeline
+    from oracle import flux_ref as R
+    cfg = {'num_attention_heads': 2, 'num_layers': 1, 'num_single_layers': 1, 'joint_attention_dim': 64, 'pooled_projection_dim': 32}
+    torch.manual_seed(0)
+    model = FluxPipeline({'model': {'dtype': 'bfloat16', 'guidance': 1.0, 'device': 'cpu', 'transformer_config': cfg}})
+    ref = R.RefFluxTransformer(dim=256, heads=2, num_double=1, num_single=1, joint_dim=64, pooled_dim=32)
+    with torch.no_grad():
+        for n, p in model.transformer.named_parameters():
+            if p.ndim == 1 and 'norm_' not in n:
+                p.normal_(0, 0.05)
+    ref.load_state_dict({k: v.detach().float() for k, v in model.transformer.state_dict().items()})
+    ref.set_emulate_bf16(True)
+    g = torch.Generator().manual_seed(3)
+    batch = {'latents': torch.randn(2, 16, 8, 8, generator=g), 'control_latents': torch.randn(2, 16, 8, 8, generator=g),
+             't5_embed': torch.randn(2, 12, 64, generator=g).bfloat16(), 'clip_embed': torch.randn(2, 32, generator=g).bfloat16(), 'mask': None}
+    torch.manual_seed(5)
+    feats, (target, mask) = model.prepare_inputs(batch)
+    x_t, _, _, _, img_ids, _, _, img_seq_len = feats
+    assert x_t.shape == (2, 32, 64) and target.shape == (2, 16, 64) and img_seq_len.tolist() == [16, 16]
+    assert img_ids[:, :16, 0].abs().max() == 0 and bool((img_ids[:, 16:, 0] == 1).all())
+    label = (target, torch.tensor([]))
+    x = tuple(f.clone() for f in feats)
+    for layer in model.to_layers():
+        x = layer(x)
+    assert x.shape == (2, 32, 64)                      # every token is predicted; the loss keeps the first 16
+    loss = model.get_loss_fn()(x, label)
+    loss.backward()
+    y = tuple(f.clone() for f in feats)
+    for layer in R.to_layers(ref):
+        y = layer(y)
+    assert y.shape == (2, 16, 64)
+    rloss = R.loss_fn(y, label)
+    rloss.backward()
+    _compare(model.transformer.named_parameters(), ref, loss, rloss)
