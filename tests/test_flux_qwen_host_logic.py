@@ -190,3 +190,41 @@ def test_flux_kontext_control_latents_match_oracle(doubles):
     rloss = R.loss_fn(y, label)
     rloss.backward()
     _compare(model.transformer.named_parameters(), ref, loss, rloss)
+
+
+@pytest.mark.parametrize('family', ['flux', 'qwen_image', 'wan'])
+@pytest.mark.parametrize('variant', ['mask', 'huber', 'smooth_l1'])
+def test_masked_and_robust_losses_match_the_reference_loss(doubles, family, variant):
+    """models/base.py:418-436: per-pixel masks (train.py masks, resized nearest-exact to the latent grid and packed like the
+    latents) and the `huber_delta` / `smooth_l1_beta` config keys, on every family's prediction layout"""
+    from oracle import flux_ref as R
+    g = torch.Generator().manual_seed(11)
+    cfg_extra = {'huber': {'huber_delta': 0.7}, 'smooth_l1': {'smooth_l1_beta': 0.3}}.get(variant, {})
+    pix = torch.rand(2, 64, 64, generator=g).round()                     # one mask per sample at pixel resolution
+    if family == 'flux':
+        from diffusion_pipe_b200.flux import FluxPipeline
+        pipe = FluxPipeline(dict({'model': {'dtype': 'bfloat16', 'lazy_layers': True, 'device': 'cpu'}}, **cfg_extra))
+        batch = {'latents': torch.randn(2, 16, 8, 8, generator=g), 't5_embed': torch.randn(2, 6, 64, generator=g).bfloat16(),
+                 'clip_embed': torch.randn(2, 32, generator=g).bfloat16(), 'mask': pix}
+    elif family == 'qwen_image':
+        from diffusion_pipe_b200.qwen_image import QwenImagePipeline
+        pipe = QwenImagePipeline(dict({'model': {'dtype': 'bfloat16', 'lazy_layers': True, 'device': 'cpu'}}, **cfg_extra))
+        batch = {'latents': torch.randn(2, 16, 1, 8, 8, generator=g), 'prompt_embeds': [torch.randn(5, 64, generator=g) for _ in range(2)], 'mask': pix}
+    else:
+        from diffusion_pipe_b200.wan import WanPipeline
+        pipe = WanPipeline(dict({'model': {'dtype': 'bfloat16', 'lazy_layers': True, 'device': 'cpu'}}, **cfg_extra))
+        batch = {'latents': torch.randn(2, 16, 3, 8, 8, generator=g), 'text_embeddings': torch.randn(2, 16, 64, generator=g),
+                 'seq_lens': torch.tensor([9, 16]), 'mask': pix}
+    _, (target, mask) = pipe.prepare_inputs(batch)
+    assert mask is not None and mask.shape[0] == 2 and torch.broadcast_shapes(mask.shape, target.shape) == target.shape
+    assert set(mask.unique().tolist()) <= {0.0, 1.0} and 0 < float(mask.mean()) < 1
+    if variant != 'mask':
+        mask = torch.tensor([])
+    pred = (target + 0.3 * torch.randn(target.shape, generator=g)).bfloat16().requires_grad_(True)
+    loss = pipe.get_loss_fn()(pred, (target, mask))
+    loss.backward()
+    ref_pred = pred.detach().float().requires_grad_(True)
+    rloss = R.loss_fn(ref_pred, (target, mask), huber_delta=cfg_extra.get('huber_delta'), smooth_l1_beta=cfg_extra.get('smooth_l1_beta'))
+    rloss.backward()
+    assert loss.item() == pytest.approx(rloss.item(), rel=1e-5)
+    torch.testing.assert_close(pred.grad.float(), ref_pred.grad, rtol=2e-2, atol=1e-6)
