@@ -95,6 +95,33 @@ class DistLink:
             out.append(t)
         return tuple(out)
 
+    # ---- the engine's four boundary operations ----
+    def send_activations(self, outputs, buf, mb, keep=True):
+        self.send_tuple(tuple(outputs), self.engine.grid.stage_to_global(self.engine.next_stage), ('act', len(outputs)))
+
+    def recv_activations(self, buf, mb):
+        return self.recv_tuple(self.engine.grid.stage_to_global(self.engine.prev_stage), 'act')
+
+    def send_grads(self, grads, buf, mb):
+        dst = self.engine.grid.stage_to_global(self.engine.prev_stage)
+        for g in grads:
+            self._send(g.contiguous(), dst)
+
+    def recv_grads(self, like, buf, mb):
+        src = self.engine.grid.stage_to_global(self.engine.next_stage)
+        out = []
+        for t in like:
+            g = torch.empty_like(t, memory_format=torch.contiguous_format)
+            dist.recv(g, src)
+            out.append(g)
+        return out
+
+    def release_grads(self, buf, mb):
+        pass        # received tensors are ordinary allocations: nothing to hand back (IpcLink recycles mailbox slots here)
+
+    def release_activations(self, buf, mb):
+        pass
+
 
 class PipelineEngine:
     def __init__(self, model, config, args=None):
@@ -239,7 +266,7 @@ class PipelineEngine:
         for tick in sched.steps():
             for cmd in tick:
                 handlers[type(cmd)](self, cmd, train)
-        self.link.flush() if hasattr(self.link, 'flush') else None
+        self.link.flush()
 
     def _exec_load_micro_batch(self, cmd, train):
         b = cmd.buffer_id
@@ -281,7 +308,7 @@ class PipelineEngine:
             self.pipe_buffers['outputs'][b] = tuple(outputs)
         if not train:
             self.pipe_buffers['inputs'][b] = None
-            if self.is_last_stage() and not self.is_first_stage() and hasattr(self.link, 'release_activations'):
+            if self.is_last_stage() and not self.is_first_stage():
                 self.link.release_activations(b, cmd.micro_batch_id)
 
     def _exec_backward_input(self, cmd, train):
@@ -314,8 +341,7 @@ class PipelineEngine:
             assert len(outs) == len(grads)
             pairs = [(t, g) for t, g in zip(outs, grads) if t.requires_grad]
             torch.autograd.backward(tensors=[p[0] for p in pairs], grad_tensors=[p[1] for p in pairs])
-            if hasattr(self.link, 'release_grads'):
-                self.link.release_grads(b, cmd.micro_batch_id)
+            self.link.release_grads(b, cmd.micro_batch_id)
         self.pipe_buffers['outputs'][b] = None
         self.pipe_buffers['grads'][b] = None
         self.pipe_buffers['labels'][b] = None
@@ -519,40 +545,6 @@ class PipelineEngine:
         self.global_steps = state.get('global_steps', 0)
         self.global_samples = state.get('global_samples', 0)
         return os.path.join(load_dir, tag), state.get('client_state', {})
-
-
-class _LinkShim:
-    """Adapts the tuple transport (DistLink) to the engine's four boundary operations."""
-
-
-def _dist_send_activations(self, outputs, buf, mb, keep=True):
-    self.send_tuple(tuple(outputs), self.engine.grid.stage_to_global(self.engine.next_stage), ('act', len(outputs)))
-
-
-def _dist_recv_activations(self, buf, mb):
-    return self.recv_tuple(self.engine.grid.stage_to_global(self.engine.prev_stage), 'act')
-
-
-def _dist_send_grads(self, grads, buf, mb):
-    dst = self.engine.grid.stage_to_global(self.engine.prev_stage)
-    for g in grads:
-        self._send(g.contiguous(), dst)
-
-
-def _dist_recv_grads(self, like, buf, mb):
-    src = self.engine.grid.stage_to_global(self.engine.next_stage)
-    out = []
-    for t in like:
-        g = torch.empty_like(t, memory_format=torch.contiguous_format)
-        dist.recv(g, src)
-        out.append(g)
-    return out
-
-
-DistLink.send_activations = _dist_send_activations
-DistLink.recv_activations = _dist_recv_activations
-DistLink.send_grads = _dist_send_grads
-DistLink.recv_grads = _dist_recv_grads
 
 
 def initialize(args=None, model=None, config=None, **kwargs):
