@@ -136,6 +136,41 @@ def _mod_bwd(dmod32, temb, lin, d_temb32):
 # =====================================================================================================================
 # double-stream block
 # =====================================================================================================================
+def _valid_rows(n_txt, Lt, Ltot, device):
+    """rows of the joint [text; image] sequence that exist for a sample with n_txt real prompt tokens"""
+    return torch.cat([torch.arange(n_txt, device=device), torch.arange(Lt, Ltot, device=device)])
+
+
+def _ragged_attn_fwd(q, k, v, Lt, txt_lens):
+    """Joint attention for a micro-batch whose prompts have different lengths (key-padding mask of
+    models/qwen_image.py:472-476): every sample attends over its own valid rows only — gathered into a dense
+    [1, H, L_b, 128] problem for the same kernels.  Padded text rows are neither keys nor (meaningful) queries; their
+    output is zero, which no loss term can see (they are masked out of the keys of every later block)."""
+    B, H, Ltot, _ = q.shape
+    o = torch.zeros((B * Ltot, H * HD), dtype=q.dtype, device=q.device)
+    o3 = o.view(B, Ltot, H * HD)
+    saved = []
+    for b, n in enumerate(txt_lens):
+        idx = _valid_rows(int(n), Lt, Ltot, q.device)
+        qb, kb, vb = (t[b:b + 1].index_select(2, idx) for t in (q, k, v))
+        ob, lse_b = ops.attn_fwd(qb, kb, vb)
+        o3[b].index_copy_(0, idx, ob)
+        saved.append((idx, qb, kb, vb, ob, lse_b))
+    return o, saved
+
+
+def _ragged_attn_bwd(saved, d_o, shape):
+    B, H, Ltot, _ = shape
+    d_o3 = d_o.view(B, Ltot, H * HD)
+    dq, dk, dv = (torch.zeros(shape, dtype=d_o.dtype, device=d_o.device) for _ in range(3))
+    for b, (idx, qb, kb, vb, ob, lse_b) in enumerate(saved):
+        dqb, dkb, dvb = ops.attn_bwd(qb, kb, vb, ob, d_o3[b].index_select(0, idx), lse_b)
+        dq[b].index_copy_(1, idx, dqb[0])
+        dk[b].index_copy_(1, idx, dkb[0])
+        dv[b].index_copy_(1, idx, dvb[0])
+    return dq, dk, dv
+
+
 class _Stream:
     """Per-stream (image or text) state saved by the double block forward."""
     __slots__ = ('x', 'mod', 'mean1', 'rstd1', 'y_attn', 'x1', 'mean2', 'rstd2', 'u', 'h', 'y_mlp', 'L', 'off')
@@ -143,7 +178,8 @@ class _Stream:
 
 class FluxDoubleBlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, blk, hidden, enc, temb, cos, sin):
+    def forward(ctx, blk, hidden, enc, temb, cos, sin, txt_lens=None):
+        """txt_lens: None (every text row is a real token) or one prompt length per sample (Qwen-Image key mask)"""
         B, Li, D = hidden.shape
         Lt = enc.shape[1]
         Ltot = Li + Lt
@@ -172,7 +208,11 @@ class FluxDoubleBlockFn(torch.autograd.Function):
             e = ops.make_qkv_epilogue(q, k, v, nq.weight, nk.weight, cos, sin, H, Ltot, off, qhat, khat, q_rstd, k_rstd)
             ops.gemm(xn, fq.weight, bias=fq.bias, epilogue=ops.EPI_QKV_ROPE, out=xn, rows_per_batch=L, qkv=e)
             streams.append(st)
-        o, lse = ops.attn_fwd(q, k, v)                                    # o: [B*Ltot, H*HD] token-major
+        if txt_lens is None:
+            o, lse = ops.attn_fwd(q, k, v)                                # o: [B*Ltot, H*HD] token-major
+        else:
+            o, lse = _ragged_attn_fwd(q, k, v, Lt, txt_lens)              # lse: per-sample saved state
+        ctx.ragged = txt_lens is not None
         o3 = o.view(B, Ltot, H * HD)
         outs = []
         tail = ((blk.attn.to_out[0], blk.ff), (blk.attn.to_add_out, blk.ff_context))
@@ -261,7 +301,10 @@ class FluxDoubleBlockFn(torch.autograd.Function):
                 ops.defer(wgrad_wo)
             dmods.append(dmod)
             dx1s.append(dx1)
-        dq, dk, dv = ops.attn_bwd(q, k, v, o, d_o, lse)
+        if ctx.ragged:
+            dq, dk, dv = _ragged_attn_bwd(lse, d_o, q.shape)
+        else:
+            dq, dk, dv = ops.attn_bwd(q, k, v, o, d_o, lse)
         d_temb = torch.zeros_like(temb, dtype=torch.float32)
         grads = []
         spec = ((blk.norm1.linear, blk.qkv, blk.attn.norm_q, blk.attn.norm_k),
@@ -289,7 +332,7 @@ class FluxDoubleBlockFn(torch.autograd.Function):
             grads.append(dx.view(B, L, D))
         ctx.streams = None
         ctx.attn = None
-        return None, grads[0], grads[1], d_temb.to(temb.dtype), None, None
+        return None, grads[0], grads[1], d_temb.to(temb.dtype), None, None, None
 
 
 class _Attn(nn.Module):
@@ -345,7 +388,7 @@ class FluxTransformerBlock(nn.Module):
             from .lora import FluxDoubleBlockLoraFn
             h, e = FluxDoubleBlockLoraFn.apply(self, hidden_states, encoder_hidden_states, temb, cos, sin)
             return e, h
-        h, e = FluxDoubleBlockFn.apply(self, hidden_states, encoder_hidden_states, temb, cos, sin)
+        h, e = FluxDoubleBlockFn.apply(self, hidden_states, encoder_hidden_states, temb, cos, sin, None)
         return e, h
 
 

@@ -16,9 +16,11 @@ QwenEmbedRope(scale_rope=True) and the pipeline layers.
 Two deliberate differences from the reference's tuple contents (both internal to these layers):
   * vid_freqs / txt_freqs travel as real fp32 `[2, tokens, 128]` (cos, sin; every frequency repeated twice) instead
     of complex64 `[tokens, 64]`: the same numbers in the form the fused q/k-norm+RoPE epilogue consumes;
-  * the bool key mask (models/qwen_image.py:472-476) must be all-True.  With micro-batch 1 — the configuration the
-    reference documents and BASELINE.json quotes — prepare_inputs trims the prompt to its real length, so it always is.
-    Ragged prompts inside one micro-batch raise NotImplementedError (no silent fallback).
+  * the bool key mask (models/qwen_image.py:472-476) is all-True with micro-batch 1 — the configuration the reference
+    documents and BASELINE.json quotes — because prepare_inputs trims the prompt to its real length.  When prompts of
+    different lengths share a micro-batch, InitialLayer appends their lengths to the tuple (one int32 tensor, last
+    element) and every block attends per sample over its valid rows (flux_blocks._ragged_attn_fwd): same loss and
+    gradients as masking, on the same dense kernels.  Masks with holes inside a prompt raise NotImplementedError.
 """
 import json
 import math
@@ -73,13 +75,16 @@ class QwenImageTransformerBlock(nn.Module):
         d['ff'], d['ff_context'] = self.img_mlp, self.txt_mlp
 
     def forward(self, hidden_states, encoder_hidden_states, temb, image_rotary_emb, encoder_hidden_states_mask=None,
-                joint_attention_kwargs=None):
+                joint_attention_kwargs=None, txt_lens=None):
+        """txt_lens: None, or the real prompt length of every sample when the micro-batch is padded (key mask)"""
         cos, sin = image_rotary_emb            # joint [text; image] tables, fp32 [L, 128]
         if 'lora' in self.__dict__:
+            if txt_lens is not None:
+                raise NotImplementedError('LoRA with ragged prompts inside one micro-batch: use micro_batch_size_per_gpu = 1')
             from .lora import FluxDoubleBlockLoraFn
             h, e = FluxDoubleBlockLoraFn.apply(self, hidden_states, encoder_hidden_states, temb, cos, sin)
             return e, h
-        h, e = FluxDoubleBlockFn.apply(self, hidden_states, encoder_hidden_states, temb, cos, sin)
+        h, e = FluxDoubleBlockFn.apply(self, hidden_states, encoder_hidden_states, temb, cos, sin, txt_lens)
         return e, h
 
 
@@ -187,12 +192,16 @@ class InitialLayer(nn.Module):
         temb = self.time_text_embed(timestep)
         shapes = img_shapes.tolist()           # host sync, as in the reference (:535-536)
         lens = txt_seq_lens.tolist()
-        if not bool(attention_mask.all()):
-            raise NotImplementedError(
-                'Qwen-Image key-padding mask with padded (ragged) prompts inside one micro-batch is not supported by the '
-                'sm_100a attention kernel yet; use micro_batch_size_per_gpu = 1 or equal-length prompts')
         vid_freqs, txt_freqs = qwen_rope_tables([tuple(s) for s in shapes[0]], max(lens), self.axes_dim,
                                                 device=hidden_states.device)
+        Lt = encoder_hidden_states.shape[1]
+        key_lens = attention_mask.reshape(attention_mask.shape[0], -1)[:, :Lt].sum(dim=1).to(torch.int32)
+        if int(key_lens.min()) < Lt:
+            # padded prompts: the per-sample prompt lengths travel with the tuple as one extra int32 tensor (LAST element;
+            # `img_seq_len` of the Edit variant is int64), which the block layers read — only in this case
+            if not bool((attention_mask.reshape(attention_mask.shape[0], -1)[:, :Lt].int().diff(dim=1) <= 0).all()):
+                raise NotImplementedError('key mask with holes inside the prompt (only trailing padding is supported)')
+            extra = list(extra) + [key_lens]
         return make_contiguous(hidden_states, encoder_hidden_states, attention_mask, temb, vid_freqs, txt_freqs) + tuple(extra)
 
 
@@ -205,9 +214,12 @@ class TransformerLayer(nn.Module):
     def forward(self, inputs):
         hidden_states, encoder_hidden_states, attention_mask, temb, vid_freqs, txt_freqs, *extra = inputs
         joint = torch.cat([txt_freqs, vid_freqs], dim=1)           # [2, Lt + Li, 128], order [text, image]
+        txt_lens = None
+        if extra and extra[-1].dtype == torch.int32:               # padded prompts (InitialLayer): host read, ragged path
+            txt_lens = extra[-1].tolist()
         encoder_hidden_states, hidden_states = self.block(
             hidden_states=hidden_states, encoder_hidden_states=encoder_hidden_states, temb=temb,
-            image_rotary_emb=(joint[0], joint[1]))
+            image_rotary_emb=(joint[0], joint[1]), txt_lens=txt_lens)
         return make_contiguous(hidden_states, encoder_hidden_states, attention_mask, temb, vid_freqs, txt_freqs) + tuple(extra)
 
 

@@ -99,10 +99,27 @@ def test_qwen_model_forward_backward_matches_oracle(doubles, control):
     rloss = R.loss_fn(y, label)
     rloss.backward()
     _compare(model.transformer.named_parameters(), ref, loss, rloss, skip_none=True)
-    # ragged prompts inside one micro-batch are refused, not silently mis-attended
-    feats2, _ = Q.prepare_inputs(latents, [pe[0][:5], pe[1]], t, noise)
-    with pytest.raises(NotImplementedError):
-        model.to_layers()[0](tuple(f.clone() for f in feats2))
+    # ragged prompts inside one micro-batch: the bool key mask of models/qwen_image.py:472-476 — every sample attends
+    # over its own real prompt tokens + all image tokens; loss and every parameter gradient match the masked oracle
+    model.transformer.zero_grad(set_to_none=True)
+    ref.zero_grad()
+    feats2, (target2, _) = Q.prepare_inputs(latents, [pe[0][:5], pe[1]], t, noise, control_latents=ctrl)
+    assert not bool(feats2[2].all())
+    label2 = (target2, torch.tensor([]))
+    x = tuple(f.clone() for f in feats2)
+    layers = model.to_layers()
+    x = layers[0](x)
+    assert x[-1].dtype == torch.int32 and x[-1].tolist() == [5, 11]      # the prompt lengths ride at the end of the tuple
+    for layer in layers[1:]:
+        x = layer(x)
+    loss2 = model.get_loss_fn()(x, label2)
+    loss2.backward()
+    y = tuple(f.clone() for f in feats2)
+    for layer in Q.to_layers(ref):
+        y = layer(y)
+    rloss2 = R.loss_fn(y, label2)
+    rloss2.backward()
+    _compare(model.transformer.named_parameters(), ref, loss2, rloss2, skip_none=True)
 
 
 def test_activation_checkpointing_of_fused_blocks_is_equivalent(doubles):

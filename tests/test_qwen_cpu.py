@@ -78,7 +78,7 @@ def test_lazy_layer_specs_cover_the_model():
     assert names == {n for n, _ in full.named_parameters()}
 
 
-def test_ragged_prompts_in_one_micro_batch_fail_loudly():
+def test_ragged_prompts_produce_a_key_mask_with_trailing_padding():
     pipe = P.QwenImagePipeline({'model': {'dtype': 'bfloat16', 'lazy_layers': True, 'transformer_config': CFG}}, device='cpu')
     lat = torch.randn(2, 16, 1, 8, 8)
     feats, _ = pipe.prepare_inputs({'latents': lat, 'prompt_embeds': [torch.randn(3, 64), torch.randn(6, 64)], 'mask': None})
