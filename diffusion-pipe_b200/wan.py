@@ -11,8 +11,9 @@ A WanAttentionBlock (models/wan/model.py:242-318) is ONE torch.autograd.Function
 GELU / gated-residual epilogues, the fused attention kernels (self-attention over the video tokens with RoPE,
 cross-attention over the 512 text slots), the LayerNorm+modulation kernels in their "bf16 after every op" mode (the
 block's operands are all bf16 tensors in the reference) and the full-width RMSNorm+RoPE kernels of csrc/wan_norm.cu.
-Scope: model_type 't2v' (Wan2.1 / Wan2.2 T2V: cross_attn_type 'default') with cached text embeddings; i2v / flf2v /
-ti2v variants (CLIP image context, per-token timesteps) raise NotImplementedError.
+Scope: model_type 't2v' (Wan2.1 / Wan2.2 T2V) and 'i2v_v2' (Wan2.2 I2V: first-frame mask + conditioning latents as extra
+input channels), both cross_attn_type 'default', with cached text embeddings; Wan2.1 i2v / flf2v (CLIP image context)
+and ti2v (per-token timesteps) raise NotImplementedError.
 
 Differences from the reference's tuple contents (internal to these layers): `freqs` travels as real fp32
 `[2, L, 128]` (cos, sin of the per-token multipliers rope_apply builds from `grid_sizes`, models/wan/model.py:41-68)
@@ -429,8 +430,10 @@ class WanModel(nn.Module):
     def __init__(self, cfg=None, dtype=torch.bfloat16, device='cuda'):
         super().__init__()
         cfg = dict(WAN_T2V_14B_CONFIG, **(cfg or {}))
-        if cfg['model_type'] != 't2v':
-            raise NotImplementedError(f"Wan model_type {cfg['model_type']!r}: only 't2v' runs on the sm_100a path")
+        if cfg['model_type'] not in ('t2v', 'i2v_v2'):
+            raise NotImplementedError(f"Wan model_type {cfg['model_type']!r}: 't2v' and 'i2v_v2' (Wan2.2 I2V) run on the sm_100a path")
+        if cfg['model_type'] == 'i2v_v2' and cfg['in_dim'] == 16:
+            cfg['in_dim'] = 36           # models/wan/configs.py (i2v_A14B): x + mask + y channels
         self.config = cfg
         dim = cfg['dim']
         self.dim, self.num_heads, self.freq_dim, self.text_len = dim, cfg['num_heads'], cfg['freq_dim'], cfg['text_len']
@@ -469,16 +472,25 @@ class InitialLayer(nn.Module):
         self.text_embedding, self.time_projection = text_embedding, time_projection
         self.dim, self.num_heads, self.freq_dim, self.text_len = cfg['dim'], cfg['num_heads'], cfg['freq_dim'], cfg['text_len']
         self.patch_size = tuple(cfg['patch_size'])
+        self.model_type = cfg.get('model_type', 't2v')
 
     def forward(self, inputs):
         for item in inputs:
             if torch.is_floating_point(item) and item.numel() > 0:
                 item.requires_grad_(True)
         x, y, t, text_embeddings, text_seq_lens, clip_fea = inputs
-        if y.numel() > 0 or clip_fea.numel() > 0:
-            raise NotImplementedError('Wan i2v / flf2v conditioning (y, clip_fea) is not on the sm_100a path')
+        if clip_fea.numel() > 0 or (y.numel() > 0) != (self.model_type == 'i2v_v2'):
+            raise NotImplementedError('Wan2.1 i2v / flf2v conditioning (CLIP image context) is not on the sm_100a path; '
+                                      "model_type 'i2v_v2' expects `y`, 't2v' must not get it")
         if torch.is_floating_point(text_seq_lens) or not torch.is_floating_point(text_embeddings):
             raise NotImplementedError('uncached text encoder (token ids in the pipeline tuple) is not supported: cache_text_embeddings must be true')
+        if self.model_type == 'i2v_v2':
+            # Wan2.2 I2V (models/wan/wan.py:459-465): first-frame mask (4 channels, 1 on frame 0) and the conditioning
+            # latents y ride as extra input channels of the patch embedding: [x | mask | y] = 16 + 4 + 16
+            bs_, _, f_, h_, w_ = x.shape
+            fmask = torch.zeros((bs_, 4, f_, h_, w_), device=x.device, dtype=x.dtype)
+            fmask[:, :, 0, ...] = 1
+            x = torch.cat([x, fmask, y.to(x.dtype)], dim=1)
         bs, c, f, h, w = x.shape
         pt, ph, pw = self.patch_size
         dev = x.device
@@ -596,6 +608,8 @@ class WanPipeline:
                 tcfg = json.load(f)
         self.tcfg = dict(WAN_T2V_14B_CONFIG, **(tcfg or {}))
         self.model_type = self.tcfg['model_type']
+        if self.model_type == 'i2v_v2' and 'in_dim' not in (tcfg or {}):
+            self.tcfg['in_dim'] = 36
         device = self.model_config.get("device", device)      # (tests: "cpu" with the kernel test doubles)
         self.dtype, self.device = dtype, device
         self.t_dist = get_t_distribution(self.model_config)
@@ -665,7 +679,8 @@ class WanPipeline:
         x_t = (1 - te) * x_1 + te * x_0
         target = x_0 - x_1
         t = t * 1000
-        return (x_t, None, t, text_embeddings, seq_lens, None), (target, mask)
+        y = inputs['y'] if self.model_type == 'i2v_v2' else None          # models/wan/wan.py:335
+        return (x_t, y, t, text_embeddings, seq_lens, None), (target, mask)
 
     # ---- layers / loss ----
     def to_layers(self):

@@ -173,8 +173,10 @@ class RefWanModel(nn.Module):
     """Parameter container with the reference's names (WanModel, model_type 't2v')."""
 
     def __init__(self, dim=5120, ffn_dim=13824, num_heads=40, num_layers=40, in_dim=16, out_dim=16, text_dim=4096,
-                 text_len=512, freq_dim=256, patch_size=(1, 2, 2), eps=1e-6):
+                 text_len=512, freq_dim=256, patch_size=(1, 2, 2), eps=1e-6, model_type='t2v'):
         super().__init__()
+        assert model_type in ('t2v', 'i2v_v2')       # i2v_v2 = Wan2.2 I2V: first-frame latents + mask as extra input channels
+        self.model_type = model_type
         self.dim, self.num_heads, self.freq_dim, self.text_len = dim, num_heads, freq_dim, text_len
         self.patch_size, self.out_dim = tuple(patch_size), out_dim
         self.patch_embedding = nn.Conv3d(in_dim, dim, kernel_size=patch_size, stride=patch_size)
@@ -220,6 +222,11 @@ class RefInitialLayer(nn.Module):
         emu = self.emulate_bf16
         x, y, t, text_embeddings, text_seq_lens, clip_fea = inputs
         context = [emb[:length] for emb, length in zip(text_embeddings, text_seq_lens)]
+        if m.model_type == 'i2v_v2':                  # models/wan/wan.py:459-465: [x | mask (first frame = 1) | y] channels
+            bs, _, f, h, w_ = x.shape
+            mask = torch.zeros((bs, 4, f, h, w_), dtype=x.dtype)
+            mask[:, :, 0, ...] = 1
+            x = torch.cat([x, mask, y], dim=1)
         w, b = self.patch_embedding.weight.float(), self.patch_embedding.bias.float()
         x = [_r(F.conv3d(_r(u.unsqueeze(0).float(), emu), w, b, stride=m.patch_size), emu) for u in x]
         grid_sizes = torch.stack([torch.tensor(u.shape[2:], dtype=torch.long) for u in x])
@@ -274,8 +281,9 @@ def t_distribution(method='logit_normal', sigmoid_scale=1.0):
     return torch.sigmoid(t * sigmoid_scale) if method == 'logit_normal' else t
 
 
-def prepare_inputs(latents, text_embeddings, seq_lens, t, noise, mask=None):
-    """models/wan/wan.py:332-373 (t2v) with the random draws (t in [0,1], x_0) passed in."""
+def prepare_inputs(latents, text_embeddings, seq_lens, t, noise, mask=None, y=None):
+    """models/wan/wan.py:332-373 (t2v; i2v_v2 when the first-frame conditioning latents `y` are given) with the random
+    draws (t in [0,1], x_0) passed in."""
     latents = latents.float()
     bs, c, f, h, w = latents.shape
     if mask is not None:
@@ -284,4 +292,4 @@ def prepare_inputs(latents, text_embeddings, seq_lens, t, noise, mask=None):
     x_t = (1 - te) * latents + te * noise
     target = noise - latents
     none = torch.tensor([])           # utils/dataset.py:1277-1279: None travels through the pipeline as an empty tensor
-    return (x_t, none, t * 1000, text_embeddings, seq_lens, none), (target, mask)
+    return (x_t, none if y is None else y, t * 1000, text_embeddings, seq_lens, none), (target, mask)

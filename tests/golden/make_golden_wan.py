@@ -119,6 +119,32 @@ def main():
                   'dx': bx.grad.clone(), 'de0': be0.grad.clone(), 'dctx': bctx.grad.clone(),
                   'rope_cos': freqs_i.real.clone(), 'rope_sin': freqs_i.imag.clone(),
                   'param_grads': {n: fingerprint(p.grad, 600 + i) for i, (n, p) in enumerate(blk.named_parameters())}}
+    # ---- Wan2.2 I2V ('i2v_v2'): the same model with 36 input channels = [x | first-frame mask | y] (wan.py:459-465) ----
+    m2 = M.WanModel(model_type='i2v_v2', in_dim=36, dim=cfg['dim'], ffn_dim=cfg['ffn_dim'], num_heads=cfg['num_heads'],
+                    num_layers=1, text_dim=cfg['text_dim'], text_len=cfg['text_len'])
+    fill_parameters(m2)
+    x2 = synth_tensor((B, 16, f, h, w), 411, 1.0).requires_grad_(True)
+    y2 = synth_tensor((B, 16, f, h, w), 412, 1.0).requires_grad_(True)
+    fmask = torch.zeros((B, 4, f, h, w))
+    fmask[:, :, 0, ...] = 1
+    yy = torch.cat([fmask, y2], dim=1)
+    xs = [torch.cat([u, v], dim=0) for u, v in zip(x2, yy)]
+    xs = [m2.patch_embedding(u.unsqueeze(0)) for u in xs]
+    gs = torch.stack([torch.tensor(u.shape[2:], dtype=torch.long) for u in xs])
+    xs = [u.flatten(2).transpose(1, 2) for u in xs]
+    sl = torch.tensor([u.size(1) for u in xs], dtype=torch.long)
+    xe2 = torch.cat(xs)
+    e_2 = m2.time_embedding(M.sinusoidal_embedding_1d(m2.freq_dim, t).unflatten(0, (B, 1)).to(torch.float32))
+    e0_2 = m2.time_projection(e_2).unflatten(2, (6, m2.dim))
+    ctx2 = m2.text_embedding(torch.stack([torch.cat([u, u.new_zeros(m2.text_len - u.size(0), u.size(1))])
+                                          for u in [emb[:n] for emb, n in zip(text.detach(), text_lens)]]))
+    h2 = m2.blocks[0](xe2, e0_2, sl, gs, m2.freqs, ctx2, None)
+    out2 = torch.stack(m2.unpatchify(m2.head(h2, e_2), gs), dim=0)
+    probe2 = synth_tensor(tuple(out2.shape), 413, 1.0)
+    (out2 * probe2).sum().backward()
+    g['i2v_v2'] = {'x': x2.detach(), 'y': y2.detach(), 'out': out2.detach(), 'probe': probe2, 'dx': x2.grad.clone(),
+                   'dy': y2.grad.clone(),
+                   'param_grads': {n: fingerprint(p.grad, 900 + i) for i, (n, p) in enumerate(m2.named_parameters())}}
     torch.save(g, OUT)
     print('wrote', OUT, os.path.getsize(OUT), 'bytes')
 

@@ -193,3 +193,48 @@ def test_deferred_weight_gradients_do_not_read_boundary_tensors(doubles, family)
     for n in base:
         assert torch.isfinite(deferred[n]).all(), n
         torch.testing.assert_close(deferred[n], base[n], rtol=1e-5, atol=1e-6, msg=n)
+
+
+def make_i2v_pair(device='cpu'):
+    from synth import fill_parameters
+    from diffusion_pipe_b200.wan import WanPipeline
+    from oracle import wan_ref as W
+    cfg = dict(CFG, model_type='i2v_v2', num_layers=1)
+    model = WanPipeline({'model': {'dtype': 'bfloat16', 'device': device, 'transformer_config': cfg}})
+    assert model.transformer.patch_embedding.weight.shape[1] == 36
+    ref = fill_parameters(W.RefWanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=1, text_dim=64, text_len=16, in_dim=36, model_type='i2v_v2'))
+    sd = ref.state_dict()
+    with torch.no_grad():
+        for n, p in model.transformer.named_parameters():
+            p.copy_(sd[n].to(p.dtype))
+    ref.set_emulate_bf16(True)
+    return model, ref
+
+
+def i2v_batch(model):
+    g = torch.Generator().manual_seed(8)
+    batch = {'latents': torch.randn(2, 16, 2, 8, 8, generator=g), 'y': torch.randn(2, 16, 2, 8, 8, generator=g),
+             'text_embeddings': torch.randn(2, 16, 64, generator=g).bfloat16().float(), 'seq_lens': torch.tensor([7, 16]), 'mask': None}
+    torch.manual_seed(3)
+    feats, (target, _) = model.prepare_inputs(batch)
+    assert feats[1] is batch['y']
+    none = torch.tensor([])
+    return tuple(none if f is None else f for f in feats), (target, none)
+
+
+def test_wan22_i2v_forward_backward_matches_oracle(doubles):
+    """model_type 'i2v_v2': first-frame mask + conditioning latents as extra patch-embedding channels (K = 144 GEMM)"""
+    model, ref = make_i2v_pair()
+    feats, label = i2v_batch(model)
+    loss = _run_product(model, feats, label)
+    rloss = _run_oracle(ref, feats, label)
+    assert abs(loss.item() - rloss.item()) / abs(rloss.item()) <= 1e-3, (loss.item(), rloss.item())
+    rg = {n: p.grad for n, p in ref.named_parameters()}
+    for n, p in model.transformer.named_parameters():
+        rel = ((p.grad.float() - rg[n]).norm() / (rg[n].norm() + 1e-12)).item()
+        assert rel <= 5e-2, (n, rel)
+    # a t2v model must not be fed `y`, an i2v_v2 model must be
+    from diffusion_pipe_b200.wan import WanPipeline
+    t2v = WanPipeline({'model': {'dtype': 'bfloat16', 'device': 'cpu', 'transformer_config': dict(CFG, num_layers=1)}})
+    with pytest.raises(NotImplementedError):
+        t2v.to_layers()[0](tuple(f.clone() for f in feats))

@@ -179,9 +179,13 @@ def synthetic_examples(syn):
     if kind == 'wan':
         frames = (syn.get('frames', 33) - 1) // 4 + 1            # VAE temporal stride 4 (models/wan/configs.py:63)
         tl = syn.get('text_len', 512)
-        return [{'latents': torch.randn(16, frames, h, w, generator=g),
-                 'text_embeddings': torch.randn(tl, syn.get('text_dim', 4096), generator=g).bfloat16(),
-                 'seq_lens': torch.tensor(syn.get('prompt_len', tl)), 'mask': None} for _ in range(n)]
+        exs = [{'latents': torch.randn(16, frames, h, w, generator=g),
+                'text_embeddings': torch.randn(tl, syn.get('text_dim', 4096), generator=g).bfloat16(),
+                'seq_lens': torch.tensor(syn.get('prompt_len', tl)), 'mask': None} for _ in range(n)]
+        if syn.get('i2v', False):        # Wan2.2 I2V (model_type 'i2v_v2'): first-frame conditioning latents
+            for ex in exs:
+                ex['y'] = torch.randn(16, frames, h, w, generator=g)
+        return exs
     raise ValueError(f"[synthetic] model = '{kind}': expected one of flux, qwen_image, wan")
 
 
