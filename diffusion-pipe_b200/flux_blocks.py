@@ -386,7 +386,7 @@ class FluxTransformerBlock(nn.Module):
         cos, sin = image_rotary_emb
         if 'lora' in self.__dict__:          # adapters attached (lora.py): frozen base, K-extended GEMMs
             from .lora import FluxDoubleBlockLoraFn
-            h, e = FluxDoubleBlockLoraFn.apply(self, hidden_states, encoder_hidden_states, temb, cos, sin)
+            h, e = FluxDoubleBlockLoraFn.apply(self, hidden_states, encoder_hidden_states, temb, cos, sin, None)
             return e, h
         h, e = FluxDoubleBlockFn.apply(self, hidden_states, encoder_hidden_states, temb, cos, sin, None)
         return e, h

@@ -189,7 +189,7 @@ class FluxDoubleBlockLoraFn(torch.autograd.Function):
     """FluxDoubleBlockFn (flux_blocks.py) with every Linear of the block carrying a LoRA adapter and the base frozen."""
 
     @staticmethod
-    def forward(ctx, blk, hidden, enc, temb, cos, sin):
+    def forward(ctx, blk, hidden, enc, temb, cos, sin, txt_lens=None):
         lo = blk.lora
         B, Li, D = hidden.shape
         Lt = enc.shape[1]
@@ -220,7 +220,13 @@ class FluxDoubleBlockLoraFn(torch.autograd.Function):
         so, sao = lo['to_out'], lo['to_add_out']
         assert so.R == sao.R
         oa = torch.empty((B * Ltot, H * HD + so.R), dtype=bf, device=dev)      # attention output + adapter columns
-        _, lse = ops.attn_fwd(q, k, v, out=oa)
+        if txt_lens is None:
+            _, lse = ops.attn_fwd(q, k, v, out=oa)
+        else:                                  # prompts of different lengths in one micro-batch (flux_blocks._ragged_attn_fwd)
+            from .flux_blocks import _ragged_attn_fwd
+            o_dense, lse = _ragged_attn_fwd(q, k, v, Lt, txt_lens)
+            oa[:, :H * HD].copy_(o_dense)
+        ctx.ragged = txt_lens is not None
         oa3 = oa.view(B, Ltot, H * HD + so.R)
         outs = []
         tail = ((so, lo['ff1'], lo['ff2']), (sao, lo['ffc1'], lo['ffc2']))
@@ -304,7 +310,11 @@ class FluxDoubleBlockLoraFn(torch.autograd.Function):
                 swo.queue_grads(oa3[b, off:off + L], dy1a[rs])
             dmods.append(dmod)
             dx1s.append(dx1)
-        dq, dk, dv = ops.attn_bwd(q, k, v, oa, d_o, lse)
+        if ctx.ragged:
+            from .flux_blocks import _ragged_attn_bwd
+            dq, dk, dv = _ragged_attn_bwd(lse, d_o, q.shape)
+        else:
+            dq, dk, dv = ops.attn_bwd(q, k, v, oa, d_o, lse)
         d_temb = torch.zeros_like(temb, dtype=torch.float32)
         grads = []
         spec = ((lo['mod'], lo['qkv'], blk.attn.norm_q, blk.attn.norm_k), (lo['mod_c'], lo['add_qkv'], blk.attn.norm_added_q, blk.attn.norm_added_k))
@@ -330,7 +340,7 @@ class FluxDoubleBlockLoraFn(torch.autograd.Function):
             grads.append(dx.view(B, L, D))
         ctx.streams = None
         ctx.attn = None
-        return None, grads[0], grads[1], d_temb.to(temb.dtype), None, None
+        return None, grads[0], grads[1], d_temb.to(temb.dtype), None, None, None
 
 
 # =====================================================================================================================

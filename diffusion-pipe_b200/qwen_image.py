@@ -79,10 +79,8 @@ class QwenImageTransformerBlock(nn.Module):
         """txt_lens: None, or the real prompt length of every sample when the micro-batch is padded (key mask)"""
         cos, sin = image_rotary_emb            # joint [text; image] tables, fp32 [L, 128]
         if 'lora' in self.__dict__:
-            if txt_lens is not None:
-                raise NotImplementedError('LoRA with ragged prompts inside one micro-batch: use micro_batch_size_per_gpu = 1')
             from .lora import FluxDoubleBlockLoraFn
-            h, e = FluxDoubleBlockLoraFn.apply(self, hidden_states, encoder_hidden_states, temb, cos, sin)
+            h, e = FluxDoubleBlockLoraFn.apply(self, hidden_states, encoder_hidden_states, temb, cos, sin, txt_lens)
             return e, h
         h, e = FluxDoubleBlockFn.apply(self, hidden_states, encoder_hidden_states, temb, cos, sin, txt_lens)
         return e, h

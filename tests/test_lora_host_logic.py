@@ -89,7 +89,7 @@ def test_adapter_structure_matches_peft_layout(doubles):
     assert sum(".lora_A." in n for n in mine) == 14 + 6
     # default init: B = 0, so the adapted model starts as the base model
     blk = model.transformer.transformer_blocks[0]
-    assert float(blk.attn.to_q.lora_B.weight.abs().max()) == 0.0 and float(blk.attn.to_q.lora_A.weight.abs().max()) > 0
+    assert float(blk.attn.to_q.lora_B.weight.detach().abs().max()) == 0.0 and float(blk.attn.to_q.lora_A.weight.detach().abs().max()) > 0
     # the base weight lives once, inside the site buffer
     site = blk.lora['qkv']
     assert blk.attn.to_k.weight.data_ptr() == site.buf[256:512].data_ptr()
@@ -174,6 +174,40 @@ def test_qwen_lora_forward_backward_matches_oracle(doubles):
     pe = [torch.randn(11, 64, generator=g).bfloat16().float() for _ in range(2)]
     t = torch.sigmoid(torch.randn(2, generator=g))
     feats, (target, _) = Q.prepare_inputs(latents, pe, t, noise)
+    label = (target, torch.tensor([]))
+    loss = _run(model.to_layers(), model.get_loss_fn(), feats, label)
+    rloss = _run(Q.to_layers(ref), R.loss_fn, feats, label)
+    assert abs(loss.item() - rloss.item()) / abs(rloss.item()) <= 1e-3, (loss.item(), rloss.item())
+    rg = {n: p.grad for n, p in ref.named_parameters()}
+    for n, p in model.transformer.named_parameters():
+        if p.requires_grad and rg[n] is not None:
+            rel = ((p.grad.float() - rg[n]).norm() / (rg[n].norm() + 1e-12)).item()
+            assert rel <= 6e-2, (n, rel)
+
+
+def test_qwen_lora_with_ragged_prompts_matches_oracle(doubles):
+    """adapters + the key mask of a padded micro-batch (prompts of 4 and 11 tokens)"""
+    from synth import fill_parameters
+    from diffusion_pipe_b200.qwen_image import QwenImagePipeline
+    from oracle import flux_ref as R
+    from oracle import lora_ref
+    from oracle import qwen_ref as Q
+    cfg = {'num_attention_heads': 2, 'num_layers': 2, 'joint_attention_dim': 64}
+    model = QwenImagePipeline({'model': {'dtype': 'bfloat16', 'device': 'cpu', 'transformer_config': cfg}})
+    ref = fill_parameters(Q.RefQwenImageTransformer(dim=256, heads=2, num_layers=2, joint_dim=64))
+    sd = ref.state_dict()
+    with torch.no_grad():
+        for n, p in model.transformer.named_parameters():
+            p.copy_(sd[n].to(p.dtype))
+    model.configure_adapter({'type': 'lora', 'rank': RANK, 'alpha': RANK, 'dropout': 0.0})
+    lora_ref.add_lora(ref, RANK)
+    ref.set_emulate_bf16(True)
+    _sync_factors(model.transformer, ref, seed=6)
+    g = torch.Generator().manual_seed(6)
+    latents, noise = torch.randn(2, 16, 1, 8, 12, generator=g), torch.randn(2, 16, 1, 8, 12, generator=g)
+    pe = [torch.randn(4, 64, generator=g).bfloat16().float(), torch.randn(11, 64, generator=g).bfloat16().float()]
+    feats, (target, _) = Q.prepare_inputs(latents, pe, torch.sigmoid(torch.randn(2, generator=g)), noise)
+    assert not bool(feats[2].all())
     label = (target, torch.tensor([]))
     loss = _run(model.to_layers(), model.get_loss_fn(), feats, label)
     rloss = _run(Q.to_layers(ref), R.loss_fn, feats, label)
