@@ -16,11 +16,12 @@ QwenEmbedRope(scale_rope=True) and the pipeline layers.
 Two deliberate differences from the reference's tuple contents (both internal to these layers):
   * vid_freqs / txt_freqs travel as real fp32 `[2, tokens, 128]` (cos, sin; every frequency repeated twice) instead
     of complex64 `[tokens, 64]`: the same numbers in the form the fused q/k-norm+RoPE epilogue consumes;
-  * the bool key mask (models/qwen_image.py:472-476) is all-True with micro-batch 1 — the configuration the reference
-    documents and BASELINE.json quotes — because prepare_inputs trims the prompt to its real length.  When prompts of
-    different lengths share a micro-batch, InitialLayer appends their lengths to the tuple (one int32 tensor, last
-    element) and every block attends per sample over its valid rows (flux_blocks._ragged_attn_fwd): same loss and
-    gradients as masking, on the same dense kernels.  Masks with holes inside a prompt raise NotImplementedError.
+  * the bool key mask (models/qwen_image.py:472-476) is not carried into the attention kernel as a mask.  prepare_inputs
+    pads every prompt of a step's batch (micro-batch x GAS examples) to the longest one, so padded prompts are the normal
+    case with real captions; InitialLayer then appends the real lengths to the tuple (one int32 tensor, last element)
+    and every block attends per sample over its valid rows (flux_blocks._ragged_attn_fwd): same loss and gradients as
+    masking, on the same dense kernels.  Equal-length prompts skip all of that.  Masks with holes inside a prompt raise
+    NotImplementedError.
 """
 import json
 import math
@@ -199,6 +200,7 @@ class InitialLayer(nn.Module):
             # `img_seq_len` of the Edit variant is int64), which the block layers read — only in this case
             if not bool((attention_mask.reshape(attention_mask.shape[0], -1)[:, :Lt].int().diff(dim=1) <= 0).all()):
                 raise NotImplementedError('key mask with holes inside the prompt (only trailing padding is supported)')
+            key_lens._dpipe_lens = key_lens.tolist()      # (already synchronised by the check above)
             extra = list(extra) + [key_lens]
         return make_contiguous(hidden_states, encoder_hidden_states, attention_mask, temb, vid_freqs, txt_freqs) + tuple(extra)
 
@@ -213,8 +215,13 @@ class TransformerLayer(nn.Module):
         hidden_states, encoder_hidden_states, attention_mask, temb, vid_freqs, txt_freqs, *extra = inputs
         joint = torch.cat([txt_freqs, vid_freqs], dim=1)           # [2, Lt + Li, 128], order [text, image]
         txt_lens = None
-        if extra and extra[-1].dtype == torch.int32:               # padded prompts (InitialLayer): host read, ragged path
-            txt_lens = extra[-1].tolist()
+        if extra and extra[-1].dtype == torch.int32:               # padded prompts (InitialLayer): ragged path
+            # one host read per micro-batch and stage, not per layer: the same tensor object flows through every layer of
+            # a stage, so the decoded lengths are parked on it
+            kl = extra[-1]
+            txt_lens = getattr(kl, '_dpipe_lens', None)
+            if txt_lens is None:
+                txt_lens = kl._dpipe_lens = kl.tolist()
         encoder_hidden_states, hidden_states = self.block(
             hidden_states=hidden_states, encoder_hidden_states=encoder_hidden_states, temb=temb,
             image_rotary_emb=(joint[0], joint[1]), txt_lens=txt_lens)
