@@ -58,7 +58,7 @@ def _micro_batches(kind, model, n, seed):
     from diffusion_pipe_b200 import data_feed
     g = torch.Generator().manual_seed(seed)
     if kind == 'qwen_image':
-        batch = {'latents': torch.randn(n, 16, 1, 8, 8, generator=g), 'prompt_embeds': [torch.randn(7, 64, generator=g).bfloat16() for _ in range(n)],
+        batch = {'latents': torch.randn(n, 16, 1, 8, 8, generator=g), 'prompt_embeds': [torch.randn(3 + (i * 2) % 5, 64, generator=g).bfloat16() for i in range(n)],      # padded to the longest: key mask
                  'mask': None}
     else:
         batch = {'latents': torch.randn(n, 16, 2, 8, 8, generator=g), 'text_embeddings': torch.randn(n, 16, 64, generator=g).bfloat16(),
