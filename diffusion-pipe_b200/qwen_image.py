@@ -18,9 +18,11 @@ Two deliberate differences from the reference's tuple contents (both internal to
     of complex64 `[tokens, 64]`: the same numbers in the form the fused q/k-norm+RoPE epilogue consumes;
   * the bool key mask (models/qwen_image.py:472-476) is not carried into the attention kernel as a mask.  prepare_inputs
     pads every prompt of a step's batch (micro-batch x GAS examples) to the longest one, so padded prompts are the normal
-    case with real captions; InitialLayer then appends the real lengths to the tuple (one int32 tensor, last element)
-    and every block attends per sample over its valid rows (flux_blocks._ragged_attn_fwd): same loss and gradients as
-    masking, on the same dense kernels.  Equal-length prompts skip all of that.  Masks with holes inside a prompt raise
+    case with real captions; InitialLayer always appends the real lengths to the tuple (one int32 tensor, last element —
+    always, so that every micro-batch of a step has the same tuple structure on the stage links) and, when any prompt
+    is shorter than the padded length, every block attends per sample over its valid rows
+    (flux_blocks._ragged_attn_fwd): same loss and gradients as masking, on the same dense kernels.  Micro-batches whose
+    prompts all fill the padded length take the unmasked path.  Masks with holes inside a prompt raise
     NotImplementedError.
 """
 import json
@@ -194,14 +196,15 @@ class InitialLayer(nn.Module):
         vid_freqs, txt_freqs = qwen_rope_tables([tuple(s) for s in shapes[0]], max(lens), self.axes_dim,
                                                 device=hidden_states.device)
         Lt = encoder_hidden_states.shape[1]
-        key_lens = attention_mask.reshape(attention_mask.shape[0], -1)[:, :Lt].sum(dim=1).to(torch.int32)
-        if int(key_lens.min()) < Lt:
-            # padded prompts: the per-sample prompt lengths travel with the tuple as one extra int32 tensor (LAST element;
-            # `img_seq_len` of the Edit variant is int64), which the block layers read — only in this case
-            if not bool((attention_mask.reshape(attention_mask.shape[0], -1)[:, :Lt].int().diff(dim=1) <= 0).all()):
-                raise NotImplementedError('key mask with holes inside the prompt (only trailing padding is supported)')
-            key_lens._dpipe_lens = key_lens.tolist()      # (already synchronised by the check above)
-            extra = list(extra) + [key_lens]
+        # The per-sample prompt lengths travel with the tuple as one int32 tensor (LAST element; `img_seq_len` of the Edit
+        # variant is int64) — always, so that every micro-batch of a step has the same tuple structure (the one holding
+        # the longest prompt is not padded, the others are).  The block layers read it once per micro-batch and stage.
+        text_mask = attention_mask.reshape(attention_mask.shape[0], -1)[:, :Lt]
+        key_lens = text_mask.sum(dim=1).to(torch.int32)
+        key_lens._dpipe_lens = key_lens.tolist()
+        if min(key_lens._dpipe_lens) < Lt and not bool((text_mask.int().diff(dim=1) <= 0).all()):
+            raise NotImplementedError('key mask with holes inside the prompt (only trailing padding is supported)')
+        extra = list(extra) + [key_lens]
         return make_contiguous(hidden_states, encoder_hidden_states, attention_mask, temb, vid_freqs, txt_freqs) + tuple(extra)
 
 
@@ -215,13 +218,15 @@ class TransformerLayer(nn.Module):
         hidden_states, encoder_hidden_states, attention_mask, temb, vid_freqs, txt_freqs, *extra = inputs
         joint = torch.cat([txt_freqs, vid_freqs], dim=1)           # [2, Lt + Li, 128], order [text, image]
         txt_lens = None
-        if extra and extra[-1].dtype == torch.int32:               # padded prompts (InitialLayer): ragged path
+        if extra and extra[-1].dtype == torch.int32:               # prompt lengths (InitialLayer)
             # one host read per micro-batch and stage, not per layer: the same tensor object flows through every layer of
             # a stage, so the decoded lengths are parked on it
             kl = extra[-1]
-            txt_lens = getattr(kl, '_dpipe_lens', None)
-            if txt_lens is None:
-                txt_lens = kl._dpipe_lens = kl.tolist()
+            lens = getattr(kl, '_dpipe_lens', None)
+            if lens is None:
+                lens = kl._dpipe_lens = kl.tolist()
+            if min(lens) < encoder_hidden_states.shape[1]:         # some prompt is padded: attend per sample over valid rows
+                txt_lens = lens
         encoder_hidden_states, hidden_states = self.block(
             hidden_states=hidden_states, encoder_hidden_states=encoder_hidden_states, temb=temb,
             image_rotary_emb=(joint[0], joint[1]), txt_lens=txt_lens)
