@@ -117,3 +117,5 @@ SIGNATURES['dpipe_mod_bwd_chunks'] = (c_int, [c_int])
 SIGNATURES['dpipe_mod_bwd'] = (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                         c_int, c_int, c_int, c_void_p])
 SIGNATURES['dpipe_mse_loss'] =(c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p])
+SIGNATURES['dpipe_fp8_to_bf16'] = (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p])
+SIGNATURES['dpipe_fp8_code_table'] = (c_int, [c_int, c_void_p])

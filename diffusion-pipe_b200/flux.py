@@ -295,6 +295,23 @@ def latent_image_ids(h2, w2, device=None, dtype=torch.float32):
     return ids.reshape(h2 * w2, 3)
 
 
+def base_storage_dtype(model_config, adapter_configured=True):
+    """`transformer_dtype` of the reference (models/flux.py:172,203-205; utils/common.py:18-20): None when the frozen base
+    stays in the compute dtype, torch.float8_e4m3fn / float8_e5m2 when the 2-D weights of the blocks are stored in fp8 and
+    widened by csrc/fp8_dequant.cu in front of every GEMM that reads them (LoRA runs only: an fp8 base cannot be trained)"""
+    v = model_config.get('transformer_dtype', None)
+    if isinstance(v, str):
+        v = {'bfloat16': torch.bfloat16, 'float8': torch.float8_e4m3fn, 'float8_e4m3fn': torch.float8_e4m3fn,
+             'float8_e5m2': torch.float8_e5m2}.get(v, v)
+    if v is None or v == torch.bfloat16:
+        return None
+    if v not in (torch.float8_e4m3fn, torch.float8_e5m2):
+        raise NotImplementedError(f'transformer_dtype {v!r}: bfloat16, float8 (e4m3fn) and float8_e5m2 are supported')
+    if not adapter_configured:
+        raise NotImplementedError('transformer_dtype float8 needs an [adapter]: a float8 base is frozen storage, not trainable')
+    return v
+
+
 class FluxPipeline:
     """Mirror of the reference FluxPipeline's training-side surface (models/flux.py:153-404)."""
     name = 'flux'
@@ -427,7 +444,7 @@ class FluxPipeline:
             dtype = {'bfloat16': torch.bfloat16, 'float32': torch.float32}[dtype]
         if dtype != torch.bfloat16:
             raise NotImplementedError('adapter dtype must be bfloat16 on the sm_100a path')
-        lora.attach(module, int(self.adapter_config['rank']), dtype)
+        lora.attach(module, int(self.adapter_config['rank']), dtype, base_storage_dtype(self.model_config))
         return module
 
     def save_model(self, save_dir, state_dict):
@@ -503,6 +520,7 @@ class FluxPipeline:
 
     # ---- layers / loss ----
     def to_layers(self):
+        base_storage_dtype(self.model_config, self.adapter_config is not None)
         if self.transformer is None:
             return self._lazy_layers()
         t = self.transformer

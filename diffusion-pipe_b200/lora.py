@@ -19,8 +19,18 @@ The trained factors are ordinary contiguous Parameters (`<linear>.lora_A.weight`
 state-dict names); they are copied into the site buffer when their version counter moves (after an optimizer step).
 The frozen base produces no weight gradient: a LoRA step runs 2/3 of the dense-training FLOPs.
 
-Supported: rank % 8 == 0 (16-byte rows for TMA), dropout 0, Flux double / single blocks and Qwen-Image blocks.
+Supported: rank % 8 == 0 (16-byte rows for TMA), dropout 0, Flux double / single blocks, Qwen-Image and Wan blocks.
 Modulation linears (AdaLayerNormZero.linear, batch-row) get their adapter through a [batch, r] torch matmul.
+
+**fp8 base** (`transformer_dtype = 'float8'` / `'float8_e5m2'`: models/flux.py:172,203-205, models/qwen_image.py:249-263,
+models/wan/wan.py:216-235).  The reference stores the frozen 2-D weights of the blocks as unscaled float8 and lets
+autocast widen them to bf16 inside every nn.Linear.  Here a site then keeps W ONLY as an `[N, K]` fp8 matrix (half the
+bytes of the bf16 buffer; the linears' `.weight` are views of it) plus two small bf16 matrices (stacked A's, block-diagonal
+B's); `w_fwd` / `w_dgrad` expand `[[W | B], [A | .]]` into ONE per-device operand scratch (the size of the largest site)
+with the widening kernel of csrc/fp8_dequant.cu right before the GEMM that reads it — stream order makes the single
+buffer safe, and the weight-gradient closures of the zero-bubble order never read W.  Every fp8 value is a bf16 value, so
+the GEMMs see exactly what the reference's autocast produces.  Cost: 3 bytes of HBM traffic per weight element per GEMM
+(≈6 % of the GEMM's own time at Flux shapes), for half the weight memory.
 """
 import math
 
@@ -43,11 +53,42 @@ def _kaiming_a(r, k, dtype, device):
     return nn.Parameter(w.to(dtype))
 
 
+# ---- fp8 storage of the frozen base (`transformer_dtype = 'float8'`; module docstring, last paragraph) ----------------
+FP8_DTYPES = (torch.float8_e4m3fn, torch.float8_e5m2)
+_SCRATCH = {}        # device -> flat bf16 operand buffer shared by every fp8 site of that device (grown on demand)
+_SCRATCH_OWNER = {}  # device -> key of what the buffer currently holds
+_UIDS = [0]
+_EPOCH = [0]         # bumped at the start of every block forward: the scratch is trusted only within one pass over a block
+
+
+def _uid():
+    _UIDS[0] += 1
+    return _UIDS[0]
+
+
+def _widened(device, key, shape, fill):
+    """bf16 [rows, cols] view of the device's operand scratch holding whatever `fill(view)` writes; the fill is skipped
+    when the scratch still holds `key`.  Everything that reads the view is enqueued on the current stream before the next
+    call can overwrite it, so ONE buffer (the size of the largest site) serves all sites."""
+    n = shape[0] * shape[1]
+    flat = _SCRATCH.get(device)
+    if flat is None or flat.numel() < n:
+        flat = torch.empty(n, dtype=torch.bfloat16, device=device)
+        _SCRATCH[device] = flat
+        _SCRATCH_OWNER.pop(device, None)
+    view = flat[:n].view(shape)
+    if _SCRATCH_OWNER.get(device) != key:
+        with torch.no_grad():
+            fill(view)
+        _SCRATCH_OWNER[device] = key
+    return view
+
+
 class LoraSite:
     """One GEMM site = one or several nn.Linear-like holders (weight [n_i, K], bias) that the kernels consume as one
     [N, K] matrix, plus their LoRA factors.  See the module docstring for the buffer layout."""
 
-    def __init__(self, lins, rank, dtype=torch.bfloat16):
+    def __init__(self, lins, rank, dtype=torch.bfloat16, base_dtype=None):
         if rank % 8:
             raise ValueError(f'LoRA rank must be a multiple of 8 on the sm_100a path (got {rank})')
         self.lins, self.r = list(lins), rank
@@ -57,17 +98,28 @@ class LoraSite:
         self.sizes = [l.weight.shape[0] for l in self.lins]
         self.N = sum(self.sizes)
         self.R = rank * len(self.lins)
-        self.buf = torch.zeros((self.N + self.R, self.K + self.R), dtype=w0.dtype, device=dev)
-        self.bias = torch.zeros(self.N, dtype=w0.dtype, device=dev)
+        self.fp8 = base_dtype in FP8_DTYPES
+        self.uid = _uid()
+        if self.fp8:
+            if self.K % 16:
+                raise ValueError(f'fp8 base storage needs in_features % 16 == 0 (got {self.K})')
+            self.buf = None
+            self.w8 = torch.empty((self.N, self.K), dtype=base_dtype, device=dev)       # the only copy of W
+            self.ab = torch.zeros((self.R, self.K), dtype=torch.bfloat16, device=dev)   # stacked A's
+            self.bb = torch.zeros((self.N, self.R), dtype=torch.bfloat16, device=dev)   # block-diagonal B's
+        else:
+            self.buf = torch.zeros((self.N + self.R, self.K + self.R), dtype=w0.dtype, device=dev)
+        self.bias = torch.zeros(self.N, dtype=torch.bfloat16 if self.fp8 else w0.dtype, device=dev)
         row = 0
         self.A, self.B = [], []
         for i, l in enumerate(self.lins):
             n = self.sizes[i]
-            self.buf[row:row + n, :self.K].copy_(l.weight.detach())
+            base = self.w8[row:row + n] if self.fp8 else self.buf[row:row + n, :self.K]
+            base.copy_(l.weight.detach().to(base.dtype))
             if l.bias is not None:
                 self.bias[row:row + n].copy_(l.bias.detach())
             # the base parameters now live inside the site buffer (frozen): checkpoints load straight into it
-            l.weight.data = self.buf[row:row + n, :self.K]
+            l.weight.data = base
             l.weight.requires_grad_(False)
             if l.bias is not None:
                 l.bias.data = self.bias[row:row + n]
@@ -82,33 +134,53 @@ class LoraSite:
         self.refresh()
 
     # ---- operand views -------------------------------------------------------------------------------------------
+    def _operand(self):
+        """[(N + R) x (K + R)] bf16 `[[W | B], [A | .]]`: the site's own buffer, or (fp8 base) the device's operand scratch
+        with W widened into it by the dequant kernel (csrc/fp8_dequant.cu) — re-expanded unless this site was the last
+        user of the scratch within the same pass (per-sample loops over one site)"""
+        if not self.fp8:
+            return self.buf
+
+        def fill(view):
+            ops.fp8_to_bf16(self.w8, view[:self.N, :self.K])
+            view[self.N:, :self.K].copy_(self.ab)
+            view[:self.N, self.K:].copy_(self.bb)
+        return _widened(self.w8.device, (self.uid, self._versions, _EPOCH[0]), (self.N + self.R, self.K + self.R), fill)
+
+    @property
+    def base_weight(self):  # [N, K] storage of the frozen W (bf16 view of the site buffer, or the fp8 matrix)
+        return self.w8 if self.fp8 else self.buf[:self.N, :self.K]
+
     @property
     def w_fwd(self):        # [N, K + R]   ([W | B]),  K-major B operand of the forward GEMM
-        return self.buf[:self.N]
+        return self._operand()[:self.N]
 
     @property
     def w_dgrad(self):      # [N + R, K]   ([W ; A]),  MN-major (b_mn) operand of the input-gradient GEMM
-        return self.buf[:, :self.K]
+        return self._operand()[:, :self.K]
 
     @property
     def a_all(self):        # [R, K]       stacked A's
-        return self.buf[self.N:, :self.K]
+        return self.ab if self.fp8 else self.buf[self.N:, :self.K]
 
     @property
     def b_blk(self):        # [N, R]       block-diagonal B's
-        return self.buf[:self.N, self.K:]
+        return self.bb if self.fp8 else self.buf[:self.N, self.K:]
 
     def refresh(self):
         """copies the trained factors into the site buffer if an optimizer step (or a load) changed them"""
+        if self.fp8:
+            _EPOCH[0] += 1      # (called at the start of every block forward) W may have been reloaded since the last pass
         v = tuple(p._version for p in self.A + self.B)
         if v == self._versions:
             return
         row = 0
+        a_dst, b_dst = self.a_all, self.b_blk
         with torch.no_grad():
             for i, (a, b) in enumerate(zip(self.A, self.B)):
                 n = self.sizes[i]
-                self.buf[self.N + i * self.r:self.N + (i + 1) * self.r, :self.K].copy_(a)
-                self.buf[row:row + n, self.K + i * self.r:self.K + (i + 1) * self.r].copy_(b)
+                a_dst[i * self.r:(i + 1) * self.r].copy_(a)
+                b_dst[row:row + n, i * self.r:(i + 1) * self.r].copy_(b)
                 row += n
         self._versions = tuple(p._version for p in self.A + self.B)
 
@@ -145,30 +217,54 @@ class LoraSite:
         ops.defer(wgrad)
 
 
+class _WidenedLin:
+    """what _mod_fwd / _mod_bwd read of a frozen linear: its (widened) weight and its bias"""
+    __slots__ = ('weight', 'bias')
+
+    def __init__(self, weight, bias):
+        self.weight, self.bias = weight, bias
+
+
 class ModLora:
     """adapter of a batch-row modulation linear (AdaLayerNormZero.linear): mod += (silu(temb) A^T) B^T on [batch, r]"""
 
-    def __init__(self, lin, rank, dtype=torch.bfloat16):
+    def __init__(self, lin, rank, dtype=torch.bfloat16, base_dtype=None):
         self.lin = lin
         dev = lin.weight.device
         lin.weight.requires_grad_(False)
         if lin.bias is not None:
             lin.bias.requires_grad_(False)
+        self.fp8 = base_dtype in FP8_DTYPES
+        self.uid = _uid()
+        if self.fp8:
+            if lin.weight.shape[1] % 16:
+                raise ValueError(f'fp8 base storage needs in_features % 16 == 0 (got {lin.weight.shape[1]})')
+            lin.weight.data = lin.weight.detach().to(base_dtype)
         self.a = _kaiming_a(rank, lin.weight.shape[1], dtype, dev)
         self.b = nn.Parameter(torch.zeros(lin.weight.shape[0], rank, dtype=dtype, device=dev))
         lin.lora_A, lin.lora_B = _LoraW(self.a), _LoraW(self.b)
 
+    def _base(self):
+        """the linear as the modulation kernels read it: itself, or (fp8 base) its weight widened into the operand scratch"""
+        if not self.fp8:
+            return self.lin
+        w8 = self.lin.weight.detach()
+        w = _widened(w8.device, (self.uid, _EPOCH[0]), tuple(w8.shape), lambda view: ops.fp8_to_bf16(w8, view))
+        return _WidenedLin(w, self.lin.bias)
+
     def fwd(self, temb):
+        if self.fp8:
+            _EPOCH[0] += 1
         s = torch.nn.functional.silu(temb.float()).to(torch.bfloat16)
         t = (s.float() @ self.a.float().t()).to(torch.bfloat16)                    # lora_A output (bf16)
-        mod = _mod_fwd(temb, self.lin)
+        mod = _mod_fwd(temb, self._base())
         return (mod.float() + (t.float() @ self.b.float().t()).to(torch.bfloat16).float()).to(torch.bfloat16), (s, t)
 
     def bwd(self, dmod32, temb, saved, d_temb32):
         """accumulates d temb (fp32) and the factor gradients"""
         s, t = saved
         d = dmod32.to(torch.bfloat16).float()
-        _mod_bwd(dmod32, temb, self.lin, d_temb32)                                # frozen base: only the d temb part
+        _mod_bwd(dmod32, temb, self._base(), d_temb32)                            # frozen base: only the d temb part
         dt = d @ self.b.float()
         _acc_vec(self.b, d.t() @ t.float())
         _acc_vec(self.a, dt.t() @ s.float())
@@ -455,57 +551,59 @@ def _name_factors(blk):
             p.original_name = prefix + n
 
 
-def attach(module, rank, dtype=torch.bfloat16):
-    """attaches adapters to every supported block found under `module`; returns the number of blocks adapted"""
+def attach(module, rank, dtype=torch.bfloat16, base_dtype=None):
+    """attaches adapters to every supported block found under `module`; returns the number of blocks adapted.
+    base_dtype = torch.float8_e4m3fn / float8_e5m2 stores the frozen 2-D weights of the blocks in fp8 (the reference's
+    `transformer_dtype`); None keeps them in the compute dtype."""
     n = 0
     for m in module.modules():
         if 'lora' in m.__dict__:
             continue
         cls = type(m).__name__
         if cls in ('FluxTransformerBlock', 'QwenImageTransformerBlock'):
-            attach_double_block(m, rank, dtype)
+            attach_double_block(m, rank, dtype, base_dtype)
             n += 1
         elif cls == 'FluxSingleTransformerBlock':
-            attach_single_block(m, rank, dtype)
+            attach_single_block(m, rank, dtype, base_dtype)
             n += 1
         elif cls == 'WanAttentionBlock':
-            attach_wan_block(m, rank, dtype)
+            attach_wan_block(m, rank, dtype, base_dtype)
             n += 1
     return n
 
 
-def attach_double_block(blk, rank, dtype=torch.bfloat16):
+def attach_double_block(blk, rank, dtype=torch.bfloat16, base_dtype=None):
     """every nn.Linear of a FluxTransformerBlock / QwenImageTransformerBlock gets an adapter (models/base.py:263-271)"""
     a = blk.attn
     lo = {
-        'mod': ModLora(blk.norm1.linear, rank, dtype), 'mod_c': ModLora(blk.norm1_context.linear, rank, dtype),
-        'qkv': LoraSite([a.to_q, a.to_k, a.to_v], rank, dtype),
-        'add_qkv': LoraSite([a.add_q_proj, a.add_k_proj, a.add_v_proj], rank, dtype),
-        'to_out': LoraSite([a.to_out[0]], rank, dtype), 'to_add_out': LoraSite([a.to_add_out], rank, dtype),
-        'ff1': LoraSite([blk.ff.net[0].proj], rank, dtype), 'ff2': LoraSite([blk.ff.net[2]], rank, dtype),
-        'ffc1': LoraSite([blk.ff_context.net[0].proj], rank, dtype), 'ffc2': LoraSite([blk.ff_context.net[2]], rank, dtype),
+        'mod': ModLora(blk.norm1.linear, rank, dtype, base_dtype), 'mod_c': ModLora(blk.norm1_context.linear, rank, dtype, base_dtype),
+        'qkv': LoraSite([a.to_q, a.to_k, a.to_v], rank, dtype, base_dtype),
+        'add_qkv': LoraSite([a.add_q_proj, a.add_k_proj, a.add_v_proj], rank, dtype, base_dtype),
+        'to_out': LoraSite([a.to_out[0]], rank, dtype, base_dtype), 'to_add_out': LoraSite([a.to_add_out], rank, dtype, base_dtype),
+        'ff1': LoraSite([blk.ff.net[0].proj], rank, dtype, base_dtype), 'ff2': LoraSite([blk.ff.net[2]], rank, dtype, base_dtype),
+        'ffc1': LoraSite([blk.ff_context.net[0].proj], rank, dtype, base_dtype), 'ffc2': LoraSite([blk.ff_context.net[2]], rank, dtype, base_dtype),
     }
     lo['sites'] = [v for v in lo.values() if isinstance(v, LoraSite)]
     for n in (a.norm_q, a.norm_k, a.norm_added_q, a.norm_added_k):
         n.weight.requires_grad_(False)                       # bias='none', no modules_to_save: only the factors train
     for fp, site in ((blk.qkv, lo['qkv']), (blk.add_qkv, lo['add_qkv'])):
-        fp.weight, fp.bias = site.buf[:site.N, :site.K], site.bias   # drop the old fused storage (the site buffer owns W now)
+        fp.weight, fp.bias = site.base_weight, site.bias   # drop the old fused storage (the site owns W now)
     blk.__dict__['lora'] = lo
     _name_factors(blk)
     return lo
 
 
-def attach_single_block(blk, rank, dtype=torch.bfloat16):
+def attach_single_block(blk, rank, dtype=torch.bfloat16, base_dtype=None):
     a = blk.attn
     lo = {
-        'mod': ModLora(blk.norm.linear, rank, dtype),
-        'lin1': LoraSite([a.to_q, a.to_k, a.to_v, blk.proj_mlp], rank, dtype),
-        'proj_out': LoraSite([blk.proj_out], rank, dtype),
+        'mod': ModLora(blk.norm.linear, rank, dtype, base_dtype),
+        'lin1': LoraSite([a.to_q, a.to_k, a.to_v, blk.proj_mlp], rank, dtype, base_dtype),
+        'proj_out': LoraSite([blk.proj_out], rank, dtype, base_dtype),
     }
     lo['sites'] = [v for v in lo.values() if isinstance(v, LoraSite)]
     for n in (a.norm_q, a.norm_k):
         n.weight.requires_grad_(False)
-    blk.lin1.weight, blk.lin1.bias = lo['lin1'].buf[:lo['lin1'].N, :lo['lin1'].K], lo['lin1'].bias
+    blk.lin1.weight, blk.lin1.bias = lo['lin1'].base_weight, lo['lin1'].bias
     blk.__dict__['lora'] = lo
     _name_factors(blk)
     return lo
@@ -682,18 +780,18 @@ class WanBlockLoraFn(torch.autograd.Function):
         return (None, dx.view(B, L, D).to(xdt), dmod.view(B, 1, 6, D).to(edt), d_ctx.view(B, Lc, D).to(cdt), None, None)
 
 
-def attach_wan_block(blk, rank, dtype=torch.bfloat16):
+def attach_wan_block(blk, rank, dtype=torch.bfloat16, base_dtype=None):
     sa, ca = blk.self_attn, blk.cross_attn
     lo = {
-        'sa_qkv': LoraSite([sa.q, sa.k, sa.v], rank, dtype), 'sa_o': LoraSite([sa.o], rank, dtype),
-        'ca_q': LoraSite([ca.q], rank, dtype), 'ca_kv': LoraSite([ca.k, ca.v], rank, dtype), 'ca_o': LoraSite([ca.o], rank, dtype),
-        'ffn1': LoraSite([blk.ffn[0]], rank, dtype), 'ffn2': LoraSite([blk.ffn[2]], rank, dtype),
+        'sa_qkv': LoraSite([sa.q, sa.k, sa.v], rank, dtype, base_dtype), 'sa_o': LoraSite([sa.o], rank, dtype, base_dtype),
+        'ca_q': LoraSite([ca.q], rank, dtype, base_dtype), 'ca_kv': LoraSite([ca.k, ca.v], rank, dtype, base_dtype), 'ca_o': LoraSite([ca.o], rank, dtype, base_dtype),
+        'ffn1': LoraSite([blk.ffn[0]], rank, dtype, base_dtype), 'ffn2': LoraSite([blk.ffn[2]], rank, dtype, base_dtype),
     }
     lo['sites'] = [v for v in lo.values() if isinstance(v, LoraSite)]
     for p in (sa.norm_q.weight, sa.norm_k.weight, ca.norm_q.weight, ca.norm_k.weight, blk.norm3.weight, blk.norm3.bias, blk.modulation):
         p.requires_grad_(False)
-    sa.qkv.weight, sa.qkv.bias = lo['sa_qkv'].buf[:lo['sa_qkv'].N, :lo['sa_qkv'].K], lo['sa_qkv'].bias
-    ca.kv.weight, ca.kv.bias = lo['ca_kv'].buf[:lo['ca_kv'].N, :lo['ca_kv'].K], lo['ca_kv'].bias
+    sa.qkv.weight, sa.qkv.bias = lo['sa_qkv'].base_weight, lo['sa_qkv'].bias
+    ca.kv.weight, ca.kv.bias = lo['ca_kv'].base_weight, lo['ca_kv'].bias
     blk.__dict__['lora'] = lo
     _name_factors(blk)
     return lo

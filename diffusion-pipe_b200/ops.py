@@ -325,6 +325,27 @@ def colsum(x, out=None):
     return out
 
 
+FP8_FORMATS = {torch.float8_e4m3fn: 0, torch.float8_e5m2: 1}      # DPIPE_FP8_E4M3 / DPIPE_FP8_E5M2
+
+
+def fp8_to_bf16(src, dst):
+    """dst (bf16 [rows, cols] view, last dimension contiguous) = widen(src) for a 2-D fp8 matrix (float8_e4m3fn or
+    float8_e5m2; exact).  The frozen base of a LoRA run stored in fp8 is expanded into a GEMM operand buffer with this
+    before each GEMM that reads it (reference: autocast widens the float8 weight inside nn.Linear)."""
+    global LAUNCHES
+    if src.dtype not in FP8_FORMATS or not src.is_cuda or src.dim() != 2 or src.stride(1) != 1:
+        raise TypeError(f'src must be a 2-D CUDA float8 tensor with a contiguous last dimension, got {src.dtype} {tuple(src.shape)}')
+    _req_bf16(dst, 'dst')
+    if dst.dim() != 2 or tuple(dst.shape) != tuple(src.shape):
+        raise ValueError(f'dst {tuple(dst.shape)} must have the shape of src {tuple(src.shape)}')
+    _e = _prof_begin()
+    check(lib().dpipe_fp8_to_bf16(_ptr(src), src.stride(0), _ptr(dst), dst.stride(0), src.shape[0], src.shape[1],
+                                  FP8_FORMATS[src.dtype], _stream()), 'dpipe_fp8_to_bf16')
+    _prof_end(_e, 0.0, 'fp8_widen')
+    LAUNCHES += 1
+    return dst
+
+
 def qknorm_rope_bwd(dq, dk, dv, qhat, khat, q_rstd, k_rstd, q_norm_w, k_norm_w, rope_cos, rope_sin, dqkv, dbias, dw,
                     batch, heads, seq_total, seq_offset, rows_per_batch):
     """Backward of the QKV_ROPE epilogue for one stream: writes token-major dqkv [batch*rows, 3*H*128] and

@@ -684,6 +684,8 @@ class WanPipeline:
 
     # ---- layers / loss ----
     def to_layers(self):
+        from .flux import base_storage_dtype
+        base_storage_dtype(self.model_config, self.adapter_config is not None)    # float8 base: LoRA runs only
         if self.transformer is None:
             return self._lazy_layers()
         m = self.transformer

@@ -281,6 +281,20 @@ long long dpipe_sched_zb_makespan_ex(int micro_batches, int stages, int tf, int 
 int dpipe_partition_balanced(const int64_t* weights, int n, int parts, int* bounds);
 
 /* ------------------------------------------------------------------------------------------ */
+/* fp8 storage of a frozen base (LoRA runs with `transformer_dtype = 'float8'`).                  */
+/* replaces: autocast widening the float8 weight to bf16 inside every nn.Linear of the blocks      */
+/*           (models/flux.py:172,203-205; models/qwen_image.py:249-262; utils/common.py:18-20).    */
+/* ------------------------------------------------------------------------------------------ */
+#define DPIPE_FP8_E4M3 0 /* torch.float8_e4m3fn */
+#define DPIPE_FP8_E5M2 1 /* torch.float8_e5m2 */
+/* dst[r*ld_dst + c] (bf16) = widen(src[r*ld_src + c]) for a rows x cols matrix of fp8 codes (exact: every fp8 value is a
+ * bf16 value).  cols and ld_src multiples of 16, ld_dst a multiple of 8, both pointers 16-byte aligned. */
+int dpipe_fp8_to_bf16(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int64_t cols, int format,
+                      void* stream);
+/* the 256 bf16 bit patterns the kernel maps the fp8 codes to (host function; used by the CPU-side table test) */
+int dpipe_fp8_code_table(int format, uint16_t* bf16_bits_256);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Stage-boundary transport: CUDA-IPC mailboxes, peer copies over NVLink, device-side flags.     */
 /* replaces: DeepSpeed _exec_send/recv_activations/_grads over NCCL p2p, as emitted by the       */
 /*           schedule at utils/patches.py:134-143.                             */

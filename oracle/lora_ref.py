@@ -68,3 +68,36 @@ def add_lora(model, rank):
         if type(m).__name__ in TARGET_BLOCKS:
             visit(m)
     return wrapped
+
+
+# ---- `transformer_dtype = 'float8'`: which weights the reference stores in fp8, restated per family ----------------------
+# The reference casts the stored tensor (`p.data = p.data.to(transformer_dtype)`) and autocast widens it back to bf16
+# inside nn.Linear, so the arithmetic sees W rounded to the nearest fp8 value.
+FP8_RULES = {
+    # models/flux.py:79,203-205
+    'flux': lambda name, p: not (any(k in name for k in ('time_text_embed', 'context_embedder', 'x_embedder'))
+                                 or name.startswith('proj_out') or name.startswith('norm_out') or p.ndim == 1),
+    # models/qwen_image.py:23,261-263
+    'qwen_image': lambda name, p: not (any(k in name for k in ('time_text_embed', 'img_in', 'txt_in', 'norm_out', 'proj_out'))
+                                       or p.ndim == 1),
+    # models/wan/wan.py:25,233-235
+    'wan': lambda name, p: not any(k in name for k in ('norm', 'bias', 'patch_embedding', 'text_embedding', 'time_embedding',
+                                                       'time_projection', 'head', 'modulation')),
+}
+
+
+def fp8_stored_names(model, family):
+    """names of the parameters the reference would hold in fp8 (adapter factors are created afterwards in the adapter
+    dtype: utils/patches.py:61-69 keeps them out of float8)"""
+    rule = FP8_RULES[family]
+    return {n for n, p in model.named_parameters() if '.lora_A.' not in n and '.lora_B.' not in n and rule(n, p)}
+
+
+def round_base_through_fp8(model, family, fp8_dtype=torch.float8_e4m3fn):
+    """W <- widen(fp8(W)) for every parameter of fp8_stored_names: what the reference computes with under transformer_dtype"""
+    names = fp8_stored_names(model, family)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n in names:
+                p.copy_(p.to(fp8_dtype).to(p.dtype))
+    return names

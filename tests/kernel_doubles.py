@@ -300,9 +300,16 @@ def mse_loss(out, target, mask=None, want_grad=True):
     return loss, dout
 
 
+def fp8_to_bf16(src, dst):
+    assert src.dtype in (torch.float8_e4m3fn, torch.float8_e5m2) and dst.dtype == torch.bfloat16
+    assert src.dim() == 2 and tuple(src.shape) == tuple(dst.shape) and src.shape[1] % 16 == 0 and dst.stride(0) % 8 == 0
+    dst.copy_(src.to(torch.bfloat16))
+    return dst
+
+
 def install(monkeypatch, ops):
     """replaces the kernel wrappers of `ops` (diffusion_pipe_b200.ops) by the doubles above"""
     for name in ('gemm', 'make_qkv_epilogue', 'qknorm_rope_bwd', 'attn_fwd', 'attn_bwd', 'nchunks', 'ln_modulate_fwd',
                  'ln_modulate_bwd', 'gate_bwd', 'colreduce_finish', 'colsum', 'wan_norm_rope_fwd', 'wan_norm_rope_bwd', 'mod_fwd',
-                 'mod_bwd', 'mse_loss'):
+                 'mod_bwd', 'mse_loss', 'fp8_to_bf16'):
         monkeypatch.setattr(ops, name, globals()[name])

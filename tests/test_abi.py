@@ -89,3 +89,27 @@ def test_new_entry_points_validate_their_arguments_without_a_gpu():
     # the batch-row modulation backward refuses what its register budget cannot hold
     assert lib.dpipe_mod_bwd(buf, 0, buf, buf, buf, 0, buf, buf, buf, 8, 1024, 5120, None) < 0
     assert b'not supported' in lib.dpipe_last_error()
+
+
+def test_fp8_code_tables_are_torchs_widening_for_all_256_codes():
+    """dpipe_fp8_code_table returns the table csrc/fp8_dequant.cu builds in shared memory: every float8_e4m3fn /
+    float8_e5m2 code must widen to the bf16 value torch's own cast gives (the reference's autocast widening)"""
+    import torch
+    lib = _lib.lib()
+    for fmt, dt in ((0, torch.float8_e4m3fn), (1, torch.float8_e5m2)):
+        out = (ctypes.c_uint16 * 256)()
+        assert lib.dpipe_fp8_code_table(fmt, out) == 0
+        got = torch.tensor(list(out), dtype=torch.int32).to(torch.int16).view(torch.bfloat16)
+        want = torch.arange(256, dtype=torch.uint8).view(dt).to(torch.bfloat16)
+        nan = torch.isnan(want.float())
+        assert torch.equal(torch.isnan(got.float()), nan)
+        assert torch.equal(got.view(torch.int16)[~nan], want.view(torch.int16)[~nan])
+        assert int(nan.sum()) == (2 if fmt == 0 else 6)
+    assert lib.dpipe_fp8_code_table(2, out) < 0 and lib.dpipe_fp8_code_table(0, None) < 0
+    # shape / alignment rules of the kernel entry point are checked before any CUDA call
+    buf = ctypes.c_void_p(256)
+    assert lib.dpipe_fp8_to_bf16(buf, 64, buf, 64, 4, 60, 0, None) < 0 and b'multiples of 16' in lib.dpipe_last_error()
+    assert lib.dpipe_fp8_to_bf16(buf, 64, buf, 60, 4, 64, 0, None) < 0
+    assert lib.dpipe_fp8_to_bf16(ctypes.c_void_p(8), 64, buf, 64, 4, 64, 0, None) < 0 and b'aligned' in lib.dpipe_last_error()
+    assert lib.dpipe_fp8_to_bf16(buf, 64, buf, 64, 4, 64, 7, None) < 0
+    assert lib.dpipe_fp8_to_bf16(buf, 64, buf, 64, 0, 64, 0, None) == 0          # empty matrix: nothing to do

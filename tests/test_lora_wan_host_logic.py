@@ -21,12 +21,15 @@ def doubles(monkeypatch):
     return ops
 
 
-def make_pair(device='cpu'):
+def make_pair(device='cpu', transformer_dtype=None):
     from synth import fill_parameters
     from diffusion_pipe_b200.wan import WanPipeline
     from oracle import lora_ref
     from oracle import wan_ref as W
-    model = WanPipeline({'model': {'dtype': 'bfloat16', 'device': device, 'transformer_config': CFG}})
+    mc = {'dtype': 'bfloat16', 'device': device, 'transformer_config': CFG}
+    if transformer_dtype:
+        mc['transformer_dtype'] = transformer_dtype
+    model = WanPipeline({'model': mc})
     ref = fill_parameters(W.RefWanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, text_len=16))
     sd = ref.state_dict()
     with torch.no_grad():

@@ -96,7 +96,7 @@ def main():
     split, per_stage = block_split(n_blocks, stages)
     pm = ManualPipelineModule(layers=model.to_layers(), num_stages=stages, partition_method='manual' if stages > 1 else 'uniform',
                               manual_partition_split=split if stages > 1 else None, loss_fn=model.get_loss_fn(), dynamic_shape=True)
-    schedule = ('zb' if stages > 1 else '1f1b') if a.schedule == 'auto' else a.schedule
+    schedule = ('zb' if stages > 2 else '1f1b') if a.schedule == 'auto' else a.schedule
     engine, _, _, _ = initialize(model=pm, config={'train_micro_batch_size_per_gpu': 1, 'gradient_accumulation_steps': M,
                                                    'gradient_clipping': 1.0, 'steps_per_print': 0, 'pipeline_schedule': schedule,
                                                    'zb_stage_weights': [max(1, b) for b in per_stage]})
