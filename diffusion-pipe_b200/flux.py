@@ -12,6 +12,7 @@ VAE / text encoders / latent caching are outside the hot path (SURVEY.md section
 import json
 import math
 import os
+import re
 
 import torch
 from torch import nn
@@ -445,7 +446,41 @@ class FluxPipeline:
         if dtype != torch.bfloat16:
             raise NotImplementedError('adapter dtype must be bfloat16 on the sm_100a path')
         lora.attach(module, int(self.adapter_config['rank']), dtype, base_storage_dtype(self.model_config))
+        if getattr(self, '_adapter_init', None) is not None:
+            FluxPipeline._load_factors(module, self._adapter_init)
         return module
+
+    def load_adapter_weights(self, adapter_path):
+        """models/base.py:367-388 (train.py:534-535, `[adapter] init_from_existing`): start the factors from a saved
+        adapter — the single *.safetensors file in `adapter_path`, keys optionally prefixed `transformer.` /
+        `diffusion_model.`; a key that names no parameter of the model raises.  With lazily built layers the file is
+        read once and every stage fills the blocks it builds."""
+        from safetensors.torch import load_file
+        files = sorted(f for f in os.listdir(adapter_path) if f.endswith('.safetensors'))
+        if len(files) == 0:
+            raise RuntimeError(f'No safetensors file found in {adapter_path}')
+        if len(files) > 1:
+            raise RuntimeError(f'Multiple safetensors files found in {adapter_path}')
+        state = {re.sub(r'^(transformer|diffusion_model)\.', '', k): v
+                 for k, v in load_file(os.path.join(adapter_path, files[0])).items()}
+        self._adapter_init = state
+        if self.transformer is not None:
+            names = {n for n, _ in self.transformer.named_parameters()}
+            for k in state:
+                if k not in names:
+                    raise RuntimeError(f'adapter key {k} is not in the model parameters')
+            FluxPipeline._load_factors(self.transformer, state)
+
+    @staticmethod
+    def _load_factors(module, state):
+        with torch.no_grad():
+            for n, p in module.named_parameters():
+                if '.lora_A.' in n or '.lora_B.' in n:
+                    key = getattr(p, 'original_name', n)
+                    if key in state:
+                        if tuple(state[key].shape) != tuple(p.shape):
+                            raise RuntimeError(f'adapter key {key}: shape {tuple(state[key].shape)} does not match {tuple(p.shape)}')
+                        p.copy_(state[key].to(p.dtype))
 
     def save_model(self, save_dir, state_dict):
         """full-model export in the diffusers layout this engine trains in (the reference re-lays Flux out to BFL names

@@ -643,6 +643,11 @@ class WanPipeline:
         from .flux import FluxPipeline
         return FluxPipeline._adapt(self, module, dev)
 
+    def load_adapter_weights(self, adapter_path):
+        """models/base.py:367-388 (`[adapter] init_from_existing`)"""
+        from .flux import FluxPipeline
+        FluxPipeline.load_adapter_weights(self, adapter_path)
+
     def save_adapter(self, save_dir, peft_state_dict):
         """models/wan/wan.py:258-262 (ComfyUI format: keys prefixed with diffusion_model.)"""
         from .flux import FluxPipeline

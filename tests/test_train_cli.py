@@ -177,3 +177,9 @@ betas = [0.9, 0.99]
     assert T.main(['--config', str(cfgp), '--resume_from_checkpoint']) == run_dir4
     lines = [json.loads(l) for l in open(os.path.join(run_dir4, 'metrics.jsonl'))]
     assert [l['x'] for l in lines if l['tag'] == 'train/loss'] == [1, 2, 3]
+    # ... and a new run can start from a saved adapter ([adapter] init_from_existing, train.py:534-535)
+    cfgp = write_cfg(1, f"[adapter]\ntype = 'lora'\nrank = 16\ninit_from_existing = '{run_dir4}/step3'\n")
+    (tmp_path / 'runs4').mkdir()
+    cfgp.write_text(cfgp.read_text().replace(f"{tmp_path}/runs'", f"{tmp_path}/runs4'"))
+    run_dir5 = T.main(['--config', str(cfgp)])
+    assert os.path.exists(os.path.join(run_dir5, 'step1', 'adapter_model.safetensors'))

@@ -298,6 +298,8 @@ def main(argv=None):
             raise NotImplementedError(f"[adapter] is not available for model type '{config['model']['type']}' yet")
         model.configure_adapter(adapter_config)
         is_adapter = True
+        if init_from_existing := adapter_config.get('init_from_existing', None):     # train.py:534-535
+            model.load_adapter_weights(init_from_existing)
 
     dataset_config = load_toml(config['dataset'])
     ds_config, micro_batch_size_per_gpu = make_ds_config(config)
