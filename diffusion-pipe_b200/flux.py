@@ -401,21 +401,58 @@ class FluxPipeline:
         return layers
 
     # ---- weights ----
-    def load_transformer_weights(self, path):
-        """Loads a diffusers-layout state dict (directory of *.safetensors or a single file)."""
-        from safetensors.torch import load_file
+    @staticmethod
+    def _weight_index(path):
+        """{parameter name: (file, key in file)} over a *.safetensors file or a directory of shards (diffusers / reference
+        parameter names; ComfyUI checkpoints carry `model.diffusion_model.` in front, models/wan/wan.py:43-46).  Only the
+        headers are read here; tensors are fetched one by one when a layer asks for them."""
+        from safetensors import safe_open
         files = [path] if os.path.isfile(path) else sorted(
             os.path.join(path, f) for f in os.listdir(path) if f.endswith('.safetensors'))
-        params = dict(self.transformer.named_parameters())
-        seen = set()
+        if not files:
+            raise RuntimeError(f'no *.safetensors under {path}')
+        index = {}
         for f in files:
-            for k, v in load_file(f).items():
-                if k in params:
-                    params[k].data.copy_(v)
-                    seen.add(k)
-        missing = set(params) - seen
+            with safe_open(f, framework='pt') as h:
+                for k in h.keys():
+                    index[re.sub(r'^model\.diffusion_model\.', '', k)] = (f, k)
+        return index
+
+    @staticmethod
+    def _copy_weights(index, named_params, what):
+        """fills every (name, parameter) from the checkpoint; a parameter the checkpoint does not have raises"""
+        from safetensors import safe_open
+        by_file, missing = {}, []
+        for name, p in named_params:
+            if name in index:
+                by_file.setdefault(index[name][0], []).append((index[name][1], name, p))
+            else:
+                missing.append(name)
         if missing:
-            raise RuntimeError(f'{len(missing)} parameters missing from {path}, e.g. {sorted(missing)[:3]}')
+            raise RuntimeError(f'{len(missing)} parameters of {what} missing from the checkpoint, e.g. {sorted(missing)[:3]}')
+        with torch.no_grad():
+            for f, items in by_file.items():
+                with safe_open(f, framework='pt') as h:
+                    for key, name, p in items:
+                        v = h.get_tensor(key)
+                        if tuple(v.shape) != tuple(p.shape):
+                            raise RuntimeError(f'{name}: checkpoint shape {tuple(v.shape)} != parameter shape {tuple(p.shape)}')
+                        p.copy_(v)
+
+    def load_transformer_weights(self, path):
+        """Loads a checkpoint in the reference's parameter names into the whole (eagerly built) transformer."""
+        FluxPipeline._copy_weights(FluxPipeline._weight_index(path), list(self.transformer.named_parameters()), 'the transformer')
+
+    def _load_stage_weights(self, module):
+        """lazily built layers (`lazy_layers`): each rank reads exactly the tensors of the layers it materialises, by
+        `original_name` — nothing when no `transformer_path` is configured (synthetic / benchmark runs)"""
+        path = self.model_config.get('transformer_path', None)
+        if not path:
+            return
+        if getattr(self, '_windex', None) is None:
+            self._windex = FluxPipeline._weight_index(path)
+        FluxPipeline._copy_weights(self._windex, [(getattr(p, 'original_name', n), p) for n, p in module.named_parameters()],
+                                   type(module).__name__)
 
     def load_diffusion_model(self):
         pass
@@ -435,7 +472,11 @@ class FluxPipeline:
     def _adapt(self, module, dev):
         """freezes `module` and attaches the configured adapters to the blocks inside it (no-op without an adapter or on
         the meta device used for parameter counting)"""
-        if self.adapter_config is None or dev == 'meta':
+        if dev == 'meta':
+            return module
+        if self.transformer is None:                       # lazy_layers: this is where a stage-local layer gets its weights
+            FluxPipeline._load_stage_weights(self, module)
+        if self.adapter_config is None:
             return module
         from . import lora
         for p in module.parameters():
