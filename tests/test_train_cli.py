@@ -183,3 +183,22 @@ betas = [0.9, 0.99]
     cfgp.write_text(cfgp.read_text().replace(f"{tmp_path}/runs'", f"{tmp_path}/runs4'"))
     run_dir5 = T.main(['--config', str(cfgp)])
     assert os.path.exists(os.path.join(run_dir5, 'step1', 'adapter_model.safetensors'))
+
+
+def test_optimizer_factory_follows_the_reference_rules():
+    """train.py:650-663,789-813: beta2 from `beta2_half_life` uses the GLOBAL batch size; 1-D parameters get no weight decay;
+    a stage without trainable parameters gets no optimizer; optimizers that are not torch-native are refused, not aliased"""
+    class M:
+        def get_param_groups(self, params):
+            return [{'params': params}]
+    w, b = torch.nn.Parameter(torch.zeros(4, 4)), torch.nn.Parameter(torch.zeros(4))
+    cfg = {'optimizer': {'type': 'AdamW', 'lr': 1e-4, 'betas': [0.9, 0.99], 'weight_decay': 0.01, 'beta2_half_life': 64}}
+    opt = T.make_optimizer_factory(cfg, M(), global_batch_size=16)([w, b])
+    assert opt.param_groups[0]['betas'] == (0.9, 0.5 ** (16 / 64))
+    assert [g['weight_decay'] for g in opt.param_groups] == [0.01, 0] and opt.param_groups[1]['params'][0] is b
+    assert cfg['optimizer']['betas'] == [0.9, 0.99]                       # the config is not edited in place
+    assert T.make_optimizer_factory(cfg, M())([]) is None
+    with pytest.raises(NotImplementedError):
+        T.make_optimizer_factory({'optimizer': {'type': 'stableadamw', 'lr': 1e-4}}, M())([w])
+    sgd = T.make_optimizer_factory({'optimizer': {'type': 'sgd', 'lr': 0.1}}, M())([w])
+    assert isinstance(sgd, torch.optim.SGD)

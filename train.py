@@ -212,8 +212,9 @@ def get_most_recent_run_dir(output_dir):
     return list(sorted(glob.glob(os.path.join(output_dir, '*'))))[-1]
 
 
-def make_optimizer_factory(config, model):
-    """train.py:650-815 for the torch-native optimizers; weight-decay / no-weight-decay split as in :789-813."""
+def make_optimizer_factory(config, model, global_batch_size=1):
+    """train.py:650-815 for the torch-native optimizers; weight-decay / no-weight-decay split as in :789-813;
+    `beta2_half_life` (in examples) -> beta2 = 0.5 ** (global_batch_size / half_life) as at :658-663."""
     def factory(params):
         if len(params) == 0:
             return None
@@ -222,7 +223,8 @@ def make_optimizer_factory(config, model):
         oc.pop('gradient_release', None)
         if half_life := oc.pop('beta2_half_life', None):
             b = oc['betas']
-            oc['betas'] = [b[0], 0.5 ** (1 / half_life)]
+            assert len(b) == 2
+            oc['betas'] = [b[0], 0.5 ** (global_batch_size / half_life)]
         if 'betas' in oc:
             oc['betas'] = tuple(oc['betas'])
         groups = []
@@ -234,7 +236,8 @@ def make_optimizer_factory(config, model):
                 groups.append(dict(pg, params=wd))
             if nowd:
                 groups.append(dict(pg, params=nowd, weight_decay=0))
-        if typ in ('adamw', 'adamw_optimi', 'stableadamw'):
+        if typ in ('adamw', 'adamw_optimi'):            # optimi.AdamW = decoupled AdamW; its Kahan-summation option is not offered
+            oc.pop('kahan_sum', None)
             return torch.optim.AdamW(groups, fused=torch.cuda.is_available(), **oc)
         if typ == 'sgd':
             return torch.optim.SGD(groups, **oc)
@@ -354,7 +357,7 @@ def main(argv=None):
     if n := config.pop('eval_every_n_examples', None):
         config['eval_every_n_steps'] = n // global_batch_size
 
-    model_engine._configure_optimizer(make_optimizer_factory(config, model), parameters_to_train)
+    model_engine._configure_optimizer(make_optimizer_factory(config, model, global_batch_size), parameters_to_train)
     optimizer = model_engine.optimizer
     model.model_engine = model_engine
     grid = model_engine.grid
