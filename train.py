@@ -390,11 +390,14 @@ def main(argv=None):
 
     step, examples = 1, global_batch_size
     if resume:
+        param_groups = optimizer.param_groups.copy() if optimizer is not None else None
         load_path, client_state = model_engine.load_checkpoint(
             run_dir, load_module_strict=False,
             load_lr_scheduler_states='force_constant_lr' not in config and not args.reset_optimizer and not args.reset_optimizer_params,
             load_optimizer_states=not args.reset_optimizer)
         assert load_path is not None
+        if args.reset_optimizer_params and optimizer is not None:        # train.py:874-875: keep the TOML's lr / betas / ...
+            optimizer.param_groups = param_groups
         if args.reset_dataloader:
             train_dataloader.epoch = client_state['custom_loader']['epoch']
         else:
