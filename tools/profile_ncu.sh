@@ -16,4 +16,11 @@ for K in gemm_bf16_kernel attn_fwd_kernel attn_bwd_dkv2_kernel attn_bwd_dq2_kern
       > gpurun_out/prof_${K}_${R}.log 2>&1
   echo "${K} rc=$?"
 done
+# 3) the HBM-bound kernels (LayerNorm+modulation, gated residual, q/k-norm+RoPE backward, column reductions, modulation linears,
+#    loss): one full capture of each on the same 1+1 block model -> DRAM GB/s against the HBM roof
+timeout 900 ncu --set full --clock-control none --import-source on \
+    -k regex:'ln_modulate|gate_bwd|qknorm_rope_bwd|colsum|colreduce|mod_fwd|mod_bwd|mse_loss|attn_bwd_delta' -s 30 -c 40 \
+    -o gpurun_out/prof_elementwise_${R} -f python bench.py --layers 1,1 --micro-batches 1 --steps 1 --warmup 1 --no-cpu-baseline --no-library-baseline \
+    > gpurun_out/prof_elementwise_${R}.log 2>&1
+echo "elementwise rc=$?"
 ls -la gpurun_out/
