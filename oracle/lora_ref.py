@@ -8,8 +8,13 @@ train.py:115-133 forces alpha = rank, so `scaling = lora_alpha / r = 1`.  A PEFT
 `result = base_layer(x); result = result + lora_B(lora_A(dropout(x))) * scaling` with lora_A ~ kaiming_uniform(a=sqrt(5)),
 lora_B = 0 and every parameter except the factors frozen.
 
-PARITY UNPINNED for this file: `peft` is a third-party dependency (requirements.txt, not vendored, not installed here) and
-the reference ships no test or golden vector for it; the forward rule above is PEFT's published `lora.Linear.forward`.
+Pinning: `peft` itself is a third-party dependency (requirements.txt, not vendored, not installed here) and the reference
+ships no test or golden vector for it; the forward rule above is PEFT's published `lora.Linear.forward`.  What the
+reference tree does contain is the consumer of the exported adapters — submodules/ComfyUI/comfy/weight_adapter/lora.py
+(`LoRAAdapter.load` :148-214 for the key layout, `calculate_weight` :224-285 for W' = W + (alpha/rank) * up @ down).
+tests/golden/make_golden_lora.py runs that code on a synthetic adapter and tests/test_oracle_lora_golden.py holds this
+file (forward, factor gradients) and the product's K-extended operands to its output.  Pinned to the reference TREE, not
+to PEFT's own code.
 Under `emulate_bf16` each Linear output (base, lora_A, lora_B) and their sum are rounded to bf16, as autocast does.
 """
 import math
