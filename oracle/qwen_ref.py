@@ -26,6 +26,11 @@ tests/test_oracle_golden.py checks this restatement against them.  The diffusers
 differently (odd latent heights: diffusers centres with h - h//2, ComfyUI with h//2) are noted where they occur and
 are "parity unpinned".
 
+SECOND PIN (the reference's own code): tests/golden/make_golden_qwen_attn.py executes `apply_rotary_emb_qwen` and
+`QwenDoubleStreamAttnProcessor2_0.__call__` from the source text of models/qwen_image.py:26-174 — with the bool key mask
+of a ragged micro-batch, which ComfyUI's model does not have — and tests/test_oracle_qwen_golden.py holds
+`RefQwenAttention` (outputs, input and parameter gradients) to tests/golden/qwen_attn_golden.pt.
+
 `emulate_bf16=True` rounds where the reference's autocast produces bf16 tensors (see oracle/flux_ref.py).
 """
 import torch
