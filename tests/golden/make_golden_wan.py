@@ -8,8 +8,9 @@ sinusoidal_embedding_1d, unpatchify).  Two stand-ins make the import possible he
     (base classes only; diffusers is not installed) — inert;
   * `flash_attention` (models/wan/attention.py asserts CUDA, :49) is replaced by softmax(q k^T / sqrt(d)) v over the
     first k_lens keys — the function flash_attn's varlen kernel computes.
-The pipeline-layer glue around the model (models/wan/wan.py:414-546 cannot be imported: it pulls in the VAE, T5, CLIP
-and DeepSpeed) is replayed here line by line on the reference's modules.
+The pipeline-layer glue around the model (models/wan/wan.py:414-546; the module cannot be imported: it pulls in the VAE,
+T5, CLIP and DeepSpeed) is replayed here line by line on the reference's modules AND executed from its own source text
+(`load_reference_layers`): both must give the identical output (asserted bit for bit) before the fixture is written.
 
 The fixture stores no weights: parameters are filled by name from tests/golden/synth.py.  Stored: inputs, the model
 output, one block's output, and gradient fingerprints of every parameter and of the inputs.
@@ -62,6 +63,46 @@ def load_reference_wan():
     return M
 
 
+def load_reference_layers(M):
+    """The pipeline layers of models/wan/wan.py:414-546 (InitialLayer, TransformerLayer, FinalLayer), taken verbatim from
+    the source text (the module itself imports the VAE, T5, CLIP, accelerate and DeepSpeed-dependent base classes) together
+    with `make_contiguous` (models/base.py:37-38).  Stand-ins: AUTOCAST_DTYPE (autocast('cuda') is inert on the CPU, so the
+    layers run in fp32) and a no-op offloader."""
+    import ast
+    ns = {'torch': torch, 'nn': nn, 'AUTOCAST_DTYPE': torch.bfloat16, 'sinusoidal_embedding_1d': M.sinusoidal_embedding_1d}
+    tree = ast.parse(open('/root/reference/models/base.py').read())
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == 'make_contiguous']
+    exec(compile(ast.Module(body=fns, type_ignores=[]), 'models/base.py', 'exec'), ns)
+    tree = ast.parse(open('/root/reference/models/wan/wan.py').read())
+    classes = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name in ('InitialLayer', 'TransformerLayer', 'FinalLayer')]
+    assert len(classes) == 3
+    exec(compile(ast.Module(body=classes, type_ignores=[]), 'models/wan/wan.py', 'exec'), ns)
+    return ns
+
+
+class _NoOffload:
+    def wait_for_block(self, i):
+        pass
+
+    def submit_move_blocks_forward(self, i):
+        pass
+
+
+def run_reference_layers(M, model, x, y, t, text, text_lens):
+    """the reference's own layer stack on the tuple its prepare_inputs emits (None -> empty tensor, utils/dataset.py:1277-1279)"""
+    import warnings
+    L = load_reference_layers(M)
+    none = torch.tensor([])
+    layers = [L['InitialLayer'](model, None)] + [L['TransformerLayer'](b, i, _NoOffload()) for i, b in enumerate(model.blocks)] \
+        + [L['FinalLayer'](model)]
+    h = (x, none if y is None else y, t, text, text_lens, none)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')          # "CUDA is not available" from the autocast decorators
+        for layer in layers:
+            h = layer(h)
+    return h
+
+
 def main():
     M = load_reference_wan()
     cfg = dict(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, text_len=16, B=2, f=3, h=8, w=12)
@@ -93,6 +134,9 @@ def main():
         hcur = blk(hcur, e0, seq_lens, grid_sizes, model.freqs, ctx, None)
     # ---- :541-546 FinalLayer.forward ----
     out = torch.stack(model.unpatchify(model.head(hcur, e), grid_sizes), dim=0)
+    # the same through the reference's own InitialLayer / TransformerLayer / FinalLayer text: must be the replay above
+    out_layers = run_reference_layers(M, model, x.detach().clone(), None, t, text.detach().clone(), text_lens)
+    assert torch.equal(out_layers, out), (out_layers - out).abs().max()
     probe = synth_tensor(tuple(out.shape), 403, 1.0)
     (out * probe).sum().backward()
     g = {'cfg': cfg, 'x': x.detach(), 'text': text.detach(), 'text_lens': text_lens, 't': t, 'out': out.detach(),
@@ -140,6 +184,8 @@ def main():
                                           for u in [emb[:n] for emb, n in zip(text.detach(), text_lens)]]))
     h2 = m2.blocks[0](xe2, e0_2, sl, gs, m2.freqs, ctx2, None)
     out2 = torch.stack(m2.unpatchify(m2.head(h2, e_2), gs), dim=0)
+    out2_layers = run_reference_layers(M, m2, x2.detach().clone(), y2.detach().clone(), t, text.detach().clone(), text_lens)
+    assert torch.equal(out2_layers, out2), (out2_layers - out2).abs().max()
     probe2 = synth_tensor(tuple(out2.shape), 413, 1.0)
     (out2 * probe2).sum().backward()
     g['i2v_v2'] = {'x': x2.detach(), 'y': y2.detach(), 'out': out2.detach(), 'probe': probe2, 'dx': x2.grad.clone(),
