@@ -252,9 +252,12 @@ def evaluate(model_engine, eval_dataloaders, step, egas, log):
     from diffusion_pipe_b200.data_feed import get_data_iterator_for_step
     cpu_state, cuda_state = torch.get_rng_state(), torch.cuda.get_rng_state() if torch.cuda.is_available() else None
     py_state = random.getstate()
-    seed = dist.get_rank()
+    import numpy as np
+    np_state = np.random.get_state()
+    seed = dist.get_rank()                                                # train.py:233-238 under isolate_rng()
     random.seed(seed)
     torch.manual_seed(seed)
+    np.random.seed(seed)
     start = time.time()
     with torch.no_grad():
         for name, dl in eval_dataloaders.items():
@@ -279,6 +282,7 @@ def evaluate(model_engine, eval_dataloaders, step, egas, log):
     if cuda_state is not None:
         torch.cuda.set_rng_state(cuda_state)
     random.setstate(py_state)
+    np.random.set_state(np_state)
 
 
 def main(argv=None):
