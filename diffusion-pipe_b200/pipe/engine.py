@@ -64,14 +64,20 @@ class DistLink:
         return self.device if self.device.type == 'cuda' else torch.device('cpu')
 
     def send_tuple(self, tensors, dst, key):
+        meta = [len(tensors)]
+        for t in tensors:
+            meta += [_DTYPE_ID[t.dtype], t.dim()] + list(t.shape)
         if key not in self._send_meta_done:
-            meta = [len(tensors)]
-            for t in tensors:
-                meta += [_DTYPE_ID[t.dtype], t.dim()] + list(t.shape)
             m = torch.tensor([len(meta)] + meta, dtype=torch.int64, device=self._meta_device())
             self._send(m[:1].clone(), dst)
             self._send(m[1:].contiguous(), dst)
-            self._send_meta_done[key] = True
+            self._send_meta_done[key] = meta
+        elif self._send_meta_done[key] != meta:
+            # the receiver allocates from the shapes announced once per step: a different tuple would be received into
+            # wrongly sized buffers without any error from the transport
+            raise RuntimeError('the boundary tuple changed shape or dtype since it was announced to the next stage: call '
+                               'engine.reset_activation_shape() before a step whose micro-batches have new shapes '
+                               '(train.py:916, train.py:181)')
         for t in tensors:
             self._send(t.contiguous(), dst)
 

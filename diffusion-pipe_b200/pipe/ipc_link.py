@@ -282,6 +282,11 @@ class IpcLink:
         if self._fresh['act_out']:
             self.act_out.handshake_send_described(ts)
             self._fresh['act_out'] = False
+        elif self.act_out.specs != [(t.dtype, tuple(t.shape)) for t in ts]:
+            # the slot layout on both sides comes from the handshake: a different tuple would be copied to wrong offsets
+            raise RuntimeError('the boundary tuple changed shape or dtype since it was announced to the next stage: call '
+                               'engine.reset_activation_shape() before a step whose micro-batches have new shapes '
+                               '(train.py:916, train.py:181)')
         self.act_out.push(ts, mb)
         if not keep and self.act_in is not None:
             # forward-only schedule: outputs may alias pass-through tensors that live in our input slot, so the slot is

@@ -307,8 +307,39 @@ def fp8_to_bf16(src, dst):
     return dst
 
 
+def _poison_uninitialised(monkeypatch):
+    """torch.empty / empty_like / new_empty hand out NaN-filled floating-point tensors while the doubles are installed:
+    host code that reads memory no kernel has written (on a GPU: whatever the caching allocator left there) turns into a
+    NaN in the test instead of a value that happens to be small.  This is how the missing reset_activation_shape() of
+    tests/test_families_pipeline_cpu.py was found.  DPIPE_TEST_POISON_EMPTY=0 switches it off."""
+    import os
+    if os.environ.get('DPIPE_TEST_POISON_EMPTY', '1') != '1' or getattr(torch.empty, '_dpipe_poison', False):
+        return
+    real_empty, real_empty_like, real_new_empty = torch.empty, torch.empty_like, torch.Tensor.new_empty
+    skip = (torch.float8_e4m3fn, torch.float8_e5m2)
+
+    def poison(t):
+        if torch.is_tensor(t) and t.is_floating_point() and t.numel() and t.dtype not in skip and t.device.type == 'cpu':
+            t.fill_(float('nan'))
+        return t
+
+    def empty(*a, **k):
+        return poison(real_empty(*a, **k))
+
+    def empty_like(*a, **k):
+        return poison(real_empty_like(*a, **k))
+
+    def new_empty(self, *a, **k):
+        return poison(real_new_empty(self, *a, **k))
+    empty._dpipe_poison = True
+    monkeypatch.setattr(torch, 'empty', empty)
+    monkeypatch.setattr(torch, 'empty_like', empty_like)
+    monkeypatch.setattr(torch.Tensor, 'new_empty', new_empty)
+
+
 def install(monkeypatch, ops):
     """replaces the kernel wrappers of `ops` (diffusion_pipe_b200.ops) by the doubles above"""
+    _poison_uninitialised(monkeypatch)
     for name in ('gemm', 'make_qkv_epilogue', 'qknorm_rope_bwd', 'attn_fwd', 'attn_bwd', 'nchunks', 'ln_modulate_fwd',
                  'ln_modulate_bwd', 'gate_bwd', 'colreduce_finish', 'colsum', 'wan_norm_rope_fwd', 'wan_norm_rope_bwd', 'mod_fwd',
                  'mod_bwd', 'mse_loss', 'fp8_to_bf16'):

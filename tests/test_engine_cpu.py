@@ -169,3 +169,30 @@ def test_deep_pipelines_match_the_single_process_engine(stages, gas, schedule):
     res = _run(stages, stages, 'uniform', schedule, gas=gas)
     assert [r['stage'] for r in res] == list(range(stages))
     _check(res, 1, gas)
+
+
+def _worker_shape_change(rank, world, port, outdir):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import toy_model
+    from diffusion_pipe_b200.pipe import ManualPipelineModule, dist, initialize
+    torch.set_num_threads(1)
+    dist.init_distributed('gloo')
+    pm = ManualPipelineModule(layers=toy_model.make_layers(), num_stages=2, partition_method='uniform', loss_fn=toy_model.loss_fn,
+                              dynamic_shape=True, device=torch.device('cpu'))
+    engine, _, _, _ = initialize(model=pm, config={'train_micro_batch_size_per_gpu': MBS, 'gradient_accumulation_steps': 2,
+                                                   'gradient_clipping': 0.5, 'steps_per_print': 0, 'stage_link': 'dist'})
+    engine._configure_optimizer(lambda ps: torch.optim.SGD(ps, lr=0.1) if ps else None, [p for p in pm.parameters() if p.requires_grad])
+    engine.reset_activation_shape()
+    engine.train_batch(iter(toy_model.make_micro_batches(2, MBS, seed=1)))
+    # a step with another micro-batch size WITHOUT reset_activation_shape(): the sending stage must refuse
+    engine.train_batch(iter(toy_model.make_micro_batches(2, MBS + 1, seed=2)))
+
+
+def test_changed_boundary_shapes_without_reset_are_refused():
+    """train.py:916 / :181 call reset_activation_shape() before every step; forgetting it used to receive the new tuple
+    into buffers sized for the old one without any error from the transport"""
+    with tempfile.TemporaryDirectory() as d:
+        with pytest.raises(Exception, match='reset_activation_shape'):
+            mp.spawn(_worker_shape_change, args=(2, _free_port(), d), nprocs=2, join=True)

@@ -100,6 +100,7 @@ def _worker(rank, world, port, kind, stages, schedule, outdir, gpu=False, link='
         mbs = _micro_batches(kind, model, GAS, 100 + step)
         it = iter(mbs) if (engine.is_first_stage() or engine.is_last_stage()) else None
         losses.append(float(engine.train_batch(it)))
+    engine.reset_activation_shape()        # train.py:181: the evaluation micro-batches have their own shapes (prompt padding)
     ev_it = iter(_micro_batches(kind, model, 2, 999)) if (engine.is_first_stage() or engine.is_last_stage()) else None
     ev = float(engine.eval_batch(ev_it, num_micro_batches=2))
     torch.save({'losses': losses, 'eval': ev, 'norm': float(engine._grad_norm)}, os.path.join(outdir, f'rank{rank}.pt'))
