@@ -4,6 +4,7 @@
 #   gpurun --gpus 8 --timeout 900 -- 'bash tools/gpu_session.sh r02 scale8'      (charged 8x: keep it short)
 # Stages (any subset, in the order given):
 #   tests     python -m pytest tests -m gpu            (no -x: one failing case must not hide the rest)
+#   poison    the same with DPIPE_TEST_POISON_EMPTY_CUDA=1: uninitialised CUDA memory reads as NaN (tests/conftest.py)
 #   bench     bench.py at N=1 (the driver's default line)
 #   launches  ncu launch list of the bench command + full captures of the top kernels (tools/profile_ncu.sh)
 #   wan       tools/probe_wan_block.py at the 14B shapes + tools/bench_family.py --model wan on a reduced depth
@@ -17,6 +18,7 @@ trun() { local n=$1; shift; python -m torch.distributed.run --nnodes=1 --nproc-p
 for S in "$@"; do
   case $S in
     tests)    T=1500 run tests python -m pytest tests -q -m gpu ;;
+    poison)   T=1500 run tests_poison env DPIPE_TEST_POISON_EMPTY_CUDA=1 python -m pytest tests -q -m gpu ;;
     bench)    T=600 run bench1 python bench.py ;;
     launches) T=2400 run ncu bash tools/profile_ncu.sh "$R" ;;
     wan)      T=600 run wan_block python tools/probe_wan_block.py
