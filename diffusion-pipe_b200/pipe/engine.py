@@ -414,11 +414,12 @@ class PipelineEngine:
         for p in params:
             g = p.grad
             base = g._base if g._base is not None else g
-            if base.data_ptr() in seen:
-                continue
             if base is not g and base.is_contiguous():
-                g = base     # fused gradient buffer: reduce it once as a whole
-            seen.add(base.data_ptr())
+                g = base     # fused gradient buffer (views of one allocation): reduce it once as a whole
+            key = (g.data_ptr(), g.numel())
+            if key in seen:
+                continue
+            seen.add(key)
             if g.numel() >= (1 << 20) and g.is_contiguous() and (comm_dtype is None or comm_dtype == g.dtype):
                 dist.all_reduce(g, group=group)
                 g.div_(world)

@@ -68,7 +68,7 @@ def _micro_batches(kind, model, n, seed):
     return data_feed.split_batch((feats, label), n)
 
 
-def _worker(rank, world, port, kind, stages, schedule, outdir, gpu=False, link='dist'):
+def _worker(rank, world, port, kind, stages, schedule, outdir, gpu=False, link='dist', gas=GAS, save_params=False):
     """gpu=False: CPU + gloo + kernel test doubles;  gpu=True (tests/test_pipeline_multigpu.py): one GPU per rank, NCCL,
     the real kernels and the requested stage link"""
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
@@ -89,7 +89,7 @@ def _worker(rank, world, port, kind, stages, schedule, outdir, gpu=False, link='
     model = _make(kind, device)
     pm = ManualPipelineModule(layers=model.to_layers(), num_stages=stages, partition_method='uniform', manual_partition_split=None,
                               loss_fn=model.get_loss_fn(), dynamic_shape=True, device=device)
-    engine, _, _, _ = initialize(model=pm, config={'train_micro_batch_size_per_gpu': 1, 'gradient_accumulation_steps': GAS,
+    engine, _, _, _ = initialize(model=pm, config={'train_micro_batch_size_per_gpu': 1, 'gradient_accumulation_steps': gas,
                                                    'gradient_clipping': 1.0, 'steps_per_print': 0, 'stage_link': link,
                                                    'pipeline_schedule': schedule})
     params = [p for p in pm.parameters() if p.requires_grad]
@@ -97,27 +97,36 @@ def _worker(rank, world, port, kind, stages, schedule, outdir, gpu=False, link='
     losses = []
     for step in range(2):
         engine.reset_activation_shape()
-        mbs = _micro_batches(kind, model, GAS, 100 + step)
+        dp, dp_rank = engine.grid.get_data_parallel_world_size(), engine.grid.get_data_parallel_rank()
+        # one global batch of gas * dp samples per step; replica r trains on samples r, r + dp, r + 2 dp, ...
+        mbs = _micro_batches(kind, model, gas * dp, 100 + step)[dp_rank::dp]
         it = iter(mbs) if (engine.is_first_stage() or engine.is_last_stage()) else None
         losses.append(float(engine.train_batch(it)))
     engine.reset_activation_shape()        # train.py:181: the evaluation micro-batches have their own shapes (prompt padding)
     ev_it = iter(_micro_batches(kind, model, 2, 999)) if (engine.is_first_stage() or engine.is_last_stage()) else None
     ev = float(engine.eval_batch(ev_it, num_micro_batches=2))
-    torch.save({'losses': losses, 'eval': ev, 'norm': float(engine._grad_norm)}, os.path.join(outdir, f'rank{rank}.pt'))
+    out = {'losses': losses, 'eval': ev, 'norm': float(engine._grad_norm), 'stage': engine.stage_id}
+    if save_params:
+        out['params'] = {p.original_name: p.detach().float().clone() for p in pm.parameters()}
+    torch.save(out, os.path.join(outdir, f'rank{rank}.pt'))
     if world > 1:
         dist.barrier()
 
 
-def _run(kind, stages, schedule, gpu=False, link='dist'):
+def _run(kind, stages, schedule, gpu=False, link='dist', dp=1, gas=GAS, save_params=False):
     with tempfile.TemporaryDirectory() as d:
         port = _free_port()
+        if dp > 1:
+            world = stages * dp
+            mp.spawn(_worker, args=(world, port, kind, stages, schedule, d, gpu, link, gas, save_params), nprocs=world, join=True)
+            return [torch.load(os.path.join(d, f'rank{r}.pt'), weights_only=False) for r in range(world)]
         if stages == 1 and not gpu:
             _worker(0, 1, port, kind, 1, schedule, d)
             import torch.distributed as tdist
             if tdist.is_initialized():
                 tdist.destroy_process_group()
         else:
-            mp.spawn(_worker, args=(stages, port, kind, stages, schedule, d, gpu, link), nprocs=stages, join=True)
+            mp.spawn(_worker, args=(stages, port, kind, stages, schedule, d, gpu, link, gas, save_params), nprocs=stages, join=True)
         return [torch.load(os.path.join(d, f'rank{r}.pt'), weights_only=False) for r in range(stages)]
 
 
@@ -130,3 +139,23 @@ def test_two_stage_pipeline_matches_single_stage(kind):
             assert r['losses'] == pytest.approx(base['losses'], rel=2e-3), (kind, schedule, r['losses'], base['losses'])
             assert r['eval'] == pytest.approx(base['eval'], rel=2e-3)
             assert r['norm'] == pytest.approx(base['norm'], rel=2e-2)
+
+
+def test_qwen_two_stages_times_two_replicas_equals_one_pipeline_on_the_same_global_batch():
+    """BASELINE.json configs[4] shape (Qwen-Image, pipeline x data parallel) on the real model code: the gradients of a
+    model whose q/k/v (and Wan's k/v) gradients live in FUSED buffers are all-reduced over the replicas of each stage,
+    then clipped by the global norm — losses, norm and every updated parameter equal the 2-stage run that sees the same
+    8 samples per step as 8 micro-batches (zero-bubble order in both)"""
+    one = _run('qwen_image', 2, 'zb', gas=8, save_params=True)
+    two = _run('qwen_image', 2, 'zb', dp=2, gas=4, save_params=True)
+    assert [r['stage'] for r in two] == [0, 0, 1, 1]
+    for r in two:
+        assert r['losses'] == pytest.approx(one[0]['losses'], rel=2e-3)
+        assert r['norm'] == pytest.approx(one[0]['norm'], rel=2e-2)
+        ref = one[r['stage']]['params']
+        assert set(ref) == set(r['params'])
+        for k, v in r['params'].items():
+            assert (v - ref[k]).norm() <= 2e-2 * (ref[k].norm() + 1e-6) + 1e-4, k
+    # replicas of a stage hold identical parameters after the step
+    for k, v in two[0]['params'].items():
+        assert torch.equal(v, two[1]['params'][k]), k
