@@ -18,6 +18,7 @@ import torch
 from torch import nn
 
 from . import ops
+from .plugin import PluginSurface
 from .flux_blocks import (FluxSingleTransformerBlock, FluxTransformerBlock, _AdaNorm, _acc_vec, _grad_buf, _mod_bwd,
                           _mod_fwd, _plain, _silu_bf16)
 
@@ -313,7 +314,7 @@ def base_storage_dtype(model_config, adapter_configured=True):
     return v
 
 
-class FluxPipeline:
+class FluxPipeline(PluginSurface):
     """Mirror of the reference FluxPipeline's training-side surface (models/flux.py:153-404)."""
     name = 'flux'
     checkpointable_layers = ['TransformerWrapper', 'SingleTransformerWrapper']

@@ -34,6 +34,7 @@ from torch import nn
 from . import ops
 from .flux import AdaLNContinuousFn, MseLossFn, _MLPEmbedder, get_lin_function, linear, make_contiguous, time_shift
 from .flux_blocks import HD, FluxDoubleBlockFn, FusedParam, _AdaNorm, _Attn, _FF, _norm_w, _plain
+from .plugin import PluginSurface
 
 QWEN_IMAGE_CONFIG = {   # reference: configs/qwen_image/transformer/config.json
     'attention_head_dim': 128, 'num_attention_heads': 24, 'num_layers': 60, 'in_channels': 64, 'out_channels': 16,
@@ -256,7 +257,7 @@ def pack_latents(x):
     return x.reshape(b, c, h // 2, 2, w // 2, 2).permute(0, 2, 4, 1, 3, 5).reshape(b, (h // 2) * (w // 2), c * 4)
 
 
-class QwenImagePipeline:
+class QwenImagePipeline(PluginSurface):
     """Mirror of the reference QwenImagePipeline's training-side surface (models/qwen_image.py:177-517).  VAE, the
     Qwen2.5-VL text encoder and latent caching are outside the hot path (SURVEY.md section 8) and are not provided;
     `prepare_inputs` consumes the same cached tensors (`latents`, `prompt_embeds`, `mask`, optional `control_latents`)."""

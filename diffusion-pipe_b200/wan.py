@@ -29,6 +29,7 @@ from torch import nn
 from . import ops
 from .flux import linear, make_contiguous
 from .flux_blocks import HD, FusedParam, _acc_vec, _grad_buf, _mod_bwd, _mod_fwd, _plain
+from .plugin import PluginSurface
 
 WAN_T2V_14B_CONFIG = {   # reference: models/wan/configs.py:60-75 (t2v_14B)
     'model_type': 't2v', 'dim': 5120, 'ffn_dim': 13824, 'num_heads': 40, 'num_layers': 40, 'in_dim': 16, 'out_dim': 16,
@@ -579,7 +580,7 @@ def sample_t(t, batch_size, quantile=None):
     return t[i]
 
 
-class WanPipeline:
+class WanPipeline(PluginSurface):
     """Mirror of the reference WanPipeline's training-side surface (models/wan/wan.py:67-411).  VAE, UMT5, CLIP and
     latent caching are outside the hot path; `prepare_inputs` consumes the same cached tensors
     (`latents`, `text_embeddings`, `seq_lens`, `mask`)."""

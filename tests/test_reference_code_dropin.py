@@ -4,6 +4,7 @@
     utils/saver.py                      imported as it is (module); `deepspeed.comm` -> diffusion_pipe_b200.pipe.dist
     utils/dataset.py:1273-1450          split_batch, PipelineDataLoader, SkipFirstNSampler   (source text)
     train.py:167-173                    get_data_iterator_for_step                            (source text)
+    train.py:39,176-242                 evaluate / _evaluate / evaluate_single + utils/isolate_rng.py (source text / module)
 
 They drive diffusion_pipe_b200's engine, PipelineModule and FluxPipeline (kernel wrappers = the CPU test doubles) for a few
 optimizer steps with model export, checkpoint and resume, for 1 and 2 pipeline stages, and must give the same losses
@@ -75,7 +76,30 @@ def load_reference_driver_code():
     tree = ast.parse(open(os.path.join(REF, 'train.py')).read())
     body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == 'get_data_iterator_for_step']
     exec(compile(ast.Module(body=body, type_ignores=[]), 'train.py', 'exec'), ns)
-    return saver.Saver, ns['PipelineDataLoader'], ns['get_data_iterator_for_step']
+    # train.py:39,176-242: the evaluation functions (quantile sweep, RNG isolation, block-swap hooks of the plugin)
+    import random
+    import time
+    import numpy as np
+    spec = importlib.util.spec_from_file_location('reference_isolate_rng', os.path.join(REF, 'utils', 'isolate_rng.py'))
+    iso = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(iso)
+
+    class tqdm:
+        def __init__(self, total=None):
+            self.total, self.n = total, 0
+
+        def update(self, k):
+            self.n += k
+
+        def close(self):
+            assert self.n == self.total, (self.n, self.total)      # the reference's own progress arithmetic adds up
+    ns.update({'random': random, 'time': time, 'np': np, 'tqdm': tqdm, 'wandb_enable': False, 'wandb': None,
+               'empty_cuda_cache': lambda: None, 'isolate_rng': iso.isolate_rng, 'get_rank': dist.get_rank})
+    body = [n for n in tree.body if (isinstance(n, ast.FunctionDef) and n.name in ('evaluate_single', '_evaluate', 'evaluate'))
+            or (isinstance(n, ast.Assign) and getattr(n.targets[0], 'id', '') == 'TIMESTEP_QUANTILES_FOR_EVAL')]
+    assert len(body) == 4
+    exec(compile(ast.Module(body=body, type_ignores=[]), 'train.py', 'exec'), ns)
+    return saver.Saver, ns['PipelineDataLoader'], ns['get_data_iterator_for_step'], ns['evaluate']
 
 
 class Batches:
@@ -126,11 +150,13 @@ def _worker(rank, world, port, which, outdir, resume):
         grid = engine.grid
         engine.first_last_stage_group = dist.new_group(ranks=[grid.pp_group[0], grid.pp_group[-1]])
     if which == 'reference':
-        RefSaver, RefLoader, get_iter = load_reference_driver_code()
+        RefSaver, RefLoader, get_iter, ref_evaluate = load_reference_driver_code()
         loader = RefLoader(Batches(2, GAS), engine, GAS, model, num_dataloader_workers=0)
+        eval_loader = RefLoader(Batches(2, 1), engine, 1, model, num_dataloader_workers=0)
     else:
         RefSaver, get_iter = my_saver.Saver, data_feed.get_data_iterator_for_step
         loader = data_feed.PipelineDataLoader(Batches(2, GAS), engine, GAS, model, num_dataloader_workers=0)
+        eval_loader = data_feed.PipelineDataLoader(Batches(2, 1), engine, 1, model, num_dataloader_workers=0)
     run_dir = os.path.join(outdir, 'run_' + which)
     if rank == 0:
         os.makedirs(run_dir, exist_ok=True)
@@ -156,7 +182,20 @@ def _worker(rank, world, port, which, outdir, resume):
             epoch = new_epoch
         saver.process_step(step, step * GAS)
         step += 1
-    torch.save({'losses': losses, 'epochs': epochs, 'state': loader.state_dict()}, os.path.join(outdir, f'{which}_resume{int(resume)}_rank{rank}.pt'))
+    # evaluation: 9 timestep quantiles x the whole eval set, seeded by rank, RNG state restored afterwards
+    scalars = []
+    rng_before = torch.get_rng_state().clone()
+    if which == 'reference':
+        tb = types.SimpleNamespace(add_scalar=lambda tag, value, x: scalars.append((tag, float(value), x)))
+        ref_evaluate(model, engine, {'eval0': eval_loader}, tb, step, 1, False)
+    else:
+        sys.path.insert(0, ROOT)
+        import train as my_train
+        my_train.evaluate(engine, {'eval0': eval_loader}, step, 1, lambda tag, value, x: scalars.append((tag, float(value), x)))
+    assert torch.equal(torch.get_rng_state(), rng_before)
+    scalars = [s for s in scalars if s[0] != 'eval/eval_time_sec']
+    torch.save({'losses': losses, 'epochs': epochs, 'state': loader.state_dict(), 'eval': scalars},
+               os.path.join(outdir, f'{which}_resume{int(resume)}_rank{rank}.pt'))
     dist.barrier()
 
 
@@ -175,6 +214,9 @@ def test_reference_loader_and_saver_drive_the_engine(world):
             assert r['losses'] == m['losses'] and all(v == v and 0 < v < 100 for v in r['losses'])
             assert r['epochs'] == m['epochs'] == [1, 2, 2]            # 2 batches per epoch: the epoch turns when the last one is RETURNED
             assert r['state'] == m['state']
+        # the reference's evaluate() logs on rank 0 only; this repo's log callback is rank-0-gated by its caller
+        assert len(ref[0]['eval']) == 10 and ref[0]['eval'] == mine[0]['eval']
+        assert [t for t, _, _ in ref[0]['eval']][:2] == ['eval0/loss_quantile_0.10', 'eval0/loss_quantile_0.20'] and ref[0]['eval'][-1][0] == 'eval0/loss'
         for which in ('reference', 'mine'):
             run = os.path.join(d, 'run_' + which)
             assert os.path.exists(os.path.join(run, 'latest')) or any(n.startswith('global_step') for n in os.listdir(run)), os.listdir(run)
