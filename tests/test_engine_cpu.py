@@ -161,7 +161,7 @@ def test_two_stages_times_two_replicas_world_4(schedule):
             assert torch.allclose(v, sd[k], rtol=1e-5, atol=1e-6), k
 
 
-@pytest.mark.parametrize('stages,gas,schedule', [(4, 8, '1f1b'), (4, 8, 'zb'), (4, 3, 'zb'), (6, 12, 'zb'), (6, 7, '1f1b')])
+@pytest.mark.parametrize('stages,gas,schedule', [(4, 8, 'zb'), (4, 3, 'zb'), (6, 12, 'zb'), (6, 7, '1f1b')])
 def test_deep_pipelines_match_the_single_process_engine(stages, gas, schedule):
     """4 and 6 stages (6 toy layers: 'uniform' gives uneven stages at 4, one layer per stage at 6), more and fewer
     micro-batches than the zero-bubble order may hold (2 x stages): the order of F / B / W across real processes changes

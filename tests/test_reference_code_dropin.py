@@ -225,6 +225,8 @@ def test_reference_loader_and_saver_drive_the_engine(world):
         b = load_file(os.path.join(d, 'run_mine', 'step2', 'model.safetensors'))
         assert set(a) == set(b) and 'transformer_blocks.0.attn.to_q.weight' in a and 'single_transformer_blocks.0.proj_out.weight' in a
         assert all(torch.equal(a[k], b[k]) for k in a)
+        if world == 1:
+            return                                                      # (the resume leg runs once, on the 2-stage pipeline)
         # resume from the checkpoint the reference's Saver asked the engine to write (end of epoch 1 = step 2)
         ref2 = _run(world, 'reference', d, resume=True)
         mine2 = _run(world, 'mine', d, resume=True)
