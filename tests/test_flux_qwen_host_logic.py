@@ -245,3 +245,41 @@ def test_masked_and_robust_losses_match_the_reference_loss(doubles, family, vari
     rloss.backward()
     assert loss.item() == pytest.approx(rloss.item(), rel=1e-5)
     torch.testing.assert_close(pred.grad.float(), ref_pred.grad, rtol=2e-2, atol=1e-6)
+
+
+def test_flux_schnell_variant_without_guidance_embedder_matches_oracle(doubles):
+    """models/flux.py:475-479: Flux-schnell has no guidance embedder (diffusers CombinedTimestepTextProjEmbeddings); the
+    guidance entry of the tuple still travels and is ignored (`guidance_embeds = false` in the transformer config)"""
+    from diffusion_pipe_b200.flux import FluxPipeline
+    from oracle import flux_ref as R
+    cfg = {'num_attention_heads': 2, 'num_layers': 1, 'num_single_layers': 1, 'joint_attention_dim': 64, 'pooled_projection_dim': 32,
+           'guidance_embeds': False}
+    torch.manual_seed(0)
+    model = FluxPipeline({'model': {'dtype': 'bfloat16', 'guidance': 1.0, 'transformer_config': cfg}}, device='cpu')
+    names = {n for n, _ in model.transformer.named_parameters()}
+    assert not any('guidance_embedder' in n for n in names) and any('timestep_embedder' in n for n in names)
+    ref = R.RefFluxTransformer(dim=256, heads=2, num_double=1, num_single=1, joint_dim=64, pooled_dim=32, guidance_embeds=False)
+    assert names == {n for n, _ in ref.named_parameters()}
+    with torch.no_grad():
+        for n, p in model.transformer.named_parameters():
+            if p.ndim == 1 and 'norm_' not in n:
+                p.normal_(0, 0.05)
+    ref.load_state_dict({k: v.detach().float() for k, v in model.transformer.state_dict().items()})
+    ref.set_emulate_bf16(True)
+    g = torch.Generator().manual_seed(3)
+    bs = 2
+    latents, noise = torch.randn(bs, 16, 8, 8, generator=g), torch.randn(bs, 16, 8, 8, generator=g)
+    t5, clip = torch.randn(bs, 12, 64, generator=g).bfloat16(), torch.randn(bs, 32, generator=g).bfloat16()
+    feats, (target, _) = R.prepare_inputs(latents, t5, clip, torch.sigmoid(torch.randn(bs, generator=g)), noise)
+    label = (target, torch.tensor([]))
+    x = tuple(f.clone() for f in feats)
+    for layer in model.to_layers():
+        x = layer(x)
+    loss = model.get_loss_fn()(x, label)
+    loss.backward()
+    y = tuple(f.clone() for f in feats)
+    for layer in R.to_layers(ref):
+        y = layer(y)
+    rloss = R.loss_fn(y, label)
+    rloss.backward()
+    _compare(model.transformer.named_parameters(), ref, loss, rloss)
