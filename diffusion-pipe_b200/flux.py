@@ -172,7 +172,7 @@ class CombinedTimestepGuidanceTextProjEmbeddings(nn.Module):
 
     def forward(self, timestep, guidance, pooled):
         emb = self.timestep_embedder(timestep_sinusoid(timestep).to(torch.bfloat16))
-        if guidance is not None and hasattr(self, 'guidance_embedder'):
+        if guidance is not None and hasattr(self, 'guidance_embedder') and not getattr(self, 'bypass_guidance', False):
             emb = emb + self.guidance_embedder(timestep_sinusoid(guidance).to(torch.bfloat16))
         return emb + self.text_embedder(pooled)
 
@@ -348,6 +348,8 @@ class FluxPipeline(PluginSurface):
         self.transformer = FluxTransformer2DModel(tcfg, dtype=dtype, device=device)
         if path := self.model_config.get('transformer_path', None):
             self.load_transformer_weights(path)
+        if self.model_config.get('bypass_guidance_embedding', False):       # models/flux.py:132-150,191-194
+            self.transformer.time_text_embed.bypass_guidance = True
         self.transformer.train()
 
     def _lazy_layers(self):
@@ -370,6 +372,8 @@ class FluxPipeline(PluginSurface):
                                  CombinedTimestepGuidanceTextProjEmbeddings(dim, cfg['pooled_projection_dim'], dtype, d,
                                                                             cfg.get('guidance_embeds', True)),
                                  _plain(dim, cfg['joint_attention_dim'], dtype, d), tuple(cfg['axes_dims_rope']))
+            if self.model_config.get('bypass_guidance_embedding', False):
+                w.time_text_embed.bypass_guidance = True
             return self._adapt(name_params(w, {'x_embedder.': 'x_embedder.', 'time_text_embed.': 'time_text_embed.',
                                                'context_embedder.': 'context_embedder.'}), dev)
 

@@ -283,3 +283,35 @@ def test_flux_schnell_variant_without_guidance_embedder_matches_oracle(doubles):
     rloss = R.loss_fn(y, label)
     rloss.backward()
     _compare(model.transformer.named_parameters(), ref, loss, rloss)
+
+
+def test_bypass_guidance_embedding_drops_the_guidance_term(doubles):
+    """models/flux.py:132-150: `bypass_guidance_embedding = true` keeps the guidance embedder's parameters but conditions on
+    timestep + pooled text only — the schnell arithmetic on a dev checkpoint"""
+    from diffusion_pipe_b200.flux import FluxPipeline
+    from oracle import flux_ref as R
+    cfg = {'num_attention_heads': 2, 'num_layers': 1, 'num_single_layers': 1, 'joint_attention_dim': 64, 'pooled_projection_dim': 32}
+    torch.manual_seed(0)
+    model = FluxPipeline({'model': {'dtype': 'bfloat16', 'guidance': 1.0, 'bypass_guidance_embedding': True, 'transformer_config': cfg}},
+                         device='cpu')
+    assert any('guidance_embedder' in n for n, _ in model.transformer.named_parameters())
+    ref = R.RefFluxTransformer(dim=256, heads=2, num_double=1, num_single=1, joint_dim=64, pooled_dim=32, guidance_embeds=False)
+    sd = {k: v.detach().float() for k, v in model.transformer.state_dict().items() if 'guidance_embedder' not in k}
+    ref.load_state_dict(sd)
+    ref.set_emulate_bf16(True)
+    g = torch.Generator().manual_seed(4)
+    latents, noise = torch.randn(2, 16, 8, 8, generator=g), torch.randn(2, 16, 8, 8, generator=g)
+    t5, clip = torch.randn(2, 12, 64, generator=g).bfloat16(), torch.randn(2, 32, generator=g).bfloat16()
+    feats, (target, _) = R.prepare_inputs(latents, t5, clip, torch.sigmoid(torch.randn(2, generator=g)), noise, guidance=3.5)
+    label = (target, torch.tensor([]))
+    x = tuple(f.clone() for f in feats)
+    for layer in model.to_layers():
+        x = layer(x)
+    loss = model.get_loss_fn()(x, label)
+    loss.backward()
+    y = tuple(f.clone() for f in feats)
+    for layer in R.to_layers(ref):
+        y = layer(y)
+    rloss = R.loss_fn(y, label)
+    assert abs(loss.item() - rloss.item()) / abs(rloss.item()) <= 1e-3
+    assert all(p.grad is None for n, p in model.transformer.named_parameters() if 'guidance_embedder' in n)
