@@ -331,9 +331,17 @@ class FluxPipeline(PluginSurface):
         if dtype != torch.bfloat16:
             raise NotImplementedError('the sm_100a Flux path computes in bf16 (model.dtype must be bfloat16)')
         tcfg = self.model_config.get('transformer_config', None)
+        # models/flux.py:174-191: without `transformer_path` the weights are `<diffusers_path>/transformer/*.safetensors`,
+        # whose config.json describes the architecture (dev / schnell)
+        dpath = self.model_config.get('diffusers_path', None)
+        if dpath and not self.model_config.get('transformer_path', None) and os.path.isdir(os.path.join(dpath, 'transformer')):
+            self.model_config['transformer_path'] = os.path.join(dpath, 'transformer')
+            cfg_json = os.path.join(dpath, 'transformer', 'config.json')
+            if tcfg is None and os.path.exists(cfg_json):
+                tcfg = cfg_json
         if isinstance(tcfg, str):
             with open(tcfg) as f:
-                tcfg = json.load(f)
+                tcfg = {k: v for k, v in json.load(f).items() if k in FLUX_DEV_CONFIG}
         self.tcfg = dict(FLUX_DEV_CONFIG, **(tcfg or {}))
         device = self.model_config.get("device", device)      # (tests: "cpu" with the kernel test doubles)
         self.dtype, self.device = dtype, device
@@ -345,7 +353,7 @@ class FluxPipeline(PluginSurface):
             # stage are ever materialised (12 B parameters do not fit eight times on the host, and need not).
             self.transformer = None
             return
-        self.transformer = FluxTransformer2DModel(tcfg, dtype=dtype, device=device)
+        self.transformer = FluxTransformer2DModel(self.tcfg, dtype=dtype, device=device)
         if path := self.model_config.get('transformer_path', None):
             self.load_transformer_weights(path)
         if self.model_config.get('bypass_guidance_embedding', False):       # models/flux.py:132-150,191-194

@@ -93,3 +93,21 @@ def test_wan_accepts_comfyui_keys_in_one_file(tmp_path):
     for spec in lazy.to_layers():
         for n, p in spec.build().named_parameters():
             assert torch.equal(p, sd[p.original_name]), p.original_name
+
+
+def test_diffusers_directory_layout(tmp_path):
+    """models/flux.py:174-191: `diffusers_path/transformer/` holds the shards and a config.json naming the architecture"""
+    import json
+    torch.manual_seed(1)
+    cfg = dict(FLUX_CFG, guidance_embeds=False, _class_name='FluxTransformer2DModel', patch_size=1)
+    src = _flux(transformer_config={k: v for k, v in cfg.items() if not k.startswith('_') and k != 'patch_size'})
+    sd = {k: v.detach().clone() for k, v in src.transformer.state_dict().items()}
+    assert not any('guidance_embedder' in k for k in sd)
+    d = tmp_path / 'flux' / 'transformer'
+    _save_sharded(sd, str(d))
+    with open(d / 'config.json', 'w') as f:
+        json.dump(cfg, f)
+    from diffusion_pipe_b200.flux import FluxPipeline
+    m = FluxPipeline({'model': {'dtype': 'bfloat16', 'guidance': 1.0, 'device': 'cpu', 'diffusers_path': str(tmp_path / 'flux')}})
+    assert m.tcfg['num_layers'] == 2 and m.tcfg['guidance_embeds'] is False
+    assert all(torch.equal(p, sd[n]) for n, p in m.transformer.named_parameters()) and len(sd) == len(list(m.transformer.parameters()))
