@@ -604,9 +604,13 @@ class WanPipeline(PluginSurface):
         if dtype != torch.bfloat16:
             raise NotImplementedError('the sm_100a Wan path computes in bf16 (model.dtype must be bfloat16)')
         tcfg = self.model_config.get('transformer_config', None)
+        if tcfg is None:
+            tcfg = self._find_checkpoint_config()
         if isinstance(tcfg, str):
             with open(tcfg) as f:
-                tcfg = json.load(f)
+                tcfg = {k: v for k, v in json.load(f).items() if k in WAN_T2V_14B_CONFIG}
+            if tcfg.get('model_type') == 'i2v' and not self._checkpoint_has('blocks.0.cross_attn.k_img.weight'):
+                tcfg['model_type'] = 'i2v_v2'            # Wan2.2 I2V ships model_type 'i2v' without the CLIP branch (wan.py:131-135)
         self.tcfg = dict(WAN_T2V_14B_CONFIG, **(tcfg or {}))
         self.model_type = self.tcfg['model_type']
         if self.model_type == 'i2v_v2' and 'in_dim' not in (tcfg or {}):
@@ -623,6 +627,30 @@ class WanPipeline(PluginSurface):
             if path := self.model_config.get('transformer_path', None):
                 self.load_transformer_weights(path)
             self.transformer.train()
+
+    def _find_checkpoint_config(self):
+        """models/wan/wan.py:80-97: `transformer_path` is a directory holding config.json next to its shards, or a single
+        file whose config.json sits in `ckpt_path` (Wan2.2: `ckpt_path/low_noise_model`).  None when no checkpoint is named
+        (synthetic runs: the 14B t2v defaults)."""
+        import os
+        mc = self.model_config
+        ckpt, tp = mc.get('ckpt_path', None), mc.get('transformer_path', None)
+        tp = tp or ckpt
+        if tp is None:
+            return None
+        if tp == ckpt and os.path.isdir(tp):
+            mc.setdefault('transformer_path', tp)
+        cands = [os.path.join(tp, 'config.json')] if os.path.isdir(tp) else \
+            ([os.path.join(ckpt, 'config.json'), os.path.join(ckpt, 'low_noise_model', 'config.json')] if ckpt else [])
+        for c in cands:
+            if os.path.exists(c):
+                return c
+        return None
+
+    def _checkpoint_has(self, key):
+        from .flux import FluxPipeline
+        path = self.model_config.get('transformer_path', None)
+        return bool(path) and key in FluxPipeline._weight_index(path)
 
     def load_transformer_weights(self, path):
         from .flux import FluxPipeline

@@ -111,3 +111,21 @@ def test_diffusers_directory_layout(tmp_path):
     m = FluxPipeline({'model': {'dtype': 'bfloat16', 'guidance': 1.0, 'device': 'cpu', 'diffusers_path': str(tmp_path / 'flux')}})
     assert m.tcfg['num_layers'] == 2 and m.tcfg['guidance_embeds'] is False
     assert all(torch.equal(p, sd[n]) for n, p in m.transformer.named_parameters()) and len(sd) == len(list(m.transformer.parameters()))
+
+
+def test_wan_reads_the_checkpoints_config_json(tmp_path):
+    """models/wan/wan.py:80-135: the architecture comes from the config.json beside the shards; a Wan2.2 I2V checkpoint says
+    model_type 'i2v' but has no CLIP image branch -> 'i2v_v2'"""
+    import json
+    from diffusion_pipe_b200.wan import WanPipeline
+    small = {'dim': 256, 'ffn_dim': 512, 'num_heads': 2, 'num_layers': 1, 'text_dim': 64, 'text_len': 16}
+    src = WanPipeline({'model': {'dtype': 'bfloat16', 'device': 'cpu', 'transformer_config': dict(small, model_type='i2v_v2')}})
+    sd = {k: v.detach().clone() for k, v in src.transformer.state_dict().items()}
+    assert sd['patch_embedding.weight'].shape[1] == 36
+    d = tmp_path / 'wan22_i2v'
+    _save_sharded(sd, str(d))
+    with open(d / 'config.json', 'w') as f:
+        json.dump(dict(small, model_type='i2v', in_dim=36, out_dim=16, freq_dim=256, eps=1e-6, _class_name='WanModel'), f)
+    m = WanPipeline({'model': {'dtype': 'bfloat16', 'device': 'cpu', 'ckpt_path': str(d)}})
+    assert m.model_type == 'i2v_v2' and m.tcfg['dim'] == 256 and m.tcfg['num_layers'] == 1
+    assert all(torch.equal(p, sd[n]) for n, p in m.transformer.named_parameters())
