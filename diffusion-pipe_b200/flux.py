@@ -435,6 +435,9 @@ class FluxPipeline(PluginSurface):
     def _copy_weights(index, named_params, what):
         """fills every (name, parameter) from the checkpoint; a parameter the checkpoint does not have raises"""
         from safetensors import safe_open
+        named_params = list(named_params)
+        if 'img_in.weight' in index and 'x_embedder.weight' not in index:
+            return FluxPipeline._copy_bfl_weights(index, named_params, what)
         by_file, missing = {}, []
         for name, p in named_params:
             if name in index:
@@ -451,6 +454,26 @@ class FluxPipeline(PluginSurface):
                         if tuple(v.shape) != tuple(p.shape):
                             raise RuntimeError(f'{name}: checkpoint shape {tuple(v.shape)} != parameter shape {tuple(p.shape)}')
                         p.copy_(v)
+
+    @staticmethod
+    def _copy_bfl_weights(index, named_params, what):
+        """the checkpoint is in the BFL / ComfyUI layout (img_in, double_blocks.N.img_attn.qkv, ...): every parameter is a
+        row range of a BFL tensor (flux_export.from_bfl_plan)"""
+        from safetensors import safe_open
+        from .flux_export import from_bfl_plan, read_bfl_tensor
+        plan = from_bfl_plan([(n, tuple(p.shape)) for n, p in named_params])
+        missing = sorted(n for n, (bk, _, _, _) in plan.items() if bk not in index)
+        if missing:
+            raise RuntimeError(f'{len(missing)} parameters of {what} missing from the checkpoint, e.g. {missing[:3]}')
+        with torch.no_grad():
+            for name, p in named_params:
+                bk, off, rows, swap = plan[name]
+                f, key = index[bk]
+                with safe_open(f, framework='pt') as h:
+                    v = read_bfl_tensor(h.get_tensor(key), off, rows, swap)
+                if tuple(v.shape) != tuple(p.shape):
+                    raise RuntimeError(f'{name}: checkpoint shape {tuple(v.shape)} != parameter shape {tuple(p.shape)}')
+                p.copy_(v)
 
     def load_transformer_weights(self, path):
         """Loads a checkpoint in the reference's parameter names into the whole (eagerly built) transformer."""
@@ -537,8 +560,15 @@ class FluxPipeline(PluginSurface):
                         p.copy_(state[key].to(p.dtype))
 
     def save_model(self, save_dir, state_dict):
-        """full-model export in the diffusers layout this engine trains in (the reference re-lays Flux out to BFL names
-        on top of this, models/flux.py:257-288 — outside the hot path)"""
+        """full-model export: the BFL / ComfyUI layout the reference writes (models/flux.py:257-288; flux_export.py), or the
+        diffusers names this engine trains in with `[model] export_layout = 'diffusers'`"""
+        if self.model_config.get('export_layout', 'bfl') == 'bfl':
+            from .flux_export import to_bfl
+            state_dict = to_bfl(state_dict)
+        FluxPipeline.write_model_file(save_dir, state_dict)
+
+    @staticmethod
+    def write_model_file(save_dir, state_dict):
         from safetensors.torch import save_file
         os.makedirs(save_dir, exist_ok=True)
         save_file({k: v.contiguous() for k, v in state_dict.items()}, os.path.join(save_dir, 'model.safetensors'),

@@ -302,7 +302,7 @@ class QwenImagePipeline(PluginSurface):
     def save_model(self, save_dir, state_dict):
         """models/qwen_image.py:296-297"""
         from .flux import FluxPipeline
-        FluxPipeline.save_model(self, save_dir, state_dict)
+        FluxPipeline.write_model_file(save_dir, state_dict)
 
     def configure_adapter(self, adapter_config):
         from .flux import FluxPipeline

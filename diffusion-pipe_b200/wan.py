@@ -662,7 +662,7 @@ class WanPipeline(PluginSurface):
     def save_model(self, save_dir, state_dict):
         """models/wan/wan.py:264-265"""
         from .flux import FluxPipeline
-        FluxPipeline.save_model(self, save_dir, state_dict)
+        FluxPipeline.write_model_file(save_dir, state_dict)
 
     def configure_adapter(self, adapter_config):
         from .flux import FluxPipeline

@@ -223,7 +223,7 @@ def test_reference_loader_and_saver_drive_the_engine(world):
             assert os.path.exists(os.path.join(run, 'step2', 'config.toml')) and not os.path.exists(os.path.join(run, 'step2', 'tmp'))
         a = load_file(os.path.join(d, 'run_reference', 'step2', 'model.safetensors'))
         b = load_file(os.path.join(d, 'run_mine', 'step2', 'model.safetensors'))
-        assert set(a) == set(b) and 'transformer_blocks.0.attn.to_q.weight' in a and 'single_transformer_blocks.0.proj_out.weight' in a
+        assert set(a) == set(b) and 'double_blocks.0.img_attn.qkv.weight' in a and 'single_blocks.0.linear2.weight' in a   # BFL layout
         assert all(torch.equal(a[k], b[k]) for k in a)
         if world == 1:
             return                                                      # (the resume leg runs once, on the 2-stage pipeline)

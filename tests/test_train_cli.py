@@ -147,8 +147,9 @@ betas = [0.9, 0.99]
     # the Saver exported the full model at step 2 (utils/saver.py:87-106): one file, reference parameter names, the TOML
     from safetensors.torch import load_file
     sd = load_file(os.path.join(run_dir, 'step2', 'model.safetensors'))
-    assert 'transformer_blocks.0.attn.to_q.weight' in sd and 'single_transformer_blocks.0.proj_out.weight' in sd
-    assert sd['transformer_blocks.0.attn.to_k.weight'].shape == (256, 256)
+    # ... in the BFL / ComfyUI layout the reference's Flux export uses (models/flux.py:257-288): fused [q; k; v] per stream
+    assert 'double_blocks.0.img_attn.qkv.weight' in sd and 'single_blocks.0.linear2.weight' in sd and 'img_in.weight' in sd
+    assert sd['double_blocks.0.img_attn.qkv.weight'].shape == (768, 256)
     assert os.path.exists(os.path.join(run_dir, 'step2', 'cfg.toml')) and not os.path.exists(os.path.join(run_dir, 'step2', 'tmp'))
     # resume continues at step 3
     write_cfg(3)
