@@ -575,11 +575,30 @@ class FluxPipeline(PluginSurface):
                   metadata={'format': 'pt'})
 
     def save_adapter(self, save_dir, peft_state_dict):
-        """models/flux.py:231-236: the adapter factors as safetensors (PEFT state-dict names)"""
+        """models/flux.py:231-236: diffusers' `save_lora_weights(save_dir, transformer_lora_layers=...)` — one file
+        `pytorch_lora_weights.safetensors` whose keys carry the `transformer.` component prefix (diffusers' convention,
+        recalled: diffusers is absent); load_adapter_weights strips it again"""
+        FluxPipeline.write_adapter_file(save_dir, {'transformer.' + k: v for k, v in peft_state_dict.items()},
+                                        'pytorch_lora_weights.safetensors')
+
+    @staticmethod
+    def write_adapter_file(save_dir, state_dict, filename='adapter_model.safetensors'):
         from safetensors.torch import save_file
         os.makedirs(save_dir, exist_ok=True)
-        save_file({k: v.contiguous() for k, v in peft_state_dict.items()}, os.path.join(save_dir, 'adapter_model.safetensors'),
-                  metadata={'format': 'pt'})
+        save_file({k: v.contiguous() for k, v in state_dict.items()}, os.path.join(save_dir, filename), metadata={'format': 'pt'})
+
+    def write_peft_config(self, save_dir, peft_state_dict):
+        """`peft_config.save_pretrained(save_dir)` of the Qwen-Image / Wan exports (models/qwen_image.py:291,
+        models/wan/wan.py:259): adapter_config.json with the fields of the LoraConfig the reference builds
+        (models/base.py:272-303: r, lora_alpha = r, dropout, bias 'none', the adapted Linear modules)"""
+        ac = self.adapter_config or {}
+        mods = sorted({re.sub(r'\.lora_[AB]\.weight$', '', k) for k in peft_state_dict})
+        cfg = {'peft_type': 'LORA', 'r': int(ac.get('rank', 0)), 'lora_alpha': int(ac.get('alpha', ac.get('rank', 0))),
+               'lora_dropout': float(ac.get('dropout', 0.0)), 'bias': 'none', 'target_modules': mods, 'inference_mode': True,
+               'base_model_name_or_path': None, 'task_type': None}
+        os.makedirs(save_dir, exist_ok=True)
+        with open(os.path.join(save_dir, 'adapter_config.json'), 'w') as f:
+            json.dump(cfg, f, indent=2)
 
     def get_param_groups(self, parameters):
         return [{'params': parameters}]

@@ -680,7 +680,8 @@ class WanPipeline(PluginSurface):
     def save_adapter(self, save_dir, peft_state_dict):
         """models/wan/wan.py:258-262 (ComfyUI format: keys prefixed with diffusion_model.)"""
         from .flux import FluxPipeline
-        FluxPipeline.save_adapter(self, save_dir, {'diffusion_model.' + k: v for k, v in peft_state_dict.items()})
+        FluxPipeline.write_peft_config(self, save_dir, peft_state_dict)
+        FluxPipeline.write_adapter_file(save_dir, {'diffusion_model.' + k: v for k, v in peft_state_dict.items()})
 
     def get_param_groups(self, parameters):
         return [{'params': parameters}]

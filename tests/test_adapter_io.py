@@ -40,6 +40,7 @@ def test_saved_flux_adapter_initialises_eager_and_lazy_models(tmp_path):
     want = _randomise_factors(src.transformer, 3)
     assert len(want) == 40
     src.save_adapter(str(tmp_path / 'ad'), lora.lora_state_dict(src.transformer))
+    assert os.listdir(tmp_path / 'ad') == ['pytorch_lora_weights.safetensors']        # diffusers' save_lora_weights layout
     # eager model
     dst = _flux()
     dst.configure_adapter(ADAPTER)
@@ -74,6 +75,9 @@ def test_comfyui_prefix_and_fp8_base(tmp_path):
     src.save_adapter(str(tmp_path / 'q'), lora.lora_state_dict(src.transformer))
     from safetensors.torch import load_file
     assert all(k.startswith('diffusion_model.') for k in load_file(str(tmp_path / 'q' / 'adapter_model.safetensors')))
+    import json
+    pc = json.load(open(tmp_path / 'q' / 'adapter_config.json'))                 # peft_config.save_pretrained (models/qwen_image.py:291)
+    assert pc['peft_type'] == 'LORA' and pc['r'] == pc['lora_alpha'] == 16 and 'transformer_blocks.0.attn.to_q' in pc['target_modules'] and len(pc['target_modules']) == 14
     dst = QwenImagePipeline({'model': {'dtype': 'bfloat16', 'device': 'cpu', 'transformer_dtype': 'float8', 'transformer_config': cfg}})
     dst.configure_adapter(ADAPTER)
     dst.load_adapter_weights(str(tmp_path / 'q'))

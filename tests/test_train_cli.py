@@ -163,9 +163,9 @@ betas = [0.9, 0.99]
     (tmp_path / 'runs2').mkdir()
     cfgp.write_text(cfgp.read_text().replace(f"{tmp_path}/runs'", f"{tmp_path}/runs2'"))
     run_dir3 = T.main(['--config', str(cfgp)])
-    ad = load_file(os.path.join(run_dir3, 'step1', 'adapter_model.safetensors'))
+    ad = load_file(os.path.join(run_dir3, 'step1', 'pytorch_lora_weights.safetensors'))      # diffusers' save_lora_weights layout (models/flux.py:231-236)
     assert ad and all('.lora_A.' in k or '.lora_B.' in k for k in ad)
-    assert 'transformer_blocks.0.attn.to_q.lora_A.weight' in ad and ad['transformer_blocks.0.attn.to_q.lora_A.weight'].shape == (16, 256)
+    assert 'transformer.transformer_blocks.0.attn.to_q.lora_A.weight' in ad and ad['transformer.transformer_blocks.0.attn.to_q.lora_A.weight'].shape == (16, 256)
     # ... and runs on a float8 base when [model] asks for it (reference: transformer_dtype = 'float8'), checkpoint + resume included
     cfgp = write_cfg(2, "[adapter]\ntype = 'lora'\nrank = 16\n")
     (tmp_path / 'runs3').mkdir()
@@ -173,7 +173,7 @@ betas = [0.9, 0.99]
     run_dir4 = T.main(['--config', str(cfgp)])
     lines = [json.loads(l) for l in open(os.path.join(run_dir4, 'metrics.jsonl'))]
     assert [l['x'] for l in lines if l['tag'] == 'train/loss'] == [1, 2]
-    assert os.path.exists(os.path.join(run_dir4, 'step2', 'adapter_model.safetensors'))
+    assert os.path.exists(os.path.join(run_dir4, 'step2', 'pytorch_lora_weights.safetensors'))
     cfgp.write_text(cfgp.read_text().replace('max_steps = 2', 'max_steps = 3'))
     assert T.main(['--config', str(cfgp), '--resume_from_checkpoint']) == run_dir4
     lines = [json.loads(l) for l in open(os.path.join(run_dir4, 'metrics.jsonl'))]
@@ -183,7 +183,7 @@ betas = [0.9, 0.99]
     (tmp_path / 'runs4').mkdir()
     cfgp.write_text(cfgp.read_text().replace(f"{tmp_path}/runs'", f"{tmp_path}/runs4'"))
     run_dir5 = T.main(['--config', str(cfgp)])
-    assert os.path.exists(os.path.join(run_dir5, 'step1', 'adapter_model.safetensors'))
+    assert os.path.exists(os.path.join(run_dir5, 'step1', 'pytorch_lora_weights.safetensors'))
 
 
 def test_optimizer_factory_follows_the_reference_rules():
