@@ -3,7 +3,7 @@ in fp8 and widened into the shared operand scratch in front of every GEMM (lora.
 csrc/fp8_dequant.cu).  Kernel wrappers are the PyTorch test doubles; the oracle is the PEFT-style restatement with the
 same weights rounded through fp8 by the reference's own per-family selection rule (oracle/lora_ref.py: FP8_RULES, citing
 models/flux.py:203-205, models/qwen_image.py:261-263, models/wan/wan.py:233-235).  The code table of the real kernel is
-checked against torch in tests/test_abi.py; the kernel itself in tests/test_zz_fp8_gpu.py."""
+checked against torch in tests/test_abi.py; the kernel itself in tests/test_zz_first_hardware_run_gpu.py."""
 import os
 import sys
 

@@ -1,0 +1,126 @@
+"""GPU tests that were written after the round's GPU budget was spent: their first hardware run is the driver's round-end tier,
+so this file sorts last (`-x` must not let a first-run failure hide the suite that already ran green on B200).  Each has a
+CPU twin on the kernel test doubles that passes.
+
+1. fp8 storage of the frozen base under LoRA (`transformer_dtype = 'float8'`) on the real kernels — the widening kernel
+(csrc/fp8_dequant.cu) bit-exact against torch's cast, and a small Flux model end to end against the oracle whose base weights
+were rounded through fp8 by the reference's selection rule.  CPU twins: tests/test_lora_fp8_host_logic.py (host logic on
+kernel doubles) and tests/test_abi.py (code tables).
+2. Qwen-Image with prompts of different lengths in one micro-batch (CPU twins: tests/test_qwen_cpu.py,
+   tests/test_lora_host_logic.py::test_qwen_lora_with_ragged_prompts_matches_oracle).
+3. Wan2.2 I2V (CPU twin: tests/test_wan_host_logic.py::test_wan22_i2v_forward_backward_matches_oracle)."""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize('dt', [torch.float8_e4m3fn, torch.float8_e5m2])
+def test_widening_kernel_is_bit_exact(dt):
+    from diffusion_pipe_b200 import ops
+    torch.manual_seed(0)
+    for rows, cols, pad in ((256, 256, 0), (300, 3072, 48), (1, 16, 8), (21504, 3072, 64)):
+        codes = torch.randint(0, 256, (rows, cols), dtype=torch.uint8, device='cuda')
+        n = min(256, rows * cols)
+        codes.view(-1)[:n] = torch.arange(n, dtype=torch.uint8, device='cuda')       # every code occurs (when there is room)
+        src = codes.view(dt)
+        dst = torch.full((rows, cols + pad), 7.0, dtype=torch.bfloat16, device='cuda')
+        out = ops.fp8_to_bf16(src, dst[:, :cols])
+        torch.cuda.synchronize()
+        want = src.to(torch.bfloat16)
+        nan = torch.isnan(want.float())
+        assert torch.equal(torch.isnan(out.float()), nan)
+        assert torch.equal(out.view(torch.int16)[~nan], want.view(torch.int16)[~nan])
+        if pad:
+            assert bool((dst[:, cols:] == 7.0).all())                      # columns outside the matrix are not touched
+    with pytest.raises(Exception):
+        ops.fp8_to_bf16(torch.zeros(4, 24, device='cuda').to(dt), torch.empty(4, 24, dtype=torch.bfloat16, device='cuda'))
+
+
+def test_flux_lora_on_an_fp8_base_matches_oracle():
+    import test_lora_fp8_host_logic as H
+    from oracle import flux_ref as R
+    from oracle import lora_ref
+    model, ref = H.flux_pair('float8', device='cuda')
+    stored = {n for n, p in model.transformer.named_parameters() if p.dtype == torch.float8_e4m3fn}
+    assert stored == lora_ref.round_base_through_fp8(ref, 'flux') and len(stored) == 20
+    feats, label = H.flux_batch(1)
+    loss = H._run(model.to_layers(), model.get_loss_fn(), feats, label, dev='cuda')
+    rloss = H._run(R.to_layers(ref), R.loss_fn, feats, label)
+    assert abs(loss.item() - rloss.item()) / abs(rloss.item()) <= 1e-3, (loss.item(), rloss.item())
+    H._check_grads(model.transformer, ref)
+    rp = dict(ref.named_parameters())
+    site = model.transformer.single_transformer_blocks[0].lora['lin1']
+    want = torch.cat([rp[l.weight.original_name] for l in site.lins])
+    assert torch.equal(site.w_fwd[:, :site.K].float().cpu(), want)           # the operand the GEMM reads, bit for bit
+
+
+def test_ragged_prompts_in_one_micro_batch_match_the_masked_oracle():
+    """the bool key mask (models/qwen_image.py:472-476): prompts of 5 and 12 tokens in one micro-batch; every sample
+    attends over its own prompt + all image tokens (gathered dense problems on the same attention kernels)"""
+    from oracle import flux_ref as R
+    from oracle import qwen_ref as Q
+    import test_qwen_gpu as QG
+    model, ref = QG._make()
+    ref.set_emulate_bf16(True)
+    g = torch.Generator().manual_seed(9)
+    lat, noise = torch.randn(2, 16, 1, 16, 24, generator=g), torch.randn(2, 16, 1, 16, 24, generator=g)
+    pe = [torch.randn(5, 64, generator=g).bfloat16().float(), torch.randn(12, 64, generator=g).bfloat16().float()]
+    feats, (target, _) = Q.prepare_inputs(lat, pe, torch.tensor([0.3, 0.6]), noise)
+    assert not bool(feats[2].all())
+    label = (target, torch.tensor([]))
+    x = tuple(f.cuda() for f in feats)
+    for layer in model.to_layers():
+        x = layer(x)
+    loss = model.get_loss_fn()(x, tuple(l.cuda() for l in label))
+    loss.backward()
+    y = tuple(f.clone() for f in feats)
+    for layer in Q.to_layers(ref):
+        y = layer(y)
+    rloss = R.loss_fn(y, label)
+    rloss.backward()
+    assert abs(loss.item() - rloss.item()) / abs(rloss.item()) <= 1e-3, (loss.item(), rloss.item())
+    rg = {n: p.grad for n, p in ref.named_parameters()}
+    bad = []
+    for n, p in model.transformer.named_parameters():
+        if rg[n] is None:
+            continue
+        err = ((p.grad.float().cpu() - rg[n]).norm() / (rg[n].norm() + 1e-12)).item()
+        if err > 5e-2:
+            bad.append((err, n))
+    assert not bad, sorted(bad, reverse=True)[:8]
+
+
+def test_wan22_i2v_matches_oracle():
+    """model_type 'i2v_v2' (Wan2.2 I2V): [x | first-frame mask | y] through a K = 144 patch-embedding GEMM, real kernels;
+    CPU twin on kernel doubles: tests/test_wan_host_logic.py::test_wan22_i2v_forward_backward_matches_oracle"""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import test_wan_host_logic as H
+    from oracle import flux_ref as R
+    from oracle import wan_ref as W
+    model, ref = H.make_i2v_pair(device='cuda')
+    feats, label = H.i2v_batch(model)
+    x = tuple(f.cuda() for f in feats)
+    for layer in model.to_layers():
+        x = layer(x)
+    loss = model.get_loss_fn()(x, tuple(l.cuda() for l in label))
+    loss.backward()
+    y = tuple(f.clone() for f in feats)
+    for layer in W.to_layers(ref):
+        y = layer(y)
+    rloss = R.loss_fn(y, label)
+    rloss.backward()
+    assert abs(loss.item() - rloss.item()) / abs(rloss.item()) <= 1e-3, (loss.item(), rloss.item())
+    rg = {n: p.grad for n, p in ref.named_parameters()}
+    bad = []
+    for n, p in model.transformer.named_parameters():
+        err = ((p.grad.float().cpu() - rg[n]).norm() / (rg[n].norm() + 1e-12)).item()
+        if err > 5e-2:
+            bad.append((err, n))
+    assert not bad, sorted(bad, reverse=True)[:8]
