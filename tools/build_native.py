@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
             if r.returncode != 0:
                 raise RuntimeError('nvcc failed for ' + cmd[-3])
     if jobs or force or not os.path.exists(OUT):
-        cmd = [NVCC, '-shared', '-o', OUT] + objs
+        cmd = [NVCC, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', OUT] + objs      # (the arch also names the link stub)
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
