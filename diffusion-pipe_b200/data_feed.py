@@ -20,6 +20,7 @@ Pinned by tests/golden/datafeed_traces.json, produced by executing the reference
 import math
 import os
 import random
+import re
 from collections import defaultdict
 
 import numpy as np
@@ -308,3 +309,92 @@ def get_data_iterator_for_step(dataloader, engine, num_micro_batches=None):
         return None
     it = iter(dataloader)
     return iter([next(it) for _ in range(n)])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's on-disk cache (utils/cache.py) — read side.  The north star leaves latent / text-embedding caching to
+# the reference; this is how the hot path consumes what it wrote.
+# ---------------------------------------------------------------------------------------------------------------------
+class ReferenceCache:
+    """Read-only view of one `utils.cache.Cache` directory: `metadata.db` (sqlite: `items(shard, shard_index)` in insertion
+    order, one `shard_<n>(offset, size)` table per shard) + `shard_<n>.bin` (concatenated `torch.save` blobs)
+    (utils/cache.py:10-36,40-76,107-128).  Nothing is written and the fingerprint is not checked: regenerating a stale
+    cache is the caching stage's job."""
+
+    def __init__(self, path):
+        import sqlite3
+        self.path = str(path)
+        db = os.path.join(self.path, 'metadata.db')
+        if not os.path.exists(db):
+            raise FileNotFoundError(f'{db}: not a cache directory written by the reference (utils/cache.py)')
+        con = sqlite3.connect(f'file:{db}?mode=ro', uri=True)
+        try:
+            self.items = con.execute('SELECT shard, shard_index FROM items').fetchall()
+            self.shard_metadata = {}
+            for (name,) in con.execute("SELECT name FROM sqlite_master WHERE type = 'table'").fetchall():
+                if name.startswith('shard_'):
+                    self.shard_metadata[int(name.split('_')[-1])] = con.execute(f'SELECT offset, size FROM {name}').fetchall()
+            row = con.execute('SELECT value FROM fingerprint').fetchone()
+            self.fingerprint = row[0] if row else None
+        finally:
+            con.close()
+        self._files = {}
+
+    def __len__(self):
+        return len(self.items)
+
+    def __getitem__(self, idx):
+        import io
+        shard, k = self.items[idx]
+        offset, size = self.shard_metadata[shard][k]
+        f = self._files.get(shard)
+        if f is None:
+            f = self._files[shard] = open(os.path.join(self.path, f'shard_{shard}.bin'), 'rb')
+        f.seek(offset)
+        return torch.load(io.BytesIO(f.read(size)), map_location='cpu', weights_only=False)
+
+    def __getstate__(self):            # DataLoader workers reopen their own file handles
+        d = dict(self.__dict__)
+        d['_files'] = {}
+        return d
+
+
+class ReferenceCacheBucket:
+    """One size-bucket cache directory of the reference (`<dataset>/cache/<model>/cache_<w>x<h>x<frames>/`,
+    utils/dataset.py:217): `latents/` plus `text_embeddings_<i>/` caches, merged per example the way
+    SizeBucketDataset.__getitem__ does (utils/dataset.py:309-333) for the plain layout — one caption per item, no
+    unconditional dropout — where item i of every cache belongs to example i (the caches are filled in the same, already
+    shuffled, order: utils/dataset.py:212,233-243,178-200).  Datasets with several captions per image or caption JSON
+    files need the reference's metadata tables and are not read here."""
+
+    def __init__(self, path, num_repeats=1):
+        self.path = str(path)
+        self.latents = ReferenceCache(os.path.join(self.path, 'latents'))
+        names = sorted((d for d in os.listdir(self.path) if d.startswith('text_embeddings_') and os.path.isdir(os.path.join(self.path, d))),
+                       key=lambda d: int(d.rsplit('_', 1)[1]))
+        self.text = [ReferenceCache(os.path.join(self.path, d)) for d in names]
+        for d, c in zip(names, self.text):
+            if len(c) != len(self.latents):
+                raise RuntimeError(f'{self.path}/{d} holds {len(c)} items for {len(self.latents)} latents: several captions per '
+                                   'image (or a partial cache) need the reference\'s metadata tables')
+        self.num_repeats = num_repeats
+        m = re.fullmatch(r'cache_(\d+)x(\d+)x(\d+)', os.path.basename(os.path.normpath(self.path)))
+        first = self.latents[0]['latents'] if len(self.latents) else None
+        if m:
+            w, h, frames = (int(x) for x in m.groups())
+        else:
+            h, w = (first.shape[-2] * 8, first.shape[-1] * 8) if first is not None else (0, 0)
+            frames = first.shape[-3] if first is not None and first.dim() == 4 else 1
+        self.size_bucket = (round(w / h, 3) if h else 1.0, w, h, frames)
+
+    def __len__(self):
+        return int(len(self.latents) * self.num_repeats)
+
+    def __getitem__(self, idx):
+        i = idx % len(self.latents)
+        ex = dict(self.latents[i])
+        for c in self.text:
+            ex.update(c[i])
+        ex.setdefault('mask', None)
+        ex.setdefault('caption', '')
+        return ex

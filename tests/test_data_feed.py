@@ -188,3 +188,40 @@ def test_sync_epoch_is_a_pure_function_of_the_step_count(golden):
             middle.sync_epoch()
             assert middle.epoch == puller.epoch
         assert puller.epoch == 2
+
+
+def test_reference_cache_directories_are_read_as_the_reference_wrote_them(golden_dir):
+    """tests/golden/ref_cache/ was written by the reference's own utils/cache.py (tests/golden/make_golden_cache.py): the
+    read side (data_feed.ReferenceCache / ReferenceCacheBucket) returns the same items in the same order, across shards,
+    and the cached examples feed the train CLI's dataset path"""
+    import pickle
+    import sys
+    sys.path.insert(0, golden_dir)
+    sys.path.insert(0, os.path.dirname(golden_dir).rsplit('/tests', 1)[0])
+    from synth import synth_tensor
+    from diffusion_pipe_b200 import data_feed
+    root = os.path.join(golden_dir, 'ref_cache')
+    lat = data_feed.ReferenceCache(os.path.join(root, 'cache_64x64x1', 'latents'))
+    assert len(lat) == 5 and lat.fingerprint == 'fixture-latents' and sorted(lat.shard_metadata) == [0, 1]      # two shards
+    assert lat.items == [(0, 0), (0, 1), (0, 2), (1, 0), (1, 1)]
+    bucket = data_feed.ReferenceCacheBucket(os.path.join(root, 'cache_64x64x1'), num_repeats=2)
+    assert len(bucket) == 10 and bucket.size_bucket == (1.0, 64, 64, 1)
+    for i in (0, 3, 4, 7):
+        ex = bucket[i]
+        j = i % 5
+        assert torch.equal(ex['latents'], synth_tensor((16, 8, 8), 1100 + j, 1.0)) and ex['mask'] is None and ex['caption'] == ''
+        assert torch.equal(ex['t5_embed'], synth_tensor((6, 32), 1200 + j, 1.0).bfloat16())
+        assert torch.equal(ex['clip_embed'], synth_tensor((16,), 1300 + j, 1.0).bfloat16())
+    clone = pickle.loads(pickle.dumps(bucket))                      # DataLoader workers get a copy without open files
+    assert torch.equal(clone[4]['latents'], bucket[4]['latents'])
+    with pytest.raises(FileNotFoundError):
+        data_feed.ReferenceCache(root)
+    # through the driver's dataset config: a bucket directory, or the directory that holds the buckets
+    import train as T
+    for path in (os.path.join(root, 'cache_64x64x1'), root):
+        buckets = T.load_size_buckets({'directory': [{'cache_dir': path, 'num_repeats': 1}]})
+        assert len(buckets) == 1 and len(buckets[0]) == 5
+        ds = data_feed.BatchedDataset(buckets, {})
+        ds.post_init(0, 1, {None: 1}, 2, {None: 1})
+        batch = ds[0]
+        assert batch['latents'].shape == (2, 16, 8, 8) and batch['t5_embed'].shape == (2, 6, 32) and batch['mask'] is None

@@ -203,3 +203,37 @@ def test_optimizer_factory_follows_the_reference_rules():
         T.make_optimizer_factory({'optimizer': {'type': 'stableadamw', 'lr': 1e-4}}, M())([w])
     sgd = T.make_optimizer_factory({'optimizer': {'type': 'sgd', 'lr': 0.1}}, M())([w])
     assert isinstance(sgd, torch.optim.SGD)
+
+
+def test_train_cli_trains_from_a_cache_the_reference_wrote(tmp_path, monkeypatch, golden_dir):
+    """[[directory]] cache_dir = ...: the examples come from tests/golden/ref_cache/, written by the reference's own
+    utils/cache.py — the caching stage is unchanged, the hot path consumes its files"""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import kernel_doubles
+    from diffusion_pipe_b200 import ops
+    kernel_doubles.install(monkeypatch, ops)
+    ds = tmp_path / 'ds.toml'
+    ds.write_text(f"[[directory]]\ncache_dir = '{golden_dir}/ref_cache'\nnum_repeats = 1\n")
+    cfgp = tmp_path / 'cfg.toml'
+    cfgp.write_text(f"""
+output_dir = '{tmp_path}/runs'
+dataset = '{ds}'
+epochs = 2
+micro_batch_size_per_gpu = 1
+gradient_accumulation_steps = 2
+save_every_n_epochs = 1
+eval_before_first_step = false
+[model]
+type = 'flux'
+dtype = 'bfloat16'
+device = 'cpu'
+transformer_config = {{ num_attention_heads = 2, num_layers = 1, num_single_layers = 1, joint_attention_dim = 32, pooled_projection_dim = 16 }}
+[optimizer]
+type = 'adamw'
+lr = 1e-4
+""")
+    run_dir = T.main(['--config', str(cfgp)])
+    lines = [json.loads(l) for l in open(os.path.join(run_dir, 'metrics.jsonl'))]
+    # 5 cached examples, global batch 2 -> 2 steps per epoch (the remainder is dropped, utils/dataset.py:350-360), 2 epochs
+    assert [l['x'] for l in lines if l['tag'] == 'train/loss'] == [1, 2, 3, 4]
+    assert os.path.exists(os.path.join(run_dir, 'epoch1', 'model.safetensors')) and os.path.exists(os.path.join(run_dir, 'epoch2', 'model.safetensors'))

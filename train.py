@@ -196,6 +196,16 @@ def load_size_buckets(dataset_config):
         frames = syn.get('frames', 33) if syn.get('model', 'flux') == 'wan' else 1
         out.append(CachedExamples(synthetic_examples(syn), (1.0, res, res, frames), syn.get('num_repeats', 1)))
     for d in dataset_config.get('directory', []):
+        if 'cache_dir' in d:
+            # the reference's own cache (utils/cache.py), one size-bucket directory `cache_<w>x<h>x<frames>` or a directory
+            # of them (`<dataset>/cache/<model name>/`)
+            root = d['cache_dir']
+            subs = [root] if os.path.isdir(os.path.join(root, 'latents')) else sorted(
+                os.path.join(root, n) for n in os.listdir(root) if os.path.isdir(os.path.join(root, n, 'latents')))
+            if not subs:
+                raise RuntimeError(f'{root}: no size-bucket cache (a directory with latents/ and text_embeddings_*/) found')
+            out += [data_feed.ReferenceCacheBucket(sd, d.get('num_repeats', 1)) for sd in subs]
+            continue
         exs = torch.load(d['path'], map_location='cpu', weights_only=False)
         by_shape = {}
         for ex in exs:
