@@ -237,3 +237,25 @@ lr = 1e-4
     # 5 cached examples, global batch 2 -> 2 steps per epoch (the remainder is dropped, utils/dataset.py:350-360), 2 epochs
     assert [l['x'] for l in lines if l['tag'] == 'train/loss'] == [1, 2, 3, 4]
     assert os.path.exists(os.path.join(run_dir, 'epoch1', 'model.safetensors')) and os.path.exists(os.path.join(run_dir, 'epoch2', 'model.safetensors'))
+
+
+def test_every_example_config_builds_its_model_plan():
+    """examples/*.toml (the non-dataset ones): defaults, model dispatch, adapter configuration and the (lazy) layer plan are
+    consistent — no parameters are materialised"""
+    import glob
+    seen = 0
+    for path in sorted(glob.glob(os.path.join(ROOT, 'examples', '*.toml'))):
+        raw = T.load_toml(path)
+        if 'model' not in raw:
+            continue                                   # a dataset file
+        cfg = T.set_config_defaults(raw)
+        cfg['model']['lazy_layers'] = True
+        cfg['model']['device'] = 'cpu'
+        model = T.make_model(cfg)
+        if 'adapter' in cfg:
+            model.configure_adapter(cfg['adapter'])
+        specs = model.to_layers()
+        assert len(specs) >= 3 and all(hasattr(s, 'build') for s in specs), path
+        assert os.path.exists(os.path.join(ROOT, cfg['dataset'])), path
+        seen += 1
+    assert seen >= 5
