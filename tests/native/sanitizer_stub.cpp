@@ -1,0 +1,7 @@
+#include <stdarg.h>
+#include <stdio.h>
+namespace dpipe {
+static thread_local char g_err[1024];
+void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); }
+int fail(int code, const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); return code; }
+}
