@@ -291,6 +291,11 @@ class PipelineModule(nn.Module):
     def mpu(self):
         return self._grid
 
+    def compile(self, *args, **kwargs):
+        """train.py:620-621 calls `pipeline_model.compile(dynamic=True)` when `compile = true`: accepted and ignored — the
+        layers already run on hand-written kernels, and a tracing compiler has nothing to fuse across the C-ABI calls."""
+        return self
+
     def topology(self):
         return self._topo
 

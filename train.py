@@ -360,6 +360,8 @@ def main(argv=None):
         layers=layers, num_stages=num_stages, partition_method=config.get('partition_method', 'parameters'),
         manual_partition_split=config.get('partition_split', None), loss_fn=model.get_loss_fn(), dynamic_shape=True, **extra)
     model.pipeline_model = pipeline_model
+    if config['compile']:                                               # train.py:620-621 (a no-op on this engine)
+        pipeline_model.compile(dynamic=True)
     parameters_to_train = [p for p in pipeline_model.parameters() if p.requires_grad]
     model_engine, optimizer, _, _ = initialize(args=args, model=pipeline_model, config=ds_config)
     global_batch_size = (model_engine.train_micro_batch_size_per_gpu() * model_engine.gradient_accumulation_steps()
