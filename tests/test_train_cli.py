@@ -259,3 +259,13 @@ def test_every_example_config_builds_its_model_plan():
         assert os.path.exists(os.path.join(ROOT, cfg['dataset'])), path
         seen += 1
     assert seen >= 5
+
+
+def test_unsupported_adapter_options_are_refused_and_harmless_keys_are_tolerated():
+    base = {'save_every_n_epochs': 1, 'model': {'dtype': 'bfloat16'}}
+    for k, v in (('exclude_modules', ['to_q']), ('fuse_adapters', [{'path': 'x'}])):
+        with pytest.raises(NotImplementedError):
+            T.set_config_defaults(dict(base, model={'dtype': 'bfloat16'}, adapter={'type': 'lora', 'rank': 8, k: v}))
+    cfg = T.set_config_defaults(dict(base, model={'dtype': 'bfloat16'}, blocks_to_swap=20, compile=True, monitoring={'enable_wandb': True},
+                                     adapter={'type': 'lora', 'rank': 8, 'exclude_modules': None}))
+    assert cfg['adapter']['alpha'] == 8 and cfg['compile'] is True

@@ -90,6 +90,10 @@ def set_config_defaults(config):
             raise NotImplementedError('alpha is forced to rank (as in the reference): remove alpha from the [adapter] table')
         if ac['type'] != 'lora':
             raise NotImplementedError(f"adapter type '{ac['type']}': only 'lora' is built for the sm_100a path")
+        for k in ('exclude_modules', 'fuse_adapters'):
+            if ac.get(k):
+                raise NotImplementedError(f"[adapter] {k} is not supported on the sm_100a path: adapters ride the fused GEMM sites of "
+                                          'every Linear of the target blocks (models/base.py:263-303 with the default module set)')
         ac['alpha'] = ac['rank']
         ac['dtype'] = DTYPE_MAP[ac['dtype']] if 'dtype' in ac else mc['dtype']
         ac.setdefault('dropout', 0.0)
@@ -348,6 +352,11 @@ def main(argv=None):
         dist.broadcast_object_list(holder, src=0)
         run_dir = holder[0]
 
+    if config.get('blocks_to_swap', 0) and is_main:                        # train.py:576-583
+        print('blocks_to_swap is ignored: block swapping exists to fit 24 GB parts; this engine keeps the whole stage resident '
+              '(180 GB HBM per GPU)')
+    if 'monitoring' in config and is_main:
+        print('[monitoring] (wandb) is ignored: metrics go to <run_dir>/metrics.jsonl')
     layers = model.to_layers()
     extra = {}
     if config['activation_checkpointing']:
