@@ -163,10 +163,17 @@ class PipelineEngine:
         self.pipeline_schedule = str(self.config.get('pipeline_schedule', '1f1b')).lower()
         self.zb_costs = tuple(self.config.get('zb_costs', (13, 17, 10)))
         self.zb_max_inflight = self.config.get('zb_max_inflight', None)
-        # relative work per stage for the zero-bubble planner; default: the number of layers each stage holds
+        # relative work per stage for the zero-bubble planner; default: the number of layers each stage holds, not counting
+        # the model's first (embedding) and last (output head) layer, which are cheap next to a transformer block in every
+        # model definition of the reference (models/flux.py:396-404, qwen_image.py:490-496, wan/wan.py:399-411)
         self.zb_stage_weights = self.config.get('zb_stage_weights', None)
         if self.zb_stage_weights is None and getattr(model, 'parts', None) is not None and len(model.parts) == self.num_stages + 1:
-            self.zb_stage_weights = [max(1, int(model.parts[i + 1] - model.parts[i])) for i in range(self.num_stages)]
+            n_layers = int(model.parts[-1])
+            w = [int(model.parts[i + 1] - model.parts[i]) for i in range(self.num_stages)]
+            if n_layers >= self.num_stages + 2:
+                w[0] -= 1
+                w[-1] -= 1
+            self.zb_stage_weights = [max(1, x) for x in w]
         self._wgrad_queues = {}
         self._broadcast_model()
         self.link = self._make_link()
