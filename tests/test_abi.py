@@ -113,3 +113,90 @@ def test_fp8_code_tables_are_torchs_widening_for_all_256_codes():
     assert lib.dpipe_fp8_to_bf16(ctypes.c_void_p(8), 64, buf, 64, 4, 64, 0, None) < 0 and b'aligned' in lib.dpipe_last_error()
     assert lib.dpipe_fp8_to_bf16(buf, 64, buf, 64, 4, 64, 7, None) < 0
     assert lib.dpipe_fp8_to_bf16(buf, 64, buf, 64, 0, 64, 0, None) == 0          # empty matrix: nothing to do
+
+
+def test_ctypes_argument_lists_match_the_header_prototypes():
+    """every prototype of include/dpipe.h against the ctypes declaration that calls it: same number of arguments, and each
+    argument in the same class (pointer / 32-bit int / 64-bit int / float / double) — a drifted scalar width would pass
+    garbage in a register without any error"""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, 'include', 'dpipe.h')).read()
+    text = re.sub(r'/\*.*?\*/', ' ', text, flags=re.S)
+    text = re.sub(r'//[^\n]*', ' ', text)
+    protos = re.findall(r'\b(int|long long|const char\s*\*)\s+(dpipe_\w+)\s*\(([^;{}]*?)\)\s*;', text)
+    assert len(protos) >= 40
+
+    def cls_of_c(arg):
+        a = arg.strip()
+        if a in ('void', ''):
+            return None
+        if '*' in a or a.endswith(']'):
+            return 'ptr'
+        base = re.sub(r'\b(const|unsigned)\b', '', a).split()
+        t = ' '.join(base[:-1]) if len(base) > 1 else base[0]
+        return {'int': 'i32', 'int64_t': 'i64', 'uint64_t': 'i64', 'long long': 'i64', 'float': 'f32', 'double': 'f64',
+                'size_t': 'i64'}[t]
+
+    def cls_of_ctypes(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, 'contents') or issubclass(t, ctypes._Pointer):
+            return 'ptr'
+        return {ctypes.c_int: 'i32', ctypes.c_int64: 'i64', ctypes.c_uint64: 'i64', ctypes.c_longlong: 'i64', ctypes.c_float: 'f32',
+                ctypes.c_double: 'f64'}[t]
+    checked = 0
+    for ret, name, args in protos:
+        if name not in _abi.SIGNATURES:
+            continue
+        restype, argtypes = _abi.SIGNATURES[name]
+        want = [c for c in (cls_of_c(a) for a in args.split(',')) if c is not None]
+        got = [cls_of_ctypes(t) for t in argtypes]
+        assert got == want, (name, got, want)
+        assert (restype is ctypes.c_longlong) == (ret == 'long long'), name
+        checked += 1
+    assert checked >= 35, checked
+
+
+def test_struct_field_offsets_match_the_c_compiler(tmp_path):
+    """every field of every argument struct of include/dpipe.h: offsetof() from gcc == the offset ctypes computed, in
+    declaration order (equal sizes alone would not notice two swapped fields of the same width... nor would this, but a
+    wrong width, a missing field or different padding would shift everything after it)"""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, 'include', 'dpipe.h')).read()
+    text = re.sub(r'/\*.*?\*/', ' ', text, flags=re.S)
+    pairs = {'dpipe_qkv_epilogue': _lib.QkvEpilogue, 'dpipe_gemm_args': _lib.GemmArgs, 'dpipe_attn_args': _abi.AttnArgs,
+             'dpipe_attn_bwd_args': _abi.AttnBwdArgs, 'dpipe_qk_bwd_args': _abi.QkBwdArgs, 'dpipe_wan_norm_proj': _abi.WanNormProj,
+             'dpipe_wan_norm_fwd_args': _abi.WanNormFwdArgs, 'dpipe_wan_norm_bwd_proj': _abi.WanNormBwdProj,
+             'dpipe_wan_norm_bwd_args': _abi.WanNormBwdArgs}
+    fields = {}
+    for name in pairs:
+        body = re.search(r'typedef struct ' + name + r'\s*\{(.*?)\}\s*' + name + r'\s*;', text, flags=re.S).group(1)
+        names = []
+        for decl in body.split(';'):
+            decl = decl.strip()
+            if decl:
+                for d in decl.split(','):                                  # `int M, N, K;` declares three fields
+                    names.append(re.sub(r'\[.*\]', '', d.split()[-1].lstrip('*')))
+        fields[name] = names
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "dpipe.h"\nint main(void){\n'
+    for name, names in fields.items():
+        for f in names:
+            src += f'  printf("{name} {f} %zu\\n", offsetof({name}, {f}));\n'
+        src += f'  printf("{name} __size__ %zu\\n", sizeof({name}));\n'
+    src += '  return 0; }\n'
+    (tmp_path / 'off.c').write_text(src)
+    subprocess.run(['gcc', '-std=c99', '-I', os.path.join(root, 'include'), str(tmp_path / 'off.c'), '-o', str(tmp_path / 'off')], check=True)
+    out = subprocess.run([str(tmp_path / 'off')], check=True, capture_output=True, text=True).stdout.split('\n')
+    c_off = {}
+    for line in out:
+        if line:
+            s, f, o = line.split()
+            c_off.setdefault(s, []).append((f, int(o)))
+    for name, cls in pairs.items():
+        want = [o for f, o in c_off[name] if f != '__size__']
+        got = [getattr(cls, fn).offset for fn, _ in cls._fields_]
+        assert got == want, (name, [fn for fn, _ in cls._fields_], fields[name], got, want)
+        assert ctypes.sizeof(cls) == dict(c_off[name])['__size__'], name
