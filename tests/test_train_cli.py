@@ -20,6 +20,14 @@ def test_cli_accepts_the_reference_flags():
     assert a.resume_from_checkpoint == '20250101_00-00-00'
 
 
+def test_flags_of_the_caching_stage_are_refused_not_ignored(tmp_path):
+    cfg = tmp_path / 'c.toml'
+    cfg.write_text("output_dir = 'x'\n")
+    for flag in (['--cache_only'], ['--regenerate_cache'], ['--dump_dataset', str(tmp_path)], ['--test_sample']):
+        with pytest.raises(NotImplementedError, match='caching'):
+            T.main(['--config', str(cfg)] + flag)
+
+
 def test_config_defaults_and_batch_tables():
     cfg = T.load_toml(os.path.join(ROOT, 'examples', 'flux_synthetic.toml'))
     cfg = T.set_config_defaults(cfg)

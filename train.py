@@ -301,6 +301,11 @@ def evaluate(model_engine, eval_dataloaders, step, egas, log):
 
 def main(argv=None):
     args = build_parser().parse_args(argv)
+    for flag in ('cache_only', 'regenerate_cache', 'dump_dataset', 'test_sample'):
+        if getattr(args, flag):
+            # train.py:537-560,897-905: these drive the caching / sampling stages (VAE, text encoders), which stay the reference's
+            raise NotImplementedError(f'--{flag} belongs to the latent / text-embedding caching and sampling stages, which stay with the '
+                                      "reference's tooling (utils/cache.py is consumed unchanged: [[directory]] cache_dir = ...)")
     config = set_config_defaults(load_toml(args.config))
     world_size = int(os.getenv('WORLD_SIZE', '1'))
     local_rank = args.local_rank if args.local_rank >= 0 else int(os.getenv('LOCAL_RANK', '0'))
