@@ -124,3 +124,23 @@ def test_wan22_i2v_matches_oracle():
         if err > 5e-2:
             bad.append((err, n))
     assert not bad, sorted(bad, reverse=True)[:8]
+
+
+# ---- 4. wider shape sweeps of the kernel tests (same checks as tests/test_kernels_gpu.py, shapes that have not run yet) ----
+@pytest.mark.parametrize('shape', [(1029, 776, 1000), (128, 8, 72), (4608, 3088, 3088), (777, 3072, 144), (2, 21504, 3072)])
+def test_gemm_layouts_on_more_shapes(shape):
+    """row / column / reduction tails in one problem, the smallest N the epilogue allows, LoRA-extended widths
+    (N + R, K + R), the Wan2.2-I2V patch-embedding reduction (K = 144), two rows against the widest weight"""
+    import test_kernels_gpu as KT
+    from diffusion_pipe_b200 import ops
+    for cg in (1, 2):
+        KT.test_gemm_layouts(ops, cg, shape)
+
+
+@pytest.mark.parametrize('shape', [(1, 3, 1003, 777), (3, 1, 130, 4101), (1, 2, 4101, 257), (2, 3, 64, 64)])
+def test_attention_on_more_shapes(shape):
+    """query / key lengths that are not multiples of the 128-row tile on both sides, more batches and heads, long keys
+    with few queries and the reverse"""
+    import test_kernels_gpu as KT
+    from diffusion_pipe_b200 import ops
+    KT.test_attention_forward_backward(ops, shape)
