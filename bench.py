@@ -493,7 +493,9 @@ def main():
             except Exception as exc:      # context only: never lose the bench line over it
                 library = {'error': repr(exc)[:300]}
         if library:
-            out['gpu_library_baseline'] = library
+            # part of the baseline leg: the same restated reference blocks as `cpu_baseline`, dispatched to the library kernels
+            # of this GPU instead of the host cores
+            (out['cpu_baseline'] if 'cpu_baseline' in out else out)['gpu_library'] = library
         print(json.dumps(out), flush=True)
     if world > 1:
         tdist.barrier()
