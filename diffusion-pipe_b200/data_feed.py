@@ -200,6 +200,7 @@ class PipelineDataLoader:
         self.next_micro_batch = None
         self.recreate_dataloader = False
         self._epoch0, self._consumed0, self._steps = 1, 0, 0     # for the communication-free epoch agreement (sync_epoch)
+        self._ever_pulled = False                                 # middle pipeline stages never pull
         self._create_dataloader()
         self.data = self._micro_batches()
 
@@ -250,6 +251,7 @@ class PipelineDataLoader:
             # the target depends on the noise drawn on the first stage: ship it to the last stage
             label = (*[self._broadcast_target(t) for t in targets], mask)
             self.num_batches_pulled += 1
+            self._ever_pulled = True
             yield from split_batch((features, label), self.gradient_accumulation_steps)
 
     def _broadcast_target(self, target):
@@ -287,8 +289,29 @@ class PipelineDataLoader:
             dist.all_gather_object(seen, self.epoch)
             assert len(set(seen)) == 1, f'ranks disagree on the epoch: {seen}'
 
+    def set_epoch(self, epoch):
+        """`--reset_dataloader` on resume (train.py:876-877): keep the checkpoint's epoch number but start the data order
+        from the beginning; the step-counted epoch agreement restarts from here too."""
+        self.epoch = int(epoch)
+        self._epoch0, self._consumed0, self._steps = self.epoch, 0, 0
+
     def state_dict(self):
-        return {'epoch': self.epoch, 'num_batches_pulled': self.num_batches_pulled}
+        """Identical on every rank of a pipeline.  Ranks that pull data report what they pulled (the reference's value,
+        utils/dataset.py:1419-1423); middle stages never touch the dataloader, so they report the same number derived from
+        the step count: k items consumed since the start of the epoch means k+1 pulled (one is always pre-pulled), and 0
+        right after the roll-over that handed out the epoch's last micro-batch.  (A checkpoint taken exactly on an epoch
+        boundary stores 0, which the reference's `- 1` resume rule turns into "replay the last batch first",
+        utils/dataset.py:1430 — kept, and counted, here.)"""
+        pulled = self.num_batches_pulled
+        if not self._ever_pulled and self._steps > 0:
+            n, k = len(self.dataset), self._steps
+            first = n - self._consumed0               # steps the (possibly resumed) first epoch lasts
+            if k < first:
+                pulled = self._consumed0 + k + 1
+            else:
+                kk = (k - first) % n
+                pulled = kk + 1 if kk > 0 else 0
+        return {'epoch': self.epoch, 'num_batches_pulled': pulled}
 
     def load_state_dict(self, state):
         assert not self.iter_called

@@ -70,8 +70,13 @@ def all_reduce(tensor, op=ReduceOp.SUM, group=None):
 
 
 def all_gather_object(object_list, obj, group=None):
+    if not tdist.is_initialized():          # single process (train.py only initialises torch.distributed when WORLD_SIZE > 1)
+        object_list[0] = obj
+        return None
     return tdist.all_gather_object(object_list, obj, group=group)
 
 
 def broadcast_object_list(object_list, src=0, group=None):
+    if not tdist.is_initialized():
+        return None
     return tdist.broadcast_object_list(object_list, src=src, group=group)

@@ -195,7 +195,11 @@ class PipelineEngine:
             if not p.requires_grad or p.data_ptr() in seen:
                 continue
             seen.add(p.data_ptr())
-            dist.broadcast(p.data, src, group=group)
+            with torch.no_grad():
+                # in place on the parameter itself (not `.data`): the version counter moves, so caches keyed on it
+                # (lora.py: the fused [[W|B],[A|0]] site buffers) are rebuilt from the broadcast values
+                dist.broadcast(p, src, group=group)
+                p.add_(0)
 
     # ------------------------------------------------------------------ DeepSpeed-compatible accessors
     def is_first_stage(self):
@@ -226,13 +230,32 @@ class PipelineEngine:
         return self.optimizer
 
     def _make_link(self):
+        """'auto' picks the CUDA-IPC link when every rank of the job sits on one host and sees the same GPUs under the same
+        ordinals (the reference's launch: one node, `deepspeed --num_gpus=N`, README.md:118); anything else — several nodes,
+        one CUDA_VISIBLE_DEVICES per rank — falls back to torch.distributed p2p with a notice.  The decision is taken from
+        one all-gather so that every rank takes the same one."""
         kind = self.config.get('stage_link', 'auto')
+        devices = None
         if kind == 'auto':
             kind = 'ipc' if (self.device.type == 'cuda' and self.is_pipe_parallel
                              and os.environ.get('DPIPE_STAGE_LINK', 'ipc') == 'ipc') else 'dist'
         if kind == 'ipc' and self.is_pipe_parallel:
+            import socket
+            mine = (socket.gethostname(), os.environ.get('CUDA_VISIBLE_DEVICES'), self.device.index, torch.cuda.device_count())
+            seen = [None] * dist.get_world_size()
+            dist.all_gather_object(seen, mine)
+            ok = (len({x[0] for x in seen}) == 1 and len({x[1] for x in seen}) == 1
+                  and all(x[2] is not None and x[2] < x[3] for x in seen))
+            if not ok:
+                if self.global_rank == 0:
+                    print('stage link: the ranks are not on one host with a common view of its GPUs; using torch.distributed '
+                          'p2p on the stage boundaries instead of CUDA-IPC peer copies', flush=True)
+                kind = 'dist'
+            else:
+                devices = [x[2] for x in seen]
+        if kind == 'ipc' and self.is_pipe_parallel:
             from .ipc_link import IpcLink
-            return IpcLink(self)
+            return IpcLink(self, devices)
         return DistLink(self)
 
     # ------------------------------------------------------------------ public API

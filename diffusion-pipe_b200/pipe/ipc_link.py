@@ -15,6 +15,7 @@ reference's metadata handshake) — host metadata, no device synchronisation.
 Replaces DeepSpeed's p2p send/recv of the boundary tuple (schedule at utils/patches.py:134-143).
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as tdist
@@ -26,7 +27,7 @@ _DTYPES = [torch.float32, torch.float16, torch.bfloat16, torch.int64, torch.int3
 _DTYPE_ID = {d: i for i, d in enumerate(_DTYPES)}
 _META_LEN = 192
 _ALIGN = 256
-_WAIT_TIMEOUT_S = 300.0
+_WAIT_TIMEOUT_S = float(os.environ.get('DPIPE_LINK_TIMEOUT_S', 300.0))   # device-side flag wait; 0 = wait forever
 
 
 def _align(n):
@@ -238,10 +239,7 @@ class _Channel:
 
 
 class IpcLink:
-    def __init__(self, engine):
-        self.engine = engine
-        self.device = engine.device
-        assert self.device.type == 'cuda'
+XX
         grid = engine.grid
         # 1F1B keeps at most `stages` micro-batches in flight on a stage; the zero-bubble order holds up to
         # `zb_max_inflight` (default 2 x stages).  A receiver that may hold n un-released activations needs n slots:
@@ -257,11 +255,12 @@ class IpcLink:
             g = tdist.new_group(ranks=ranks, backend='gloo')
             if d == grid.data_parallel_id:
                 self.ctrl_group = g
-        # peers: same node, device ordinal == local rank of the peer (all GPUs visible in every process)
+        # peers: same node, all GPUs visible in every process under the same ordinals (two stages may share one device:
+        # the peer copy degenerates to a device-local copy — tests/test_stage_link_one_gpu.py)
         local_rank = self.device.index
         def peer(stage):
             r = grid.stage_to_global(stage)
-            return r, local_rank + (r - engine.global_rank)
+            return r, (rank_devices[r] if rank_devices is not None else local_rank + (r - engine.global_rank))
         s = engine.stage_id
         self.act_out = _Channel(self, *peer(s + 1), sending=True, tag=100) if s + 1 < engine.num_stages else None
         self.act_in = _Channel(self, *peer(s - 1), sending=False, tag=100) if s > 0 else None

@@ -190,6 +190,68 @@ def test_sync_epoch_is_a_pure_function_of_the_step_count(golden):
         assert puller.epoch == 2
 
 
+def test_every_stage_saves_the_same_loader_state_and_resumes_in_step(golden):
+    """every rank restores the loader from ITS OWN stage checkpoint (train.py:870-879).  Middle stages never
+    pull data, so their saved state is derived from the step count and must equal what the pulling stages saved — mid-epoch,
+    right at an epoch boundary and before the first step — or a >= 3-stage pipeline disagrees on the epoch after resume."""
+    class Mid(Engine):
+        def is_first_stage(self):
+            return False
+
+        def is_last_stage(self):
+            return False
+    key = sorted(golden['loader'])[0]
+    lname, gas = key.split('|')
+    gas = int(gas)
+
+    def mk(engine):
+        ds = make(LAYOUTS[lname], with_mask=True)
+        ds.post_init(0, 1, {None: 2}, gas, {None: 2})
+        return DF.PipelineDataLoader(ds, engine, gas, Model(), num_dataloader_workers=0)
+
+    def run(loaders, steps):
+        for _ in range(steps):
+            for ld in loaders:
+                it = DF.get_data_iterator_for_step(ld, ld.model_engine, num_micro_batches=gas)
+                if it is not None:
+                    assert len(list(it)) == gas
+            for ld in loaders:
+                ld.sync_epoch()
+            assert len({ld.epoch for ld in loaders}) == 1
+    n = len(mk(Engine()).dataset)
+    assert n >= 3
+    for save_after in (0, 1, n - 1, n, n + 2, 2 * n):
+        first, middle, last = mk(Engine()), mk(Mid()), mk(Engine())
+        run((first, middle, last), save_after)
+        states = [ld.state_dict() for ld in (first, middle, last)]
+        assert states[0] == states[1] == states[2], (save_after, states)
+        # a second generation: resume, run across the next epoch boundary, save again, resume again
+        for _generation in range(2):
+            resumed = (mk(Engine()), mk(Mid()), mk(Engine()))
+            for ld, st in zip(resumed, states):
+                ld.load_state_dict(st)                          # each rank: its own checkpoint's client_state
+            run(resumed, n + 1)
+            states = [ld.state_dict() for ld in resumed]
+            assert states[0] == states[1] == states[2], (save_after, states)
+
+
+def test_reset_dataloader_keeps_the_checkpoint_epoch(golden):
+    """`--reset_dataloader` (train.py:876-877) resumes at the checkpoint's epoch with the data order restarted; the
+    step-counted epoch agreement must restart from that epoch instead of raising 'epoch bookkeeping diverged'."""
+    key = sorted(golden['loader'])[0]
+    lname, gas = key.split('|')
+    gas = int(gas)
+    ds = make(LAYOUTS[lname], with_mask=True)
+    ds.post_init(0, 1, {None: 2}, gas, {None: 2})
+    ld = DF.PipelineDataLoader(ds, Engine(), gas, Model(), num_dataloader_workers=0)
+    ld.set_epoch(3)
+    n = len(ds)
+    for step in range(1, n + 2):
+        list(DF.get_data_iterator_for_step(ld, ld.model_engine, num_micro_batches=gas))
+        ld.sync_epoch()
+        assert ld.epoch == 3 + step // n
+
+
 def test_reference_cache_directories_are_read_as_the_reference_wrote_them(golden_dir):
     """tests/golden/ref_cache/ was written by the reference's own utils/cache.py (tests/golden/make_golden_cache.py): the
     read side (data_feed.ReferenceCache / ReferenceCacheBucket) returns the same items in the same order, across shards,

@@ -429,7 +429,7 @@ def main(argv=None):
         if args.reset_optimizer_params and optimizer is not None:        # train.py:874-875: keep the TOML's lr / betas / ...
             optimizer.param_groups = param_groups
         if args.reset_dataloader:
-            train_dataloader.epoch = client_state['custom_loader']['epoch']
+            train_dataloader.set_epoch(client_state['custom_loader']['epoch'])
         else:
             train_dataloader.load_state_dict(client_state['custom_loader'])
         step = client_state['step'] + 1
