@@ -344,8 +344,12 @@ class PipelineEngine:
             self.pipe_buffers['outputs'][b] = tuple(outputs)
         if not train:
             self.pipe_buffers['inputs'][b] = None
-            if self.is_last_stage() and not self.is_first_stage():
-                self.link.release_activations(b, cmd.micro_batch_id)
+            if self.is_last_stage():
+                # forward-only: the loss is already in total_loss, nothing will come back for this buffer
+                self.pipe_buffers['outputs'][b] = None
+                self.pipe_buffers['labels'][b] = None
+                if not self.is_first_stage():
+                    self.link.release_activations(b, cmd.micro_batch_id)
 
     def _exec_backward_input(self, cmd, train):
         """split backward: weight-gradient work of the layers that support it is queued instead of launched.
