@@ -30,6 +30,15 @@ FWD_TFLOP_PER_BLOCK = 1.3046          # 1.0437 GEMM + 0.
 TRAIN_TFLOP_PER_SAMPLE = 223.2        # 57 blocks x 1.305 x 3 (forward + backward, no recompute)
 METRIC = 'training samples/sec (device-timed, max over stages) Flux-dev 1024^2 bf16'   # BASELINE.json:metric
 GEMM_FRACTION = 0.80
+# the other BASELINE.json configurations (`--family wan|qwen`): full model blocks, algorithmic training TFLOP / sample
+FAMILIES = {
+    'flux': {'blocks': 57, 'train_tflop': 223.2, 'metric': METRIC},
+    'wan': {'blocks': 40, 'train_tflop': 887.8,
+            'metric': 'training samples/sec (device-timed, max over ranks) Wan2.1-14B t2v 33f 512^2 bf16'},
+    'qwen': {'blocks': 60, 'train_tflop': 219.4,
+             'metric': 'training samples/sec (device-timed, max over ranks) Qwen-Image 1024^2 bf16, 256 text tokens'},
+}
+WEIGHT_SEED = 1234                    # layer i of the model is initialised from WEIGHT_SEED + i on whatever rank builds it
 
 
 def parse():
@@ -50,6 +59,17 @@ def parse():
     ap.add_argument('--schedule', default='auto', choices=['auto', '1f1b', 'zb'],
                     help="pipeline order: the reference's 1F1B or the split-backward zero-bubble order (auto: zb from 3 stages up; at 2 stages the 1F1B bubble is 1/17 of the step and measured no worse)")
     ap.add_argument('--profile-kernels', action='store_true', default=True)
+    ap.add_argument('--family', default='flux', choices=['flux', 'wan', 'qwen'],
+                    help='flux = the BASELINE.json metric (configs[1]/[2]); wan = configs[3] (Wan2.1-14B t2v, 33 frames 512^2); '
+                         'qwen = configs[4] (Qwen-Image 1024^2, 256 text tokens)')
+    ap.add_argument('--pp', type=int, default=0, help='pipeline stages (default: every GPU is a stage)')
+    ap.add_argument('--blocks', type=int, default=0, help='wan / qwen: transformer blocks (default: the full model, 40 / 60)')
+    ap.add_argument('--frames', type=int, default=33)
+    ap.add_argument('--max-inflight', type=int, default=0, help='zero-bubble order: micro-batches a stage may hold (activation memory bound)')
+    ap.add_argument('--partition', default='time', choices=['time', 'blocks'],
+                    help='flux stage split: balanced by MEASURED block times (double vs single block, probed before the model is built) or by block count')
+    ap.add_argument('--instrumented-steps', type=int, default=2,
+                    help='extra steps, after the timed region, with a CUDA event pair around every kernel launch (roofline, shares)')
     return ap.parse_args()
 
 
@@ -195,13 +215,14 @@ def run_reference_arm(a):
     # one sample = 1 double + 1 single block forward+backward at the full shape (~40 s on 128 threads): the arm is bounded
     # to one untimed and at most two timed samples whatever --warmup / --steps say, so that it ends within ~2 minutes
     vals = []
-    n_warm, n_timed = min(a.warmup, 1), max(1, min(a.steps, 2))
+    n_warm, n_timed = min(a.warmup, 1), max(1, min(a.steps, 3))
     for i in range(n_warm + n_timed):
         t0 = time.perf_counter()
         v, desc, cores = cpu_reference_sample(a.res, a.text_len, n_double, n_single)
         if i >= n_warm:
             vals.append((v, time.perf_counter() - t0))
-    value = sum(v for v, _ in vals) / len(vals)
+    value = sorted(v for v, _ in vals)[len(vals) // 2]           # median of the timed samples
+    spread = [min(v for v, _ in vals), max(v for v, _ in vals)]
     out = {
         'impl': 'reference', 'metric': METRIC, 'value': value,
         'unit': 'samples/s', 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
@@ -212,7 +233,7 @@ def run_reference_arm(a):
                    'micro_batches': a.micro_batches, 'seq_len': (a.res // 16) ** 2 + a.text_len, 'parallelism': 'host cores',
                    'arithmetic': 'fp32 restatement of the reference path (oracle/flux_ref.py); the reference itself cannot be installed here'},
         'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
-                         'sample': desc + f'; {len(vals)} timed sample(s) after {n_warm} untimed'},
+                         'sample': desc + f'; median of {len(vals)} timed sample(s) after {n_warm} untimed', 'min_max': spread},
         'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -223,12 +244,17 @@ def run_reference_arm(a):
 # the GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
 def gemm_traffic_from_profile():
-    """dram bytes (read + write) per launch of the dominant GEMM shape, from the committed ncu --set full capture"""
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'r01_gemm_traffic.json')) as f:
-            return json.load(f)['dram_bytes_total']
-    except Exception:
-        return None
+    """(dram bytes read + written per launch of the dominant GEMM shape, which capture it comes from).  DRAM counters
+    exist only under ncu, and a number measured under a profiler is never a bench value: the figure is read from the newest
+    committed `ncu --set full` capture of this same command (profiles/rNN_gemm_traffic.json), named next to it."""
+    import glob
+    for fn in sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_gemm_traffic.json')), reverse=True):
+        try:
+            with open(fn) as f:
+                return json.load(f)['dram_bytes_total'], 'profiles/' + os.path.basename(fn)
+        except Exception:
+            continue
+    return None, None
 
 
 def flop_balanced_split(n_double, n_single, stages):
@@ -282,6 +308,137 @@ def synth_micro_batches(a, n, seed, device, pinned):
     return out
 
 
+def probe_block_times(device, res, text_len, iters=3):
+    """Measured cost of one Flux double and one single block at the bench shape, before the model is built: forward,
+    input-gradient pass (weight gradients queued, as the split-backward order runs them) and the queued weight-gradient pass,
+    CUDA events, median of `iters`.  Returns {'double': (tf, tb, tw), 'single': (tf, tb, tw)} in ms."""
+    import torch
+    from diffusion_pipe_b200 import flux_blocks as FB
+    from diffusion_pipe_b200 import ops
+    D, H = 3072, 24
+    Li, Lt = (res // 16) ** 2, text_len
+    cos = torch.ones(Li + Lt, 128, device=device)
+    sin = torch.zeros(Li + Lt, 128, device=device)
+    out = {}
+    for kind, cls in (('double', FB.FluxTransformerBlock), ('single', FB.FluxSingleTransformerBlock)):
+        torch.manual_seed(1)
+        blk = cls(D, H, device=device)
+        hid = torch.randn(1, Li, D, device=device).bfloat16().requires_grad_(True)
+        enc = torch.randn(1, Lt, D, device=device).bfloat16().requires_grad_(True)
+        temb = torch.randn(1, D, device=device).bfloat16().requires_grad_(True)
+        gh, ge = torch.randn_like(hid), torch.randn_like(enc)
+        samples = []
+        for it in range(iters + 1):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+            eo, ho = blk(hid, enc, temb, (cos, sin))
+            ev[1].record()
+            q = []
+            ops.WGRAD_DEFER = q
+            try:
+                torch.autograd.backward([ho, eo], [gh, ge])
+            finally:
+                ops.WGRAD_DEFER = None
+            ev[2].record()
+            with torch.no_grad():
+                for fn in q:
+                    fn()
+            ev[3].record()
+            torch.cuda.synchronize()
+            if it:
+                samples.append(tuple(ev[i].elapsed_time(ev[i + 1]) for i in range(3)))
+            hid.grad = enc.grad = temb.grad = None
+        out[kind] = tuple(sorted(x[i] for x in samples)[len(samples) // 2] for i in range(3))
+        del blk, hid, enc, temb, gh, ge, q
+    torch.cuda.empty_cache()
+    return out
+
+
+def time_balanced_split(n_double, n_single, stages, t_double, t_single, micro_batches=16, costs=(30, 40, 30), max_inflight=0):
+    """Contiguous split of [embed, double x n, single x n, out] by MEASURED block time (a double block costs more time than
+    a single block at equal FLOPs: two streams, twice the launches).  Start: the C++ min-max partitioner behind
+    partition_method='parameters' fed with times instead of parameter counts; then a local search moves one stage boundary at
+    a time while the SIMULATED makespan of the split-backward schedule (csrc/sched.cpp, per-stage costs = the stage's summed
+    block time) keeps falling — the pipeline's fill/drain makes the best split slightly uneven.  The embedding and the output
+    head are charged 2 % of a single block.  Returns (split, per-stage time in ms, per-stage blocks)."""
+    import ctypes
+    from diffusion_pipe_b200 import _lib
+    from diffusion_pipe_b200.pipe.module import partition_balanced
+    unit = 1000.0 / t_single
+    w = [20] + [int(round(t_double * unit))] * n_double + [1000] * n_single + [20]
+    parts = list(partition_balanced(w, stages))
+
+    def stage_w(pt):
+        return [max(1, sum(w[pt[i]:pt[i + 1]]) // 10) for i in range(stages)]
+
+    def makespan(pt):
+        sw = (ctypes.c_int * stages)(*stage_w(pt))
+        m = _lib.lib().dpipe_sched_zb_makespan_ex(micro_batches, stages, *costs, max_inflight or 2 * stages, sw)
+        return (m, sum(x * x for x in sw)) if m > 0 else (0, 0)      # ties: the more even split
+    best = makespan(parts)
+    improved = True
+    while improved and best[0] > 0:
+        improved = False
+        for b in range(1, stages):
+            for d in (-1, 1):
+                cand = list(parts)
+                cand[b] += d
+                if not (cand[b - 1] < cand[b] < cand[b + 1]):
+                    continue
+                m = makespan(cand)
+                if m[0] > 0 and m < best:
+                    parts, best, improved = cand, m, True
+    per_time = [sum(w[parts[i]:parts[i + 1]]) * t_single / 1000.0 for i in range(stages)]
+    per_blocks = [parts[i + 1] - parts[i] - (1 if i == 0 else 0) - (1 if i == stages - 1 else 0) for i in range(stages)]
+    return list(parts[1:-1]), per_time, per_blocks
+
+
+def build_family(a, device):
+    """(model, layers, example-batch maker or None, workload string, n_blocks)"""
+    import torch
+    if a.family == 'flux':
+        from diffusion_pipe_b200.flux import FluxPipeline
+        n_double, n_single = (int(x) for x in a.layers.split(','))
+        model = FluxPipeline({'model': {'dtype': 'bfloat16', 'guidance': 1.0, 'lazy_layers': True,
+                                        'transformer_config': {'num_layers': n_double, 'num_single_layers': n_single}}},
+                             device=device)
+        return model, None, f'Flux-dev full fine-tune bf16 {a.res}x{a.res} (configs[1]/[2] model), {n_double}+{n_single} blocks', n_double + n_single
+    if a.family == 'wan':
+        from diffusion_pipe_b200.wan import WAN_T2V_14B_CONFIG, WanPipeline
+        n_blocks = a.blocks or WAN_T2V_14B_CONFIG['num_layers']
+        res = a.res if a.res != 1024 else 512
+        model = WanPipeline({'model': {'dtype': 'bfloat16', 'lazy_layers': True, 'transformer_config': {'num_layers': n_blocks}}}, device=device)
+        lat_f = (a.frames - 1) // 4 + 1
+
+        def example(g):
+            return {'latents': torch.randn(16, lat_f, res // 8, res // 8, generator=g),
+                    'text_embeddings': torch.randn(512, 4096, generator=g).bfloat16(), 'seq_lens': torch.tensor(512), 'mask': None}
+        return model, example, f'Wan2.1-14B t2v full fine-tune bf16, {a.frames} frames {res}x{res} (configs[3] model), {n_blocks} blocks', n_blocks
+    from diffusion_pipe_b200.qwen_image import QWEN_IMAGE_CONFIG, QwenImagePipeline
+    n_blocks = a.blocks or QWEN_IMAGE_CONFIG['num_layers']
+    text_len = a.text_len if a.text_len != 512 else 256
+    model = QwenImagePipeline({'model': {'dtype': 'bfloat16', 'lazy_layers': True, 'transformer_config': {'num_layers': n_blocks}}}, device=device)
+
+    def example(g):
+        return {'latents': torch.randn(16, 1, a.res // 8, a.res // 8, generator=g),
+                'prompt_embeds': torch.randn(text_len, 3584, generator=g).bfloat16(), 'mask': None}
+    return model, example, f'Qwen-Image full fine-tune bf16, {a.res}x{a.res}, {text_len} text tokens (configs[4] model), {n_blocks} blocks', n_blocks
+
+
+def seed_layers(layers):
+    """every lazily built layer draws its initial weights from WEIGHT_SEED + its index in the model: the same model whatever
+    the partition and whichever rank builds the layer, so the loss of the bench line must agree across --gpus 1/2/4/8"""
+    import torch
+    from diffusion_pipe_b200.pipe.module import LayerSpec
+    for idx, spec in enumerate(layers):
+        if isinstance(spec, LayerSpec):
+            def build(orig=spec.build, idx=idx):
+                torch.manual_seed(WEIGHT_SEED + idx)
+                return orig()
+            spec.build = build
+    return layers
+
+
 def main():
     a = parse()
     if a.impl == 'reference':
@@ -289,8 +446,7 @@ def main():
 
     import torch
     import torch.distributed as tdist
-    from diffusion_pipe_b200 import ops
-    from diffusion_pipe_b200.flux import FluxPipeline
+    from diffusion_pipe_b200 import data_feed, ops
     from diffusion_pipe_b200.pipe import ManualPipelineModule, initialize
     from diffusion_pipe_b200.pipe import dist
 
@@ -304,32 +460,85 @@ def main():
     device = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_distributed('nccl')
-    n_double, n_single = (int(x) for x in a.layers.split(','))
-    stages = world
+    stages = a.pp or world
+    if world % stages:
+        raise SystemExit(f'--pp {stages} does not divide the world size {world}')
+    dp = world // stages
     M, mbs = a.micro_batches, a.micro_batch_size
+    fam = FAMILIES[a.family]
+    schedule = ('zb' if stages > 2 else '1f1b') if a.schedule == 'auto' else a.schedule
 
-    torch.manual_seed(1234 + rank)
-    model = FluxPipeline({'model': {'dtype': 'bfloat16', 'guidance': 1.0, 'lazy_layers': True,
-                                    'transformer_config': {'num_layers': n_double, 'num_single_layers': n_single}}},
-                         device=device)
-    layers = model.to_layers()
-    split, blocks_per_stage = flop_balanced_split(n_double, n_single, stages)
+    # ---- stage partition: measured block times (Flux: double vs single), block count otherwise ----
+    probe = None
+    zb_costs = None
+    if a.family == 'flux':
+        n_double, n_single = (int(x) for x in a.layers.split(','))
+        if stages > 1 and a.partition == 'time' and n_double and n_single:
+            probe = probe_block_times(device, a.res, a.text_len)
+            t = torch.tensor([sum(probe['double']), sum(probe['single'])] + list(probe['double']) + list(probe['single']),
+                             device=device, dtype=torch.float64)
+            tdist.all_reduce(t)                       # every rank must derive the same split: average the measurements
+            t = (t / world).tolist()
+            tf, tb, tw = (n_double * t[2 + i] + n_single * t[5 + i] for i in range(3))
+            zb_costs = tuple(max(1, int(round(100.0 * x / (tf + tb + tw)))) for x in (tf, tb, tw))     # measured F : B : W shares
+            split, stage_ms, blocks_per_stage = time_balanced_split(n_double, n_single, stages, t[0], t[1], M, zb_costs, a.max_inflight)
+            stage_weights = [max(1, int(round(100 * x))) for x in stage_ms]
+            partition_desc = {'method': 'measured block times, contiguous min-max', 'double_ms': round(t[0], 3), 'single_ms': round(t[1], 3),
+                              'double_over_single': round(t[0] / t[1], 3), 'blocks_per_stage': blocks_per_stage,
+                              'stage_ms_per_micro_batch': [round(x, 2) for x in stage_ms]}
+        else:
+            split, blocks_per_stage = flop_balanced_split(n_double, n_single, stages)
+            stage_weights = [max(1, b) for b in blocks_per_stage]
+            partition_desc = {'method': 'equal block count (extra blocks on the earliest stages)', 'blocks_per_stage': blocks_per_stage}
+    model, example, workload, n_blocks = build_family(a, device)
+    if a.family != 'flux':
+        split, blocks_per_stage = flop_balanced_split(n_blocks, 0, stages)
+        stage_weights = [max(1, b) for b in blocks_per_stage]
+        partition_desc = {'method': 'equal block count (identical blocks)', 'blocks_per_stage': blocks_per_stage}
+    layers = seed_layers(model.to_layers())
     pm = ManualPipelineModule(layers=layers, num_stages=stages, partition_method='manual' if stages > 1 else 'uniform',
                               manual_partition_split=split if stages > 1 else None, loss_fn=model.get_loss_fn(),
                               dynamic_shape=True)
-    engine, _, _, _ = initialize(model=pm, config={'train_micro_batch_size_per_gpu': mbs, 'gradient_accumulation_steps': M,
-                                                   'gradient_clipping': 1.0, 'steps_per_print': 0,
-                                                   'pipeline_schedule': ('zb' if stages > 2 else '1f1b') if a.schedule == 'auto' else a.schedule,
-                                                   'zb_stage_weights': [max(1, b) for b in blocks_per_stage]})
+    cfg = {'train_micro_batch_size_per_gpu': mbs, 'gradient_accumulation_steps': M, 'gradient_clipping': 1.0, 'steps_per_print': 0,
+           'pipeline_schedule': schedule, 'zb_stage_weights': stage_weights}
+    if zb_costs is not None:
+        cfg['zb_costs'] = zb_costs
+    max_inflight = a.max_inflight or (stages if a.family == 'wan' else 0)     # Wan-14B: 9 GB of activations per micro-batch and stage
+    if max_inflight:
+        cfg['zb_max_inflight'] = max_inflight
+    engine, _, _, _ = initialize(model=pm, config=cfg)
     params = [p for p in pm.parameters() if p.requires_grad]
     if not a.no_optimizer:
         engine._configure_optimizer(lambda ps: torch.optim.AdamW(ps, lr=1e-5, betas=(0.9, 0.99), weight_decay=0.01,
-                                                                 fused=True), params)
-    n_params = sum(p.numel() for p in params)
+                                                                 fused=True) if ps else None, params)
+    seen, n_local = set(), 0
+    for p_ in params:
+        if p_.data_ptr() not in seen:
+            seen.add(p_.data_ptr())
+            n_local += p_.numel()
+    np_t = torch.tensor([float(n_local)], device=device, dtype=torch.float64)
+    if world > 1:
+        tdist.all_reduce(np_t)
+    n_params = np_t.item() / dp                     # one replica of the model (every stage once)
 
     need_data = engine.is_first_stage() or engine.is_last_stage()
-    dev_batches = synth_micro_batches(a, M, 1234 + rank * 0, device, pinned=False) if need_data else None
-    host_batches = synth_micro_batches(a, M, 1234 + rank * 0, device, pinned=True) if need_data else None
+    dp_rank = engine.grid.get_data_parallel_rank()
+
+    def family_micro_batches(pinned):
+        if not need_data:
+            return None
+        if a.family == 'flux':
+            return synth_micro_batches(a, M, 1234 + dp_rank, device, pinned=pinned)
+        g = torch.Generator().manual_seed(1234 + dp_rank)
+        torch.manual_seed(99 + dp_rank)
+        batch = data_feed.BatchedDataset.collate([example(g) for _ in range(M * mbs)])
+        feats, label = model.prepare_inputs(batch)
+        out = []
+        for f, l in data_feed.split_batch((feats, label), M):
+            mv = (lambda t: t.pin_memory()) if pinned else (lambda t: t.to(device))
+            out.append((tuple(mv(t) for t in f), tuple(mv(t) for t in l)))
+        return out
+    dev_batches, host_batches = family_micro_batches(False), family_micro_batches(True)
 
     h2d_local = 0
     if need_data:
@@ -352,18 +561,24 @@ def main():
             tdist.barrier()
         torch.cuda.synchronize()
 
+    reduce_ms = []
+
     def timed(batches, read_loss, nsteps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
+        waits = []
         for _ in range(nsteps):
             last = step(batches, read_loss)
+            if engine.dp_reduce_events is not None:
+                waits.append(engine.dp_reduce_events)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=device)
         if world > 1:
             tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
+        reduce_ms[:] = [x.elapsed_time(y) for x, y in waits]
         return ms.item(), float(last)
 
     for _ in range(a.warmup):
@@ -372,23 +587,29 @@ def main():
     if rank == 0:
         clocks.start()
     launches0 = ops.LAUNCHES
-    if a.profile_kernels:
-        ops.PROFILE = []
-    ms_dev, loss_dev = timed(dev_batches, False, a.steps)
-    prof = ops.PROFILE
-    ops.PROFILE = None
+    ms_dev, loss_dev = timed(dev_batches, False, a.steps)           # `value`: no per-kernel events inside
     launches = ops.LAUNCHES - launches0
+    exposed_reduce = sum(reduce_ms) / max(1, len(reduce_ms)) if reduce_ms else 0.0
     ms_e2e, loss_e2e = timed(host_batches, True, a.steps)
+    # the same step again with a CUDA event pair around EVERY kernel launch: per-kernel time, roofline, shares (costs ~3 %)
+    prof, ms_prof = None, None
+    if a.profile_kernels and a.instrumented_steps > 0:
+        ops.PROFILE = []
+        ms_prof, _ = timed(dev_batches, False, a.instrumented_steps)
+        prof, ops.PROFILE = ops.PROFILE, None
     clk = clocks.stop() if rank == 0 else None
 
-    samples_per_step = mbs * M
+    samples_per_step = mbs * M * dp
     value = samples_per_step * a.steps / (ms_dev / 1000.0)
     e2e_value = samples_per_step * a.steps / (ms_e2e / 1000.0)
     lt = torch.tensor([launches], device=device, dtype=torch.float64)
     mem_t = torch.tensor([torch.cuda.max_memory_allocated(device) / 2**30], device=device, dtype=torch.float64)
+    red_t = torch.tensor([exposed_reduce], device=device, dtype=torch.float64)
     if world > 1:
         tdist.all_reduce(lt)
         tdist.all_reduce(mem_t, op=tdist.ReduceOp.MAX)
+        tdist.all_reduce(red_t, op=tdist.ReduceOp.MAX)
+    train_tflop = fam['train_tflop'] * n_blocks / fam['blocks']
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): algorithmic 2MNK per launch / CUDA-event duration ----
     roof = None
@@ -396,17 +617,22 @@ def main():
     if prof:
         torch.cuda.synchronize()
         tot_ms = sum(s.elapsed_time(e) for s, e, _, _, _ in prof)
-        busy_local = tot_ms / ms_dev if ms_dev else 0.0
-        tot_fl = sum(f for _, _, f, _, _ in prof)
+        busy_local = tot_ms / ms_prof if ms_prof else 0.0
         gemm_ms = sum(s.elapsed_time(e) for s, e, _, k, _ in prof if k == 'gemm')
         gemm_fl = sum(f for _, _, f, k, _ in prof if k == 'gemm')
-        attn_ms = sum(s.elapsed_time(e) for s, e, _, k, _ in prof if k.startswith('attn'))
-        attn_fl = sum(f for _, _, f, k, _ in prof if k.startswith('attn'))
+        attn = {}
+        for s_, e_, f_, k_, _t in prof:
+            if k_.startswith('attn'):
+                d = attn.setdefault(k_, [0.0, 0.0])
+                d[0] += s_.elapsed_time(e_)
+                d[1] += f_
+        attn_ms = sum(v[0] for v in attn.values())
+        attn_fl = sum(v[1] for v in attn.values())
         n_gemm = sum(1 for p in prof if p[3] == 'gemm')
         kind_ms = {}
         for s_, e_, f_, k_, _t in prof:
             kind_ms[k_] = kind_ms.get(k_, 0.0) + s_.elapsed_time(e_)
-        kind_share = {k: round(v / (ms_dev if ms_dev else 1), 4) for k, v in sorted(kind_ms.items(), key=lambda kv: -kv[1])}
+        kind_share = {k: round(v / (ms_prof if ms_prof else 1), 4) for k, v in sorted(kind_ms.items(), key=lambda kv: -kv[1])}
         by_shape = {}
         for s_, e_, f_, k_, tag in prof:
             if k_ == 'gemm':
@@ -415,10 +641,10 @@ def main():
                 d[1] += s_.elapsed_time(e_)
                 d[2] += f_
         breakdown = [{'MNK_aMN_bMN_epi_acc': list(t), 'n': v[0], 'ms': round(v[1], 2), 'tflops': round(v[2] / v[1] / 1e9, 1)}
-                     for t, v in sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:14]]
+                     for t, v in sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:16]]
         try:
             os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-            with open(os.path.join(ROOT, 'gpurun_out', f'bench_gemm_breakdown_rank{rank}.json'), 'w') as f:
+            with open(os.path.join(ROOT, 'gpurun_out', f'bench_gemm_breakdown_{a.family}_rank{rank}.json'), 'w') as f:
                 json.dump(breakdown, f, indent=1)
         except OSError:
             pass
@@ -430,17 +656,22 @@ def main():
             pass
         peak = peaks.get('bf16_tflops_sustained', 1400.0)
         achieved = gemm_fl / gemm_ms / 1e9 if gemm_ms > 0 else 0.0
+        traffic = gemm_traffic_from_profile()
         roof = {'bound': 'tensor', 'kernel': 'gemm_bf16_kernel (tcgen05, all epilogues/layouts)', 'achieved': achieved,
                 'peak': peak, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PF sustained',
-                'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': gemm_traffic_from_profile(),
+                'peak_measured_at_sm_mhz': (peaks.get('clocks_under_load') or {}).get('sm_mhz_median'),
+                'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic[0], 'traffic_source': traffic[1],
                 'launches_timed': n_gemm, 'avg_launch_ms': gemm_ms / max(1, n_gemm),
-                'share_of_step': gemm_ms / (ms_dev if ms_dev else 1),
+                'measured_over': f'{a.instrumented_steps} instrumented step(s) after the timed region ({ms_prof / a.instrumented_steps:.1f} ms/step; '
+                                 f'the timed region itself carries no per-kernel events: {ms_dev / a.steps:.1f} ms/step)',
+                'share_of_step': gemm_ms / (ms_prof if ms_prof else 1),
                 'attention': {'achieved': attn_fl / attn_ms / 1e9 if attn_ms > 0 else None, 'unit': 'TFLOP/s (algorithmic: 4LqLkD fwd, 2.5x bwd)',
-                              'share_of_step': attn_ms / (ms_dev if ms_dev else 1)},
-                'kernels_share_of_step': tot_ms / (ms_dev if ms_dev else 1), 'share_by_kernel': kind_share,
-                'step_tflops': TRAIN_TFLOP_PER_SAMPLE * (n_double + n_single) / 57.0 * value / max(1, world)}
+                              'share_of_step': attn_ms / (ms_prof if ms_prof else 1),
+                              'by_kernel': {k: round(v[1] / v[0] / 1e9, 1) for k, v in attn.items() if v[0] > 0}},
+                'kernels_share_of_step': tot_ms / (ms_prof if ms_prof else 1), 'share_by_kernel': kind_share,
+                'step_tflops_per_gpu': train_tflop * value / max(1, world)}
 
-    # kernel-busy fraction of every stage (instrumented kernels / step time): separates pipeline bubbles from imbalance
+    # kernel-busy fraction of every rank (instrumented kernels / step time): separates pipeline bubbles from imbalance
     busy_t = torch.zeros(world, device=device, dtype=torch.float64)
     busy_t[rank] = busy_local
     if world > 1:
@@ -448,47 +679,60 @@ def main():
     stage_busy = [round(float(x), 4) for x in busy_t.tolist()]
 
     cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and a.family == 'flux':
         del dev_batches, host_batches
-        v, desc, cores = cpu_reference_sample(a.res, a.text_len, n_double, n_single)
-        cpu = {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': desc}
+        n_double, n_single = (int(x) for x in a.layers.split(','))
+        vals = [cpu_reference_sample(a.res, a.text_len, n_double, n_single) for _ in range(3)]
+        vs = sorted(v for v, _, _ in vals)
+        cpu = {'value': vs[1], 'unit': 'samples/s', 'cores': vals[0][2], 'kind': 'port',
+               'sample': vals[-1][1] + '; median of 3 samples', 'min_max': [vs[0], vs[-1]]}
 
     link_name, schedule_name = type(engine.link).__name__, engine.pipeline_schedule
 
     if rank == 0:
         h2d = int(h2d_t.item())
         out = {
-            'metric': METRIC, 'value': value,
+            'metric': fam['metric'], 'value': value,
             'unit': 'samples/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms_dev / a.steps,
-            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-            'config': {'workload': f'Flux-dev full fine-tune bf16 {a.res}x{a.res} (configs[1]/[2] model), {n_double}+{n_single} blocks, '
-                                   f'{n_params * (1 if stages == 1 else stages) / 1e9:.1f}B params' + ('' if stages == 1 else ' (approx.)'),
-                       'global_batch': samples_per_step, 'micro_batch': mbs, 'micro_batches': M, 'seq_len': 4096 + a.text_len,
-                       'parallelism': f'pp{stages}', 'partition': 'flop-balanced manual split' if stages > 1 else 'single stage',
-                       'activation_recompute': False, 'train_tflop_per_sample': TRAIN_TFLOP_PER_SAMPLE,
-                       'optimizer': 'none (diagnostic)' if a.no_optimizer else 'torch.optim.AdamW(fused) bf16, clip 1.0',
+            'higher_is_better': True, 'scaling': 'strong' if dp == 1 else 'strong in pp, weak in dp', 'vs_baseline': None,
+            'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': workload + f', {n_params / 1e9:.2f}B parameters',
+                       'global_batch': samples_per_step, 'micro_batch': mbs, 'micro_batches': M,
+                       'seq_len': (4096 + a.text_len) if a.family == 'flux' else None,
+                       'parallelism': f'pp{stages}' + (f' x dp{dp}' if dp > 1 else ''), 'partition': partition_desc,
+                       'activation_recompute': False, 'train_tflop_per_sample': train_tflop,
+                       'optimizer': 'none (diagnostic)' if a.no_optimizer else 'torch.optim.AdamW(fused) bf16, clip 1.0 (fused squared-norm kernel)',
                        'l2_flush': 'working set (>=24 GB of weights+grads per step) is far larger than the 126 MB L2',
+                       'weights': f'random init, layer i seeded {WEIGHT_SEED}+i (identical model for every partition / GPU count)',
                        'stage_link': link_name, 'pipeline_schedule': schedule_name},
             'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
-                    'ms_per_step': ms_e2e / a.steps},
+                    'ms_per_step': ms_e2e / a.steps, 'loss': loss_e2e},
             'gpu_launches': int(lt.item()),
             'loss': loss_dev,
             'peak_mem_gib_max_rank': round(float(mem_t.item()), 1),
             'stage_kernel_busy_frac': stage_busy,
             'clocks': clk,
         }
+        if dp > 1:
+            out['dp_allreduce'] = {'exposed_ms_per_step_max_rank': round(float(red_t.item()), 3),
+                                   'overlapped_with_backward': bool(engine.dp_overlap and schedule_name != 'zb'),
+                                   'layers_started_in_backward_rank0': engine.dp_early_layers,
+                                   'bytes_per_rank': int(2 * n_params / stages)}
+        if probe:
+            out['config']['partition']['probe_ms_fwd_bwdin_bwdw'] = {k: [round(x, 3) for x in v] for k, v in probe.items()}
         if roof:
             out['roofline'] = roof
         if cpu:
             out['cpu_baseline'] = cpu
         # every value of `out` is a plain Python number by now: whatever the context measurement below does, the line prints
         library = None
-        if world == 1 and not a.no_library_baseline:
+        if world == 1 and not a.no_library_baseline and a.family == 'flux':
             try:
                 del engine, pm, model, layers, params
                 import gc
                 gc.collect()
                 torch.cuda.empty_cache()
+                n_double, n_single = (int(x) for x in a.layers.split(','))
                 library = gpu_library_sample(a.res, a.text_len, n_double, n_single, device)
             except Exception as exc:      # context only: never lose the bench line over it
                 library = {'error': repr(exc)[:300]}

@@ -119,3 +119,8 @@ SIGNATURES['dpipe_mod_bwd'] = (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_
 SIGNATURES['dpipe_mse_loss'] =(c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p])
 SIGNATURES['dpipe_fp8_to_bf16'] = (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p])
 SIGNATURES['dpipe_fp8_code_table'] = (c_int, [c_int, c_void_p])
+SIGNATURES['dpipe_grad_sumsq_blocks'] = (c_int, [])
+SIGNATURES['dpipe_grad_sumsq'] = (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p])
+SIGNATURES['dpipe_grad_scale'] = (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p])
+SIGNATURES['dpipe_noise_pack'] = (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int,
+                                          c_int, c_void_p])

@@ -30,7 +30,8 @@ constexpr int AB_THREADS = 384;
 constexpr int BT = 128;  // tile edge (queries and keys)
 constexpr int BHALF = 128 * 64 * 2;
 constexpr int BTILE = 2 * BHALF;  // 32 KiB
-constexpr int AB_SMEM_BYTES = 6 * BTILE + 4 * 512 /*lse,D x 2 stages*/ + 1024 + 256;
+constexpr int AB_STATS_BYTES = 4096;   // v1/v2: [2][lse 128 | D 128] floats; v3: 4-deep ring of the same
+constexpr int AB_SMEM_BYTES = 6 * BTILE + AB_STATS_BYTES + 1024 + 256;
 
 struct AttnBwdParams {
   const float* lse;    // [B,H,Lq] log2 domain
@@ -84,7 +85,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
   uint8_t* do_smem = smem + 4 * BTILE;  // 2 stages
   float* lse_smem = reinterpret_cast<float*>(smem + 6 * BTILE);  // [2][128]
   float* dl_smem = lse_smem + 256;                               // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * BTILE + 4 * 512);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * BTILE + AB_STATS_BYTES);
   uint64_t* kv_full = bars;        // [1]
   uint64_t* q_full = bars + 1;     // [2]
   uint64_t* q_empty = bars + 3;    // [2]
@@ -300,7 +301,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
   uint8_t* do_smem = smem + BTILE;
   uint8_t* k_smem = smem + 2 * BTILE;  // 2 stages
   uint8_t* v_smem = smem + 4 * BTILE;  // 2 stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * BTILE + 4 * 512);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * BTILE + AB_STATS_BYTES);
   uint64_t* qdo_full = bars;       // [1]
   uint64_t* k_full = bars + 1;     // [2]
   uint64_t* k_empty = bars + 3;    // [2]
@@ -502,6 +503,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
 // bf16 P / dS for the 32 columns a warp owns are written over the first 16 of those same columns.
 // =============================================================================================
 
+// STATS_WARPS: the two otherwise idle control warps (2, 3) stream LSE / D of every query tile into a 4-deep shared-memory
+// ring ahead of the softmax warpgroups (mbarrier full/empty), so the softmax loop holds no global load and no named barrier
+// (r01b capture: `barrier` 2.47 + `long_scoreboard` 2.33 warps per issue were the top stalls of this kernel).
+template <bool STATS_WARPS>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                      const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do,
@@ -512,8 +517,8 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   uint8_t* v_smem = smem + BTILE;
   uint8_t* q_smem = smem + 2 * BTILE;   // 2 stages of [128 q][128 d]
   uint8_t* do_smem = smem + 4 * BTILE;  // 2 stages
-  float* lse_smem = reinterpret_cast<float*>(smem + 6 * BTILE);  // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * BTILE + 4 * 512);
+  float* lse_smem = reinterpret_cast<float*>(smem + 6 * BTILE);  // !STATS_WARPS: [2][128]; STATS_WARPS: ring [4][lse 128 | D 128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * BTILE + AB_STATS_BYTES);
   uint64_t* kv_full = bars;        // [1]
   uint64_t* q_full = bars + 1;     // [2]
   uint64_t* q_empty = bars + 3;    // [2]
@@ -523,7 +528,9 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   uint64_t* p_ready = bars + 11;   // [2] softmax -> MMA (8 warps)
   uint64_t* ds_ready = bars + 13;  // [2] softmax -> MMA (8 warps)
   uint64_t* acc_done = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* stats_full = bars + 16;   // [4] loader warps -> softmax
+  uint64_t* stats_empty = bars + 20;  // [4] softmax (8 warps) -> loader warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const uint32_t warp = warp_id_uniform();
   const uint32_t lane = lane_id();
@@ -545,6 +552,7 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       mbar_init(smem_u32(&p_ready[s]), 4); mbar_init(smem_u32(&ds_ready[s]), 4);   // one softmax warpgroup per buffer
     }
     mbar_init(smem_u32(acc_done), 1);
+    for (int s = 0; s < 4; ++s) { mbar_init(smem_u32(&stats_full[s]), 2); mbar_init(smem_u32(&stats_empty[s]), 8); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<1>(smem_u32(tmem_slot), 512);
@@ -553,6 +561,24 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   const uint32_t T_ST = tmem_base, T_DPT = tmem_base + 128, T_DV = tmem_base + 256, T_DK = tmem_base + 384;
+
+  if (STATS_WARPS && (warp == 2 || warp == 3)) {
+    // warp 2: LSE, warp 3: D = rowsum(O * dO); rows beyond seq_q get LSE = +inf (P = 0) and D = 0
+    const float* src = (warp == 2 ? p.lse : p.delta) + (int64_t)bh * p.seq_q;
+    const float fill = warp == 2 ? INFINITY : 0.f;
+    for (int j = 0; j < nq; ++j) {
+      const int stage = j & 3;
+      mbar_wait(smem_u32(&stats_empty[stage]), ((j >> 2) & 1) ^ 1);
+      float* dst = lse_smem + stage * 256 + (warp == 2 ? 0 : 128);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int q = j * BT + r * 32 + (int)lane;
+        dst[r * 32 + lane] = q < p.seq_q ? __ldg(src + q) : fill;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&stats_full[stage]));
+    }
+  }
 
   if (warp == 0) {
     if (elect_one()) {
@@ -639,7 +665,12 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
     const uint32_t buf = wg;
     for (int t = wg, it = 0; t < nsub; t += 2, ++it) {
       const uint32_t rph = it & 1;
-      {   // stage LSE / D of the 64 query rows of this sub-tile (rows beyond seq_q: +inf -> P = 0)
+      if (STATS_WARPS) {   // the loader warps are several query tiles ahead: normally no wait at all
+        const int j = t >> 1, stage = j & 3;
+        mbar_wait(smem_u32(&stats_full[stage]), (j >> 2) & 1);
+        lse_s = lse_smem + stage * 256 + (t & 1) * 64;
+        dl_s = lse_s + 128;
+      } else {   // stage LSE / D of the 64 query rows of this sub-tile (rows beyond seq_q: +inf -> P = 0)
         const int q = t * 64 + (wg_tid & 63);
         named_bar_sync(1 + wg, 128);                   // previous sub-tile's readers are done
         if (wg_tid < 64) lse_s[wg_tid] = (q < p.seq_q) ? p.lse[(int64_t)bh * p.seq_q + q] : INFINITY;
@@ -680,7 +711,10 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&ds_ready[buf]));
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&ds_ready[buf]));
+        if (STATS_WARPS) mbar_arrive(smem_u32(&stats_empty[(t >> 1) & 3]));
+      }
     }
     mbar_wait(smem_u32(acc_done), 0);
     tc_fence_after();
@@ -728,7 +762,7 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
   uint8_t* do_smem = smem + BTILE;
   uint8_t* k_smem = smem + 2 * BTILE;  // 2 stages of [128 kv][128 d]
   uint8_t* v_smem = smem + 4 * BTILE;  // 2 stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * BTILE + 4 * 512);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * BTILE + AB_STATS_BYTES);
   uint64_t* qdo_full = bars;       // [1]
   uint64_t* k_full = bars + 1;     // [2]
   uint64_t* k_empty = bars + 3;    // [2]
@@ -897,6 +931,196 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
   if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// v3 dQ: three S / dP accumulator buffers in TMEM instead of two, and K / V streamed as 64-row half tiles.
+//   TMEM: S[3] 3x64 | dP[3] 3x64 | dQ 128  = 512 columns.
+// With two buffers the scores of sub-tile t+2 can only be issued once dS(t) has been consumed, so each softmax warpgroup
+// sits in the chain  dS(t) -> dQ(t) MMA -> scores(t+2) MMA -> softmax(t+2)  and the tensor pipe idles for the softmax
+// latency of every sub-tile (r01b: 52 % tensor-pipe active).  With three, scores(t+2) go out BEFORE the wait for dS(t):
+// when a warpgroup finishes sub-tile t its next one (t+2) is already in TMEM, and the pipe is fed as long as one softmax
+// pass (2 warpgroups alternating) is shorter than two sub-tiles of MMA work.  K / V travel as four 64-row slots each
+// (slot = t & 3, released per sub-tile), so a slot has two sub-tile periods to land before its scores are issued and the
+// MMA thread does not block on a full-tile load behind a pending dQ.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k64,
+                    const __grid_constant__ CUtensorMap tma_v64, const __grid_constant__ CUtensorMap tma_do,
+                    const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* q_smem = smem;
+  uint8_t* do_smem = smem + BTILE;
+  uint8_t* k_smem = smem + 2 * BTILE;  // 2 tiles of [128 kv][128 d] = 4 half-tile slots
+  uint8_t* v_smem = smem + 4 * BTILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * BTILE + AB_STATS_BYTES);
+  uint64_t* qdo_full = bars;        // [1]
+  uint64_t* k_full = bars + 1;      // [4]
+  uint64_t* k_empty = bars + 5;     // [4]
+  uint64_t* v_full = bars + 9;      // [4]
+  uint64_t* v_empty = bars + 13;    // [4]
+  uint64_t* sd_full = bars + 17;    // [3]
+  uint64_t* ds_ready = bars + 20;   // [3] (4 warps)
+  uint64_t* acc_done = bars + 23;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  constexpr int NB = 3;
+
+  const uint32_t warp = warp_id_uniform();
+  const uint32_t lane = lane_id();
+  const int q0 = blockIdx.x * BT;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int bh = b * p.heads + head;
+  const int nsub = (p.seq_k + 63) / 64;   // 64-key sub-tiles
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tma_q); tma_prefetch_desc(&tma_k64); tma_prefetch_desc(&tma_v64); tma_prefetch_desc(&tma_do);
+  }
+  if (warp == 1 && elect_one()) {
+    mbar_init(smem_u32(qdo_full), 1);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(smem_u32(&k_full[s]), 1); mbar_init(smem_u32(&k_empty[s]), 1);
+      mbar_init(smem_u32(&v_full[s]), 1); mbar_init(smem_u32(&v_empty[s]), 1);
+    }
+    for (int s = 0; s < NB; ++s) { mbar_init(smem_u32(&sd_full[s]), 1); mbar_init(smem_u32(&ds_ready[s]), 4); }
+    mbar_init(smem_u32(acc_done), 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<1>(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t T_S = tmem_base, T_DP = tmem_base + NB * 64, T_DQ = tmem_base + 2 * NB * 64;
+  // byte offset of half-tile slot `s` inside a 2-tile operand buffer: tile (s >> 1), rows 64 * (s & 1)
+  auto slot_off = [](int s) { return (uint32_t)((s >> 1) * BTILE + (s & 1) * 8192); };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t qb = smem_u32(qdo_full);
+      mbar_expect_tx(qb, 2 * BTILE);
+      for (int h = 0; h < 2; ++h) {
+        tma_load_3d(&tma_q, qb, smem_u32(q_smem + h * BHALF), h * 64, q0, bh, kEvictFirst);
+        tma_load_4d(&tma_do, qb, smem_u32(do_smem + h * BHALF), h * 64, q0, head, b, kEvictFirst);
+      }
+      for (int t = 0; t < nsub; ++t) {
+        const int slot = t & 3;
+        const uint32_t ph = ((t >> 2) & 1) ^ 1;
+        mbar_wait(smem_u32(&k_empty[slot]), ph);
+        const uint32_t kb = smem_u32(&k_full[slot]);
+        mbar_expect_tx(kb, BTILE / 2);
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(&tma_k64, kb, smem_u32(k_smem + slot_off(slot) + h * BHALF), h * 64, t * 64, bh, kEvictLast);
+        mbar_wait(smem_u32(&v_empty[slot]), ph);
+        const uint32_t vb = smem_u32(&v_full[slot]);
+        mbar_expect_tx(vb, BTILE / 2);
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(&tma_v64, vb, smem_u32(v_smem + slot_off(slot) + h * BHALF), h * 64, t * 64, bh, kEvictLast);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(BT, 64, false, false);   // [128 q] x [64 kv]
+      constexpr uint32_t idesc_g = make_idesc_bf16(BT, 128, false, true);   // [128 q] x [128 d], K = 64 keys
+      const uint32_t qb = smem_u32(q_smem), dob = smem_u32(do_smem);
+      mbar_wait(smem_u32(qdo_full), 0);
+      auto issue_scores = [&](int t) {
+        const int slot = t & 3;
+        const uint32_t ph = (t >> 2) & 1;
+        mbar_wait(smem_u32(&k_full[slot]), ph);
+        mbar_wait(smem_u32(&v_full[slot]), ph);
+        tc_fence_after();
+        const uint32_t kb = smem_u32(k_smem + slot_off(slot));
+        const uint32_t vb = smem_u32(v_smem + slot_off(slot));
+        const uint32_t buf = t % NB;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss<1>(T_S + buf * 64, make_smem_desc(qb + kmajor_off(k), 16, 1024), make_smem_desc(kb + kmajor_off(k), 16, 1024),
+                     idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss<1>(T_DP + buf * 64, make_smem_desc(dob + kmajor_off(k), 16, 1024), make_smem_desc(vb + kmajor_off(k), 16, 1024),
+                     idesc_s, k != 0);
+        umma_commit<1>(smem_u32(&sd_full[buf]));
+        umma_commit<1>(smem_u32(&v_empty[slot]));      // this V half tile is consumed by its dP
+      };
+      for (int t = 0; t < NB - 1 && t < nsub; ++t) issue_scores(t);
+      for (int t = 0; t < nsub; ++t) {
+        if (t + NB - 1 < nsub) issue_scores(t + NB - 1);
+        const int slot = t & 3;
+        const uint32_t buf = t % NB, rph = (t / NB) & 1;
+        const uint32_t kb = smem_u32(k_smem + slot_off(slot));
+        mbar_wait(smem_u32(&ds_ready[buf]), rph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // dQ[q, d] += dS[q, 64 kv] K[64 kv, d]
+          umma_ts(T_DQ, T_DP + buf * 64 + k * 8, make_smem_desc(kb + k * 2048, BHALF, 1024), idesc_g, (t | k) != 0);
+        umma_commit<1>(smem_u32(&k_empty[slot]));
+      }
+      umma_commit<1>(smem_u32(acc_done));
+    }
+  } else if (warp >= 4) {
+    const uint32_t quad = warp & 3;
+    const int wg = (warp - 4) >> 2;          // warpgroup wg takes the key sub-tiles t with t % 2 == wg (buffer t % 3)
+    const int half = wg;                     // (epilogue: which 64 output columns this warp stores)
+    const uint32_t lane_base = (quad * 32u) << 16;
+    const int q = q0 + quad * 32 + lane;
+    const bool ok = q < p.seq_q;
+    const float lse = ok ? p.lse[(int64_t)bh * p.seq_q + q] : INFINITY;
+    const float dl = ok ? p.delta[(int64_t)bh * p.seq_q + q] : 0.f;
+    const float c = p.scale_log2;
+    for (int t = wg; t < nsub; t += 2) {
+      const uint32_t buf = t % NB, rph = (t / NB) & 1;
+      const int valid = p.seq_k - t * 64;    // keys of this sub-tile that exist (>= 64 except in the last one)
+      mbar_wait(smem_u32(&sd_full[buf]), rph);
+      tc_fence_after();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32], rd[32], pk[16];
+        tmem_ld_x32(T_S + lane_base + buf * 64 + hh * 32, r);
+        tmem_ld_x32(T_DP + lane_base + buf * 64 + hh * 32, rd);
+        tmem_ld_wait();
+#pragma unroll
+        for (int x = 0; x < 32; x += 2) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(r[x]), c, -lse));
+          float p1 = fast_exp2(fmaf(__uint_as_float(r[x + 1]), c, -lse));
+          if (hh * 32 + x >= valid) p0 = 0.f;
+          if (hh * 32 + x + 1 >= valid) p1 = 0.f;
+          pk[x >> 1] = pack_bf16(p0 * (__uint_as_float(rd[x]) - dl), p1 * (__uint_as_float(rd[x + 1]) - dl));
+        }
+        tmem_st_x16(T_DP + lane_base + buf * 64 + hh * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ds_ready[buf]));
+    }
+    mbar_wait(smem_u32(acc_done), 0);
+    tc_fence_after();
+    __nv_bfloat16* dst = p.dq + ((int64_t)bh * p.seq_q + q) * 128 + half * 64;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      uint32_t rr[32];
+      tmem_ld_x32(T_DQ + lane_base + half * 64 + cc * 32, rr);
+      tmem_ld_wait();
+      if (ok) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + cc * 32);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          uint4 qv;
+          qv.x = pack_bf16(__uint_as_float(rr[x * 8 + 0]) * p.scale, __uint_as_float(rr[x * 8 + 1]) * p.scale);
+          qv.y = pack_bf16(__uint_as_float(rr[x * 8 + 2]) * p.scale, __uint_as_float(rr[x * 8 + 3]) * p.scale);
+          qv.z = pack_bf16(__uint_as_float(rr[x * 8 + 4]) * p.scale, __uint_as_float(rr[x * 8 + 5]) * p.scale);
+          qv.w = pack_bf16(__uint_as_float(rr[x * 8 + 6]) * p.scale, __uint_as_float(rr[x * 8 + 7]) * p.scale);
+          d4[x] = qv;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
 }  // namespace dpipe
 
 extern "C" int dpipe_attn_bwd(const dpipe_attn_bwd_args* a, void* stream) {
@@ -930,8 +1154,10 @@ extern "C" int dpipe_attn_bwd(const dpipe_attn_bwd_args* a, void* stream) {
   if (!configured) {
     DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
     DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
-    DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
+    DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
+    DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
     DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
+    DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
     configured = true;
   }
   AttnBwdParams p;
@@ -941,15 +1167,25 @@ extern "C" int dpipe_attn_bwd(const dpipe_attn_bwd_args* a, void* stream) {
   p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv);
   p.batch = B; p.heads = H; p.seq_q = Lq; p.seq_k = Lk;
   p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
-  static int variant = -1;   // DPIPE_ATTN_BWD=1 selects the un-pipelined v1 kernels (kept for A/B measurements)
-  if (variant < 0) { const char* e = getenv("DPIPE_ATTN_BWD"); variant = (e && e[0] == '1') ? 1 : 2; }
-  if (variant == 1) {
+  // DPIPE_ATTN_BWD selects older variants for A/B measurements: 1 = un-pipelined v1, 2 = v2 (round 1), default 3 =
+  // v2 dK/dV with the LSE / D loader warps + v3 dQ (three TMEM score buffers, half-tile K / V slots)
+  static int variant = -1;
+  if (variant < 0) { const char* e = getenv("DPIPE_ATTN_BWD"); variant = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3; }
+  if (variant == 3) {
+    CUtensorMap tk64, tv64;
+    if ((rc = make_tmap_3d_bf16(&tk64, a->k, 128, Lk, bh, 128, (uint64_t)Lk * 128, 64, 64, 1))) return rc;
+    if ((rc = make_tmap_3d_bf16(&tv64, a->v, 128, Lk, bh, 128, (uint64_t)Lk * 128, 64, 64, 1))) return rc;
+    attn_bwd_dkv2_kernel<true><<<dim3((Lk + BT - 1) / BT, H, B), AB_THREADS, AB_SMEM_BYTES, s>>>(tq, tk, tv, tdo, p);
+    DPIPE_CUDA_CHECK(cudaGetLastError());
+    attn_bwd_dq3_kernel<<<dim3((Lq + BT - 1) / BT, H, B), AB_THREADS, AB_SMEM_BYTES, s>>>(tq, tk64, tv64, tdo, p);
+    DPIPE_CUDA_CHECK(cudaGetLastError());
+  } else if (variant == 1) {
     attn_bwd_dkv_kernel<<<dim3((Lk + BT - 1) / BT, H, B), AB_THREADS, AB_SMEM_BYTES, s>>>(tq, tk, tv, tdo, p);
     DPIPE_CUDA_CHECK(cudaGetLastError());
     attn_bwd_dq_kernel<<<dim3((Lq + BT - 1) / BT, H, B), AB_THREADS, AB_SMEM_BYTES, s>>>(tq, tk, tv, tdo, p);
     DPIPE_CUDA_CHECK(cudaGetLastError());
   } else {
-    attn_bwd_dkv2_kernel<<<dim3((Lk + BT - 1) / BT, H, B), AB_THREADS, AB_SMEM_BYTES, s>>>(tq, tk, tv, tdo, p);
+    attn_bwd_dkv2_kernel<false><<<dim3((Lk + BT - 1) / BT, H, B), AB_THREADS, AB_SMEM_BYTES, s>>>(tq, tk, tv, tdo, p);
     DPIPE_CUDA_CHECK(cudaGetLastError());
     attn_bwd_dq2_kernel<<<dim3((Lq + BT - 1) / BT, H, B), AB_THREADS, AB_SMEM_BYTES, s>>>(tq, tk, tv, tdo, p);
     DPIPE_CUDA_CHECK(cudaGetLastError());

@@ -639,16 +639,21 @@ class FluxPipeline(PluginSurface):
             t = time_shift(mu, 1.0, t)
         x_1 = latents
         x_0 = torch.randn_like(x_1)
-        te = t.view(-1, 1, 1, 1)
-        x_t = (1 - te) * x_1 + te * x_0
-        target = x_0 - x_1
-        guidance_vec = torch.full((bs,), float(self.model_config.get('guidance', 1.0)), device=x_t.device,
-                                  dtype=torch.float32)
-        x_t = pack_latents(x_t)
-        target = pack_latents(target)
-        img_seq_len = torch.tensor(x_t.shape[1], device=x_t.device).repeat((bs,))
+        if self._noise_on_device(x_1):
+            # t and x_0 come from the host RNG in the reference's order; mix + target + packing run on the device
+            x_t, target = ops.noise_on_device(x_1, x_0, t, True, self.device)
+            guidance_vec = torch.full((bs,), float(self.model_config.get('guidance', 1.0)), dtype=torch.float32)
+        else:
+            te = t.view(-1, 1, 1, 1)
+            x_t = (1 - te) * x_1 + te * x_0
+            target = x_0 - x_1
+            guidance_vec = torch.full((bs,), float(self.model_config.get('guidance', 1.0)), device=x_t.device,
+                                      dtype=torch.float32)
+            x_t = pack_latents(x_t)
+            target = pack_latents(target)
+        img_seq_len = torch.tensor(x_t.shape[1], device=latents.device).repeat((bs,))
         if 'control_latents' in inputs:
-            control = inputs['control_latents'].float()
+            control = inputs['control_latents'].float().to(x_t.device)
             assert control.shape == latents.shape
             cids = latent_image_ids(h // 2, w // 2, control.device, control.dtype)
             cids[..., 0] = 1

@@ -12,8 +12,9 @@ kernels consume as one matrix (q,k,v[,proj_mlp]) are allocated fused and exposed
 The arithmetic (including where bf16 roundings happen under the reference's autocast) is the one restated in
 oracle/flux_ref.py; tests/test_flux_blocks_gpu.py checks both directions against it.
 
-Memory policy (B200, 180 GB): no activation recompute of GEMMs or attention — a block saves its bf16 intermediates
-(~0.5 GB per block per sample at 1024^2) and only the cheap LayerNorm+modulation is recomputed in backward.
+Memory policy (B200, 180 GB): no activation recompute at all — a block saves its bf16 intermediates, including the
+LayerNorm+modulation outputs that feed its GEMMs (~0.54 GB per block per sample at 1024^2; round 1 recomputed those two
+HBM passes per stream in backward: 1.5 % of the step for 2 GB per sample).
 """
 import torch
 from torch import nn
@@ -173,7 +174,7 @@ def _ragged_attn_bwd(saved, d_o, shape):
 
 class _Stream:
     """Per-stream (image or text) state saved by the double block forward."""
-    __slots__ = ('x', 'mod', 'mean1', 'rstd1', 'y_attn', 'x1', 'mean2', 'rstd2', 'u', 'h', 'y_mlp', 'L', 'off')
+    __slots__ = ('x', 'mod', 'mean1', 'rstd1', 'xn', 'y_attn', 'x1', 'mean2', 'rstd2', 'xn2', 'u', 'h', 'y_mlp', 'L', 'off')
 
 
 class FluxDoubleBlockFn(torch.autograd.Function):
@@ -206,7 +207,8 @@ class FluxDoubleBlockFn(torch.autograd.Function):
             m = st.mod
             xn, st.mean1, st.rstd1 = ops.ln_modulate_fwd(st.x, m[:, D:2 * D], m[:, 0:D], B, L)
             e = ops.make_qkv_epilogue(q, k, v, nq.weight, nk.weight, cos, sin, H, Ltot, off, qhat, khat, q_rstd, k_rstd)
-            ops.gemm(xn, fq.weight, bias=fq.bias, epilogue=ops.EPI_QKV_ROPE, out=xn, rows_per_batch=L, qkv=e)
+            ops.gemm(xn, fq.weight, bias=fq.bias, epilogue=ops.EPI_QKV_ROPE, out=xn, rows_per_batch=L, qkv=e)   # (no token-major output: `out` is not written)
+            st.xn = xn
             streams.append(st)
         if txt_lens is None:
             o, lse = ops.attn_fwd(q, k, v)                                # o: [B*Ltot, H*HD] token-major
@@ -225,6 +227,7 @@ class FluxDoubleBlockFn(torch.autograd.Function):
                 ops.gemm(o3[b, off:off + L], wo.weight, bias=wo.bias, epilogue=ops.EPI_GATE_RES, aux=st.x[rs],
                          gate=m[b:b + 1, 2 * D:3 * D], out=st.x1[rs], out2=st.y_attn[rs], rows_per_batch=L)
             xn2, st.mean2, st.rstd2 = ops.ln_modulate_fwd(st.x1, m[:, 4 * D:5 * D], m[:, 3 * D:4 * D], B, L)
+            st.xn2 = xn2
             w1, w2 = ff.net[0].proj, ff.net[2]
             st.u = torch.empty((B * L, w1.weight.shape[0]), dtype=bf, device=dev)
             st.h = ops.gemm(xn2, w1.weight, bias=w1.bias, epilogue=ops.EPI_BIAS_GELU, out2=st.u)
@@ -271,7 +274,7 @@ class FluxDoubleBlockFn(torch.autograd.Function):
                     ops.gemm(dy2, h, a_mn=True, b_mn=True, out=g, accumulate=acc)                      # dW2 = dy2^T h
                     _acc_vec(w2.bias, db2)
                 ops.defer(wgrad_w2)
-            xn2, _, _ = ops.ln_modulate_fwd(st.x1, m[:, 4 * D:5 * D], m[:, 3 * D:4 * D], B, L, save_stats=False)
+            xn2 = st.xn2
             if w1.weight.requires_grad:
                 db1 = ops.colsum(du)
 
@@ -316,7 +319,7 @@ class FluxDoubleBlockFn(torch.autograd.Function):
             dw = torch.zeros((2, HD), dtype=torch.float32, device=dev)
             ops.qknorm_rope_bwd(dq, dk, dv, qhat, khat, q_rstd, k_rstd, nq.weight, nk.weight, cos, sin, dqkv, dbias, dw,
                                 B, H, Ltot, off, L)
-            xn, _, _ = ops.ln_modulate_fwd(st.x, m[:, D:2 * D], m[:, 0:D], B, L, save_stats=False)
+            xn = st.xn
             if fq.requires_grad():
                 def wgrad_qkv(fq=fq, nq=nq, nk=nk, dqkv=dqkv, xn=xn, dbias=dbias, dw=dw):
                     wgrad, bgrad, acc = fq.grads()
@@ -395,6 +398,19 @@ class FluxTransformerBlock(nn.Module):
 # =====================================================================================================================
 # single-stream block
 # =====================================================================================================================
+def _joint(enc, hidden):
+    """[enc; hidden] along the sequence.  The layer protocol hands the two streams over separately (models/flux.py:520-533),
+    but between two single blocks they are the two halves of ONE buffer (the previous block's output / the next block's
+    input gradient): then the joint tensor is a view, not a copy (batch 1: rows of the same [L, D] matrix)."""
+    B, Lt, D = enc.shape
+    Li = hidden.shape[1]
+    if (B == 1 and enc.dtype == hidden.dtype and enc.is_contiguous() and hidden.is_contiguous()
+            and enc.untyped_storage().data_ptr() == hidden.untyped_storage().data_ptr()
+            and hidden.storage_offset() == enc.storage_offset() + Lt * D):
+        return enc.as_strided((B, Lt + Li, D), ((Lt + Li) * D, D, 1))
+    return torch.cat([enc, hidden], dim=1)
+
+
 class FluxSingleBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, blk, hidden, enc, temb, cos, sin):
@@ -404,7 +420,7 @@ class FluxSingleBlockFn(torch.autograd.Function):
         H = blk.heads
         dev = hidden.device
         bf = torch.bfloat16
-        x = torch.cat([enc, hidden], dim=1).reshape(B * L, D)
+        x = _joint(enc, hidden).reshape(B * L, D)
         mod = _mod_fwd(temb, blk.norm.linear)                               # [B, 3D]: shift, scale, gate
         xn, mean, rstd = ops.ln_modulate_fwd(x, mod[:, D:2 * D], mod[:, 0:D], B, L)
         shp = (B, H, L, HD)
@@ -426,10 +442,10 @@ class FluxSingleBlockFn(torch.autograd.Function):
         y = torch.empty((B * L, D), dtype=bf, device=dev)
         po = blk.proj_out
         xo = ops.gemm(cat, po.weight, bias=po.bias, epilogue=ops.EPI_GATE_RES, aux=x, gate=mod[:, 2 * D:3 * D], out2=y,
-                      rows_per_batch=L, out=xn)
+                      rows_per_batch=L)
         xo3 = xo.view(B, L, D)
         ctx.blk = blk
-        ctx.saved = (x, mod, mean, rstd, q, k, v, qhat, khat, q_rstd, k_rstd, cat, u, lse, y)
+        ctx.saved = (x, mod, mean, rstd, q, k, v, qhat, khat, q_rstd, k_rstd, cat, u, lse, y, xn)
         ctx.save_for_backward(temb, cos, sin)
         ctx.dims = (B, Li, Lt, D, H)
         return xo3[:, Lt:], xo3[:, :Lt]
@@ -442,9 +458,9 @@ class FluxSingleBlockFn(torch.autograd.Function):
         L = Li + Lt
         dev = temb.device
         bf = torch.bfloat16
-        x, mod, mean, rstd, q, k, v, qhat, khat, q_rstd, k_rstd, cat, u, lse, y = ctx.saved
+        x, mod, mean, rstd, q, k, v, qhat, khat, q_rstd, k_rstd, cat, u, lse, y, xn = ctx.saved
         inner = blk.mlp_dim
-        dxo = torch.cat([d_enc, d_hidden], dim=1).reshape(B * L, D)
+        dxo = _joint(d_enc, d_hidden).reshape(B * L, D)
         if dxo.dtype != bf:
             dxo = dxo.to(bf)
         dmod = torch.empty((B, 3 * D), dtype=torch.float32, device=dev)
@@ -468,7 +484,6 @@ class FluxSingleBlockFn(torch.autograd.Function):
         dw = torch.zeros((2, HD), dtype=torch.float32, device=dev)
         ops.qknorm_rope_bwd(dq, dk, dv, qhat, khat, q_rstd, k_rstd, blk.attn.norm_q.weight, blk.attn.norm_k.weight, cos,
                             sin, dlin1, dbias[:3 * H * HD], dw, B, H, L, 0, L)
-        xn, _, _ = ops.ln_modulate_fwd(x, mod[:, D:2 * D], mod[:, 0:D], B, L, save_stats=False)
         if f1.requires_grad():
             ops.colsum(dlin1[:, 3 * H * HD:], out=dbias[3 * H * HD:])
 

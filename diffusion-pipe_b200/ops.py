@@ -497,3 +497,84 @@ def mse_loss(out, target, mask=None, want_grad=True):
     _prof_end(_e, 0.0, 'mse')
     LAUNCHES += 2
     return loss, dout
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# optimizer-step tail (gradient norm / clipping) and micro-batch preparation
+# ---------------------------------------------------------------------------------------------------------------
+_GRAD_DTYPES = {torch.bfloat16: 0, torch.float32: 1}
+
+
+def _tensor_lists(tensors):
+    n = len(tensors)
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tensors])
+    numels = (ctypes.c_int64 * n)(*[t.numel() for t in tensors])
+    dtypes = (ctypes.c_int * n)(*[_GRAD_DTYPES[t.dtype] for t in tensors])
+    return ptrs, numels, dtypes
+
+
+def grads_supported(tensors):
+    return all(t.is_cuda and t.dtype in _GRAD_DTYPES and t.is_contiguous() for t in tensors)
+
+
+def grad_sumsq(tensors):
+    """fp32 device scalar: sum over `tensors` (contiguous CUDA bf16 / fp32) of sum(g^2) — one pass, no fp32 copies"""
+    global LAUNCHES
+    dev = tensors[0].device
+    nl = max(1, (len(tensors) + 63) // 64)
+    blocks = lib().dpipe_grad_sumsq_blocks()
+    partials = torch.empty(blocks * nl, dtype=torch.float32, device=dev)
+    out = torch.empty((), dtype=torch.float32, device=dev)
+    ptrs, numels, dtypes = _tensor_lists(tensors)
+    _e = _prof_begin()
+    check(lib().dpipe_grad_sumsq(ptrs, numels, dtypes, len(tensors), _ptr(partials), partials.numel(), _ptr(out), _stream()),
+          'dpipe_grad_sumsq')
+    _prof_end(_e, 0.0, 'grad_sumsq')
+    LAUNCHES += nl + 1
+    return out
+
+
+def grad_scale(tensors, coef):
+    """g *= coef (fp32 device scalar) in place; the kernels return immediately when coef >= 1"""
+    global LAUNCHES
+    _req_f32(coef, 'coef')
+    ptrs, numels, dtypes = _tensor_lists(tensors)
+    _e = _prof_begin()
+    check(lib().dpipe_grad_scale(ptrs, numels, dtypes, len(tensors), _ptr(coef), _stream()), 'dpipe_grad_scale')
+    _prof_end(_e, 0.0, 'grad_scale')
+    LAUNCHES += max(1, (len(tensors) + 63) // 64)
+
+
+def noise_pack(x1, x0, t, pack):
+    """(x_t, target) = ((1-t) x1 + t x0, x0 - x1) on the device, fp32, bit-identical to the separate host ops; x1/x0 any
+    [bs, ...] shape; pack=True ([bs, c, h, w]) writes diffusers' 2x2-packed [bs, (h/2)(w/2), 4c] layout."""
+    global LAUNCHES
+    for a, n in ((x1, 'x1'), (x0, 'x0'), (t, 't')):
+        _req_f32(a, n)
+    assert x1.shape == x0.shape and x1.dim() >= 2 and t.numel() == x1.shape[0]
+    bs = x1.shape[0]
+    if pack:
+        assert x1.dim() == 4, 'packing takes [bs, c, h, w] latents'
+        c, frames, h, w = x1.shape[1], 1, x1.shape[2], x1.shape[3]
+        shape = (bs, (h // 2) * (w // 2), 4 * c)
+    else:
+        c, frames, h, w = 1, 1, 1, x1.numel() // bs
+        shape = tuple(x1.shape)
+    xt = torch.empty(shape, dtype=torch.float32, device=x1.device)
+    target = torch.empty(shape, dtype=torch.float32, device=x1.device)
+    check(lib().dpipe_noise_pack(_ptr(x1), _ptr(x0), _ptr(t), _ptr(xt), _ptr(target), bs, c, frames, h, w, int(bool(pack)),
+                                 _stream()), 'dpipe_noise_pack')
+    LAUNCHES += 1
+    return xt, target
+
+
+def noise_on_device(x1, x0, t, pack, device):
+    """`device_prepare_inputs`: the clean latents, the noise and the timesteps drawn on the host (same RNG stream and order
+    as the reference's prepare_inputs) go to the device through pinned memory, asynchronously; the flow-matching mix, the
+    target and the packing run there in one kernel.  Returns device tensors with the host path's bits."""
+    def up(a):
+        a = a.float().contiguous()
+        if a.device.type == 'cpu':
+            a = a.pin_memory() if not a.is_pinned() else a
+        return a.to(device, non_blocking=True)
+    return noise_pack(up(x1), up(x0), up(t), pack)

@@ -175,6 +175,11 @@ class PipelineEngine:
                 w[-1] -= 1
             self.zb_stage_weights = [max(1, x) for x in w]
         self._wgrad_queues = {}
+        self._comm_stream = None                      # side stream of the data-parallel gradient all-reduce
+        self._dp_reduced_layers, self._dp_reduced_ptrs = set(), set()
+        self.dp_reduce_events = None
+        self.dp_early_layers = 0                      # layers whose all-reduce started under the backward pass (last step)
+        self.dp_overlap = bool(self.config.get('dp_overlap', True))
         self._broadcast_model()
         self.link = self._make_link()
         self.total_loss = None
@@ -264,6 +269,7 @@ class PipelineEngine:
         self.total_loss = None
         self.fwd_losses = []
         self._data_iter = data_iter
+        self.dp_early_layers = 0
         if self.pipeline_schedule == 'zb':
             sched = ZeroBubbleSchedule(self.micro_batches, self.num_stages, self.stage_id, self.zb_costs, self.zb_max_inflight,
                                        self.zb_stage_weights)
@@ -314,7 +320,10 @@ class PipelineEngine:
             loaded = []
             for x in feats:
                 assert torch.is_tensor(x)
-                y = x.clone().detach().to(self.device, non_blocking=True)
+                # a private copy on the device, like the reference's `clone().detach().to(device)` — but a host tensor is
+                # copied ONCE (pinned memory: asynchronously), never cloned into pageable memory first
+                y = x.detach()
+                y = y.clone() if y.device == self.device else y.to(self.device, non_blocking=True)
                 y.requires_grad = y.is_floating_point() and train
                 loaded.append(y)
             self.pipe_buffers['inputs'][b] = tuple(loaded)
@@ -329,7 +338,15 @@ class PipelineEngine:
     def _exec_forward_pass(self, cmd, train):
         b = cmd.buffer_id
         inputs = self.pipe_buffers['inputs'][b]
-        outputs = self.module(inputs if len(inputs) > 1 else inputs[0])
+        # 1F1B runs the backward passes in micro-batch order: the gradients a layer holds after the backward of the LAST
+        # micro-batch are final, and the data-parallel all-reduce of that layer may start while earlier layers still compute
+        arm = (train and self.is_data_parallel and self.dp_overlap and self.pipeline_schedule != 'zb'
+               and getattr(cmd, 'micro_batch_id', -1) == self.micro_batches - 1)
+        self.module._grads_ready_cb = self._dp_reduce_layers if arm else None
+        try:
+            outputs = self.module(inputs if len(inputs) > 1 else inputs[0])
+        finally:
+            self.module._grads_ready_cb = None
         if self.is_last_stage():
             if self.loss_fn is not None:
                 loss = self.loss_fn(outputs, self.pipe_buffers['labels'][b])
@@ -421,42 +438,37 @@ class PipelineEngine:
     def _exec_reduce_tied_grads(self, cmd, train):
         pass   # no tied layers in any reference model definition
 
-    def _exec_reduce_grads(self, cmd, train):
-        if not self.is_data_parallel:
-            return
+    # ------------------------------------------------------------------ data-parallel gradient all-reduce (E7)
+    def _dp_reduce_buffers(self, grads):
+        """mean over the data-parallel group of every tensor in `grads`, in place.  Large contiguous buffers (the fused
+        weight-gradient allocations) go one collective each; small ones are coalesced.  NCCL averages inside the collective
+        (ReduceOp.AVG); other backends sum and divide."""
         group = self.grid.get_data_parallel_group()
         world = self.grid.data_parallel_size
-        params = [p for p in self.module.parameters() if p.requires_grad and p.grad is not None]
         comm_dtype = self.communication_data_type
-        # large gradients go in place; small ones are coalesced
+        avg = bool(grads) and grads[0].is_cuda and 'nccl' in str(dist.tdist.get_backend(group))
+        op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
         small, small_elems = [], 0
-        seen = set()
 
         def flush_small():
             nonlocal small, small_elems
             if not small:
                 return
             flat = torch.cat([g.reshape(-1).to(comm_dtype or g.dtype) for g in small])
-            dist.all_reduce(flat, group=group)
-            flat.div_(world)
+            dist.all_reduce(flat, op=op, group=group)
+            if not avg:
+                flat.div_(world)
             off = 0
             for g in small:
                 g.copy_(flat[off:off + g.numel()].view_as(g))
                 off += g.numel()
             small, small_elems = [], 0
 
-        for p in params:
-            g = p.grad
-            base = g._base if g._base is not None else g
-            if base is not g and base.is_contiguous():
-                g = base     # fused gradient buffer (views of one allocation): reduce it once as a whole
-            key = (g.data_ptr(), g.numel())
-            if key in seen:
-                continue
-            seen.add(key)
+        for g in grads:
             if g.numel() >= (1 << 20) and g.is_contiguous() and (comm_dtype is None or comm_dtype == g.dtype):
-                dist.all_reduce(g, group=group)
-                g.div_(world)
+                dist.all_reduce(g, op=op, group=group)
+                if not avg:
+                    g.div_(world)
             else:
                 small.append(g)
                 small_elems += g.numel()
@@ -464,10 +476,82 @@ class PipelineEngine:
                     flush_small()
         flush_small()
 
+    def _dp_reduce_layers(self, first, last, early=True):
+        """all-reduce the gradients of local layers [first, last) that have not been reduced in this step.  On CUDA the
+        collectives are enqueued on a side stream ordered after everything the compute stream holds right now, so they
+        run under the backward passes of the layers still to come (utils/patches.py:152-156 reduces after the drain)."""
+        params = []
+        for i in range(first, last):
+            if i in self._dp_reduced_layers:
+                continue
+            self._dp_reduced_layers.add(i)
+            self.dp_early_layers += int(early)
+            f = self.module.forward_funcs[i]
+            if isinstance(f, torch.nn.Module):
+                params += [p for p in f.parameters() if p.requires_grad and p.grad is not None]
+        grads = [g for g in self._unique_grad_buffers(params) if g.data_ptr() not in self._dp_reduced_ptrs]
+        if not grads:
+            return
+        self._dp_reduced_ptrs.update(g.data_ptr() for g in grads)
+        if self.device.type != 'cuda':
+            self._dp_reduce_buffers(grads)
+            return
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._comm_stream):
+            self._comm_stream.wait_event(ev)
+            self._dp_reduce_buffers(grads)
+
+    def _exec_reduce_grads(self, cmd, train):
+        if not self.is_data_parallel:
+            return
+        cuda = self.device.type == 'cuda'
+        if cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self._dp_reduce_layers(0, len(self.module.forward_funcs), early=False)      # whatever the backward hooks did not start
+        if cuda and self._comm_stream is not None:
+            done = torch.cuda.Event()
+            done.record(self._comm_stream)
+            torch.cuda.current_stream().wait_event(done)
+            e1.record()
+            self.dp_reduce_events = (e0, e1)     # elapsed = the part of the all-reduce the step actually waited for
+        self._dp_reduced_layers.clear()
+        self._dp_reduced_ptrs.clear()
+
+    @staticmethod
+    def _unique_grad_buffers(params):
+        """the gradient storage behind `params`, every byte once: per-projection views of one fused buffer collapse into
+        that buffer (flux_blocks.FusedParam), everything else is the .grad tensor itself"""
+        out, seen = [], set()
+        for p in params:
+            g = p.grad
+            if g is None:
+                continue
+            base = g._base if g._base is not None else g
+            if base is not g and base.is_contiguous() and base.dtype == g.dtype:
+                g = base
+            key = (g.data_ptr(), g.numel())
+            if key in seen:
+                continue
+            seen.add(key)
+            out.append(g.detach())
+        return out
+
     def _clip_grad_norm(self, params, max_norm):
-        """utils/patches.py:175-246: sqrt(sum of squared per-parameter fp32 norms) over the whole pipeline."""
-        grads = [p.grad for p in params if p.grad is not None]
-        if grads:
+        """utils/patches.py:175-246: sqrt(sum of squared per-parameter fp32 norms) over the whole pipeline, then
+        g *= min(1, max_norm / (norm + 1e-6)).  On the device both passes are one multi-tensor kernel each
+        (csrc/step_tail.cu): no fp32 copies of the gradients, and no pass at all over them when nothing is clipped."""
+        from .. import ops
+        grads = PipelineEngine._unique_grad_buffers(params)
+        fused = bool(grads) and ops.grads_supported(grads) and PipelineEngine._fused_views_cover(params, grads)
+        if not fused:
+            grads = [p.grad for p in params if p.grad is not None]
+        if fused:
+            total = ops.grad_sumsq(grads)
+        elif grads:
             norms = torch._foreach_norm([g.detach().float() if g.dtype != torch.float32 else g.detach() for g in grads])
             total = torch.stack(norms).square().sum().float()
         else:
@@ -482,9 +566,17 @@ class PipelineEngine:
             dist.all_reduce(scaled, group=self.grid.get_data_parallel_group())
             total_norm = scaled
         clip_coef = torch.clamp(max_norm / (total_norm + 1e-6), max=1.0)
-        if grads:
+        if fused:
+            ops.grad_scale(grads, clip_coef.float().reshape(1).contiguous())
+        elif grads:
             torch._foreach_mul_(grads, clip_coef.to(grads[0].device))
         return total_norm
+
+    @staticmethod
+    def _fused_views_cover(params, buffers):
+        """a fused buffer may be summed as a whole only if its views cover it (they do: FusedParam slices the whole
+        allocation; checked by element count so that a partially trainable fused weight falls back to the per-tensor path)"""
+        return sum(b.numel() for b in buffers) == sum(p.grad.numel() for p in params if p.grad is not None)
 
     def _exec_optimizer_step(self, cmd, train):
         params = [p for p in self.module.parameters() if p.requires_grad]

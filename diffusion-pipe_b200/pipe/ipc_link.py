@@ -239,7 +239,11 @@ class _Channel:
 
 
 class IpcLink:
-XX
+    def __init__(self, engine, rank_devices=None):
+        """rank_devices[r] = CUDA ordinal of global rank r (engine._make_link gathers them); None = ordinal follows the rank"""
+        self.engine = engine
+        self.device = engine.device
+        assert self.device.type == 'cuda'
         grid = engine.grid
         # 1F1B keeps at most `stages` micro-batches in flight on a stage; the zero-bubble order holds up to
         # `zb_max_inflight` (default 2 x stages).  A receiver that may hold n un-released activations needs n slots:

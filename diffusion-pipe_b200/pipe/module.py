@@ -264,16 +264,38 @@ class PipelineModule(nn.Module):
         params = [f.parameters() for f in funcs if isinstance(f, nn.Module)]
         return any(len(list(p)) > 0 for p in params)
 
+    @staticmethod
+    def _arm_grads_ready(x, first, last, cb):
+        """calls cb(first, last) once the gradient of EVERY input of layers [first, last) that takes part in autograd has
+        been computed: from then on no kernel of these layers' backward is still to be launched, so their parameter
+        gradients are final for this micro-batch (the engine starts their data-parallel all-reduce, pipe/engine.py)"""
+        ts = [t for t in (x if isinstance(x, (tuple, list)) else (x,)) if torch.is_tensor(t) and t.requires_grad]
+        if not ts:
+            return
+        left = [len(ts)]
+
+        def hook(_grad):
+            left[0] -= 1
+            if left[0] == 0:
+                cb(first, last)
+        for t in ts:
+            t.register_hook(hook)
+
     def forward(self, forward_input):
         x = forward_input
         interval = self.activation_checkpoint_interval
+        ready_cb = getattr(self, '_grads_ready_cb', None) if torch.is_grad_enabled() else None
         if interval == 0 or not torch.is_grad_enabled():
-            for f in self.forward_funcs:
+            for i, f in enumerate(self.forward_funcs):
+                if ready_cb is not None:
+                    self._arm_grads_ready(x, i, i + 1, ready_cb)
                 x = f(x)
             return x
         n = len(self.forward_funcs)
         for start in range(0, n, interval):
             funcs = self.forward_funcs[start:min(start + interval, n)]
+            if ready_cb is not None:
+                self._arm_grads_ready(x, start, min(start + interval, n), ready_cb)
 
             def run(*inputs, _funcs=funcs):
                 y = inputs if len(inputs) > 1 else inputs[0]

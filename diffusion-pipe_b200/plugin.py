@@ -9,6 +9,15 @@ class PluginSurface:
     framerate = None
     pixels_round_to_multiple = 16
 
+    def _noise_on_device(self, latents):
+        """`device_prepare_inputs = true` under [model]: prepare_inputs draws the timesteps and the noise
+        from the HOST generator exactly as the reference does (same stream, same order: bit-identical micro-batches) and
+        leaves the flow-matching mix, the target and the packing to one device kernel (csrc/step_tail.cu: noise_pack) fed
+        through pinned memory.  Only for host-resident latents and a CUDA model device."""
+        import torch
+        dev = torch.device(getattr(self, 'device', 'cpu'))
+        return bool(self.model_config.get('device_prepare_inputs', False)) and dev.type == 'cuda' and latents.device.type == 'cpu'
+
     # ---- block swapping (models/base.py:438-445): not needed on 180 GB parts; the driver calls the prepare_* hooks
     #      around every evaluation (train.py:230-241), so they exist and do nothing, as in BasePipeline ----
     def enable_block_swap(self, blocks_to_swap):

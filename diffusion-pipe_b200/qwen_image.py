@@ -367,15 +367,18 @@ class QwenImagePipeline(PluginSurface):
             t = time_shift(mu, 1.0, t)
         x_1 = latents
         x_0 = torch.randn_like(x_1)
-        te = t.view(-1, 1, 1)
-        x_t = (1 - te) * x_1 + te * x_0
-        target = x_0 - x_1
+        if self._noise_on_device(x_1):
+            x_t, target = ops.noise_on_device(x_1, x_0, t, False, self.device)     # latents are already packed here
+        else:
+            te = t.view(-1, 1, 1)
+            x_t = (1 - te) * x_1 + te * x_0
+            target = x_0 - x_1
         img_shapes = [(1, h // 2, w // 2)]
         if 'control_latents' in inputs:
             control = pack_latents(inputs['control_latents'].float())
             assert control.shape == latents.shape, (control.shape, latents.shape)
             extra = (torch.tensor(x_t.shape[1], device=device).repeat((bs,)),)
-            x_t = torch.cat([x_t, control], dim=1)
+            x_t = torch.cat([x_t, control.to(x_t.device)], dim=1)
             img_shapes.append((1, h // 2, w // 2))
         else:
             extra = tuple()

@@ -710,9 +710,12 @@ class WanPipeline(PluginSurface):
         t = sample_t(t, bs, quantile=timestep_quantile).to(latents.device)
         x_1 = latents
         x_0 = torch.randn_like(x_1)
-        te = t.view(-1, 1, 1, 1, 1)
-        x_t = (1 - te) * x_1 + te * x_0
-        target = x_0 - x_1
+        if self._noise_on_device(x_1):
+            x_t, target = ops.noise_on_device(x_1, x_0, t, False, self.device)
+        else:
+            te = t.view(-1, 1, 1, 1, 1)
+            x_t = (1 - te) * x_1 + te * x_0
+            target = x_0 - x_1
         t = t * 1000
         y = inputs['y'] if self.model_type == 'i2v_v2' else None          # models/wan/wan.py:335
         return (x_t, y, t, text_embeddings, seq_lens, None), (target, mask)

@@ -232,6 +232,27 @@ int dpipe_mse_loss(const void* out, const float* target, const float* mask, int6
                    float* loss, void* dout, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Optimizer-step tail and micro-batch preparation (HBM-bound).                                   */
+/* ------------------------------------------------------------------------------------------ */
+/* out[0] (device fp32) = sum over the n tensors of sum(g^2), fp32 accumulation per thread, per-CTA partials folded in
+ * double in a fixed order.  dtypes[i]: 0 = bf16, 1 = fp32; every tensor contiguous.  partials: at least
+ * dpipe_grad_sumsq_blocks() * ceil(n / 64) floats.
+ * replaces: the per-parameter `p.grad.data.float().norm(2)` loop of clip_grad_norm_ (utils/patches.py:204-224). */
+int dpipe_grad_sumsq_blocks(void);
+int dpipe_grad_sumsq(const void* const* ptrs, const int64_t* numels, const int* dtypes, int n, float* partials,
+                     int64_t partials_len, float* out, void* stream);
+/* g *= *coef (device fp32 scalar) for the same tensor lists; returns without touching memory when *coef >= 1.
+ * replaces: `p.grad.data.mul_(clip_coef)` (utils/patches.py:238-243). */
+int dpipe_grad_scale(const void* const* ptrs, const int64_t* numels, const int* dtypes, int n, const float* coef,
+                     void* stream);
+/* flow-matching noising of one batch on the device, fp32, IEEE-rounded multiplies and adds (bit-identical to the host ops):
+ *   xt = (1 - t[b]) * x1 + t[b] * x0,   target = x0 - x1      x1, x0: [bs, c, frames, h, w] contiguous; t: [bs]
+ * pack != 0 (frames == 1): both outputs in diffusers' packed layout [bs, (h/2)(w/2), 4c] (2x2 patches, channel-major).
+ * replaces: models/flux.py:368-378, models/qwen_image.py:447-455 (pack) and models/wan/wan.py:400-404 (plain). */
+int dpipe_noise_pack(const float* x1, const float* x0, const float* t, float* xt, float* target, int bs, int c,
+                     int64_t frames, int h, int w, int pack, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* 1F1B pipeline schedule planner (host only).                                                   */
 /* replaces: utils/patches.py:113-160 (train_schedule_steps) driven by deepspeed==0.18.4          */
 /*           runtime/pipe/schedule.py TrainSchedule / InferenceSchedule helpers.                  */

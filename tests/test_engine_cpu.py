@@ -62,7 +62,7 @@ def _worker(rank, world, port, stages, outdir, partition, schedule='1f1b', pertu
         if (engine.is_first_stage() or engine.is_last_stage()) else float(engine.eval_batch(None, num_micro_batches=3))
     sd = {p.original_name: p.detach().clone() for p in pm.parameters()}
     torch.save({'losses': losses, 'norms': norms, 'eval': ev, 'params': sd, 'stage': engine.stage_id, 'dp': dp_rank,
-                'parts': pm.parts}, os.path.join(outdir, f'rank{rank}.pt'))
+                'parts': pm.parts, 'early': engine.dp_early_layers, 'nlayers': len(pm.forward_funcs)}, os.path.join(outdir, f'rank{rank}.pt'))
     dist.barrier()
 
 
@@ -132,6 +132,8 @@ def test_data_parallel_world_2():
     res = _run(2, 1)
     assert [r['dp'] for r in res] == [0, 1]
     _check(res, 2)
+    # the all-reduce of (all but at most the first) layers was started from inside the last micro-batch's backward pass
+    assert all(r['early'] >= r['nlayers'] - 1 for r in res), [(r['early'], r['nlayers']) for r in res]
 
 
 def test_engine_broadcasts_trainable_parameters_over_the_dp_group():

@@ -132,3 +132,45 @@ def test_activation_checkpointing_on_the_real_kernels(reentrant):
         for k in base:
             rel = ((grads[k] - base[k]).norm() / (base[k].norm() + 1e-12)).item()
             assert rel <= 2e-3, (k, rel)
+
+
+@pytest.mark.parametrize('family', ['flux', 'qwen', 'wan'])
+def test_device_side_noising_is_bit_identical_to_the_host_path(family):
+    """SURVEY.md 8(f)4, `device_prepare_inputs = true`: timesteps and noise still come from the host generator in the
+    reference's order (models/flux.py:343-372), the mix / target / packing run in one device kernel — every tensor of the
+    micro-batch must carry the bits of the host path (which tests/test_host_golden.py pins to the reference's own code)."""
+    if DEVICE != 'cuda':
+        pytest.skip('needs the device kernel')
+    g = torch.Generator().manual_seed(9)
+    bs = 2
+    if family == 'flux':
+        from diffusion_pipe_b200.flux import FluxPipeline as P
+        cfg = {'transformer_config': CFG, 'guidance': 1.0}
+        batch = {'latents': torch.randn(bs, 16, 32, 48, generator=g), 't5_embed': torch.randn(bs, 32, 64, generator=g).bfloat16(),
+                 'clip_embed': torch.randn(bs, 32, generator=g).bfloat16(), 'mask': torch.rand(bs, 64, 96, generator=g)}
+    elif family == 'qwen':
+        from diffusion_pipe_b200.qwen_image import QwenImagePipeline as P
+        cfg = {'transformer_config': {'num_attention_heads': 2, 'num_layers': 1, 'joint_attention_dim': 64}}
+        batch = {'latents': torch.randn(bs, 16, 1, 16, 24, generator=g), 'prompt_embeds': [torch.randn(n, 64, generator=g).bfloat16() for n in (9, 12)],
+                 'mask': None}
+        from diffusion_pipe_b200 import data_feed
+        batch = data_feed.BatchedDataset.collate([{'latents': batch['latents'][i], 'prompt_embeds': batch['prompt_embeds'][i], 'mask': None}
+                                                  for i in range(bs)])
+    else:
+        from diffusion_pipe_b200.wan import WanPipeline as P
+        cfg = {'transformer_config': {'dim': 256, 'ffn_dim': 512, 'num_heads': 2, 'num_layers': 1, 'text_dim': 64, 'text_len': 16}}
+        batch = {'latents': torch.randn(bs, 16, 3, 8, 12, generator=g), 'text_embeddings': torch.randn(bs, 16, 64, generator=g).bfloat16(),
+                 'seq_lens': torch.tensor([10, 16]), 'mask': None}
+    outs = []
+    for on_device in (False, True):
+        model = P({'model': dict(cfg, dtype='bfloat16', lazy_layers=True, device_prepare_inputs=on_device)})
+        torch.manual_seed(31)
+        outs.append(model.prepare_inputs({k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}))
+    (f0, l0), (f1, l1) = outs
+    assert any(torch.is_tensor(t) and t.is_cuda for t in f1) and l1[0].is_cuda       # the device path really ran
+    for a, b in zip(list(f0) + list(l0), list(f1) + list(l1)):
+        if a is None or b is None:
+            assert a is None and b is None
+            continue
+        assert a.dtype == b.dtype and a.shape == b.shape
+        assert torch.equal(a.cpu(), b.cpu())

@@ -222,3 +222,44 @@ def test_mse_loss(ops):
         l.backward()
         assert abs(loss.item() - l.item()) <= 1e-5 * max(1, abs(l.item()))
         _check(dout, of.grad)
+
+
+def test_grad_sumsq_and_scale_match_torch():
+    """csrc/step_tail.cu: the multi-tensor squared norm / conditional scale behind engine._clip_grad_norm
+    (utils/patches.py:175-246) — > 64 tensors (several launches), unaligned bf16 views, an fp32 tensor, tiny tensors"""
+    from diffusion_pipe_b200 import ops
+    torch.manual_seed(3)
+    big = torch.randn(3_000_017, device='cuda').bfloat16()
+    ts = [big[1:], torch.randn(1 << 20, device='cuda').bfloat16(), torch.randn(7, device='cuda').bfloat16(),
+          torch.randn(12345, device='cuda'), torch.randn(1, device='cuda').bfloat16()]
+    ts += [torch.randn(1000 + 13 * i, device='cuda').bfloat16() for i in range(140)]
+    ts = [t.contiguous() if not t.is_contiguous() else t for t in ts]
+    assert ops.grads_supported(ts)
+    want = sum(t.double().pow(2).sum() for t in ts).item()
+    got = ops.grad_sumsq(ts).item()
+    assert abs(got - want) / want <= 1e-5, (got, want)
+    assert ops.grad_sumsq(ts).item() == got                       # fixed reduction order: bitwise repeatable
+    before = [t.clone() for t in ts]
+    ops.grad_scale(ts, torch.ones(1, device='cuda'))              # coef >= 1: untouched
+    assert all(torch.equal(a, b) for a, b in zip(ts, before))
+    coef = torch.full((1,), 0.37, device='cuda')
+    ops.grad_scale(ts, coef)
+    for a, b in zip(ts, before):
+        assert torch.equal(a, (b.float() * coef).to(b.dtype))
+
+
+@pytest.mark.parametrize('shape,pack', [((2, 16, 32, 48), True), ((1, 16, 128, 128), True), ((2, 16, 3, 8, 12), False)])
+def test_noise_pack_is_bit_identical_to_the_host_ops(shape, pack):
+    """x_t = (1 - t) x_1 + t x_0, target = x_0 - x_1 and the 2x2 packing on the device give the bits of the reference's host
+    ops (models/flux.py:368-378): no FMA contraction, same rounding points"""
+    from diffusion_pipe_b200 import ops
+    from diffusion_pipe_b200.flux import pack_latents
+    g = torch.Generator().manual_seed(5)
+    x1, x0 = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+    t = torch.sigmoid(torch.randn(shape[0], generator=g))
+    te = t.view(-1, *([1] * (len(shape) - 1)))
+    xt_h, tg_h = (1 - te) * x1 + te * x0, x0 - x1
+    if pack:
+        xt_h, tg_h = pack_latents(xt_h), pack_latents(tg_h)
+    xt_d, tg_d = ops.noise_pack(x1.cuda(), x0.cuda(), t.cuda(), pack)
+    assert torch.equal(xt_d.cpu(), xt_h) and torch.equal(tg_d.cpu(), tg_h)

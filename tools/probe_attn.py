@@ -95,6 +95,26 @@ def run_case(name):
                 res['fa2_bwd_ms'] = ts[len(ts) // 2]; res['fa2_bwd_tflops'] = fl / ts[len(ts) // 2] / 1e9
             except Exception as ex:  # noqa
                 res['fa2_err'] = repr(ex)[:200]
+            # torch SDPA backward: the library path diffusers' Flux / Qwen attention processors dispatch to (cuDNN or flash)
+            for name, backend in (('cudnn', 'CUDNN_ATTENTION'), ('flash', 'FLASH_ATTENTION')):
+                try:
+                    from torch.nn.attention import SDPBackend, sdpa_kernel
+                    qs, ks, vs = (x.clone().requires_grad_(True) for x in (q, k, v))
+                    with sdpa_kernel(getattr(SDPBackend, backend)):
+                        osd = torch.nn.functional.scaled_dot_product_attention(qs, ks, vs)
+                        gos = torch.randn_like(osd)
+                        ts = []
+                        for it in range(8):
+                            flush.zero_()
+                            s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+                            s.record(); osd.backward(gos, retain_graph=True); e.record(); torch.cuda.synchronize()
+                            if it >= 3:
+                                ts.append(s.elapsed_time(e))
+                    ts.sort()
+                    res[f'sdpa_{name}_bwd_ms'] = ts[len(ts) // 2]; res[f'sdpa_{name}_bwd_tflops'] = fl / ts[len(ts) // 2] / 1e9
+                except Exception as ex:  # noqa
+                    res[f'sdpa_{name}_err'] = repr(ex)[:200]
+            res['variant'] = os.environ.get('DPIPE_ATTN_BWD', 'default(3)')
             res['rel'] = 0.0; res['bad_frac'] = 0.0
     elif kind == 'perf':
         q = torch.randn(B, H, Lq, 128, device=dev).bfloat16()
