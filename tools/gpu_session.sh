@@ -7,8 +7,8 @@
 #   poison    the same with DPIPE_TEST_POISON_EMPTY_CUDA=1: uninitialised CUDA memory reads as NaN (tests/conftest.py)
 #   bench     bench.py at N=1 (the driver's default line)
 #   launches  ncu launch list of the bench command + full captures of the top kernels (tools/profile_ncu.sh)
-#   wan       tools/probe_wan_block.py at the 14B shapes + tools/bench_family.py --model wan on a reduced depth
-#   qwen      tools/bench_family.py --model qwen_image on a reduced depth
+#   wan       tools/probe_wan_block.py at the 14B shapes + bench.py --family wan on a reduced depth
+#   qwen      bench.py --family qwen on a reduced depth
 #   scaleN    bench.py on N = 2 / 4 / 8 GPUs, 1F1B and zero-bubble
 set -u
 R=${1:-r02}; shift
@@ -22,8 +22,8 @@ for S in "$@"; do
     bench)    T=600 run bench1 python bench.py ;;
     launches) T=2400 run ncu bash tools/profile_ncu.sh "$R" ;;
     wan)      T=600 run wan_block python tools/probe_wan_block.py
-              T=600 run wan_family python tools/bench_family.py --model wan --layers 8 --micro-batches 4 ;;
-    qwen)     T=600 run qwen_family python tools/bench_family.py --model qwen_image --layers 12 --micro-batches 8 ;;
+              T=600 run wan_family python bench.py --family wan --blocks 8 --micro-batches 4 ;;
+    qwen)     T=600 run qwen_family python bench.py --family qwen --blocks 12 --micro-batches 8 ;;
     scale2|scale4|scale8)
               N=${S#scale}
               for SCH in 1f1b zb; do
