@@ -124,3 +124,13 @@ SIGNATURES['dpipe_grad_sumsq'] = (c_int, [c_void_p, c_void_p, c_void_p, c_int, c
 SIGNATURES['dpipe_grad_scale'] = (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p])
 SIGNATURES['dpipe_noise_pack'] = (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int,
                                           c_int, c_void_p])
+SIGNATURES['dpipe_exec_create'] = (c_int, [c_int, c_int, ctypes.c_double, ctypes.POINTER(c_void_p)])
+SIGNATURES['dpipe_exec_destroy'] = (c_int, [c_void_p])
+SIGNATURES['dpipe_exec_copy_stream'] = (c_void_p, [c_void_p])
+SIGNATURES['dpipe_exec_bind'] = (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int])
+SIGNATURES['dpipe_exec_set_layout'] = (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p])
+SIGNATURES['dpipe_exec_forget_layouts'] = (c_int, [c_void_p])
+SIGNATURES['dpipe_exec_load_plan'] = (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int])
+SIGNATURES['dpipe_exec_stage_send'] = (c_int, [c_void_p, c_int, c_int, c_int, c_void_p])
+SIGNATURES['dpipe_exec_recv_base'] = (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(c_void_p)])
+SIGNATURES['dpipe_exec_next'] = (c_int, [c_void_p, c_void_p, c_void_p])

@@ -565,7 +565,8 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   if (STATS_WARPS && (warp == 2 || warp == 3)) {
     // warp 2: LSE, warp 3: D = rowsum(O * dO); rows beyond seq_q get LSE = +inf (P = 0) and D = 0
     const float* src = (warp == 2 ? p.lse : p.delta) + (int64_t)bh * p.seq_q;
-    const float fill = warp == 2 ? INFINITY : 0.f;
+    const float fill = warp == 2 ? -INFINITY : 0.f;     // the ring holds -LSE (one packed FFMA2 operand per column pair)
+    const float sgn = warp == 2 ? -1.f : 1.f;
     for (int j = 0; j < nq; ++j) {
       const int stage = j & 3;
       mbar_wait(smem_u32(&stats_empty[stage]), ((j >> 2) & 1) ^ 1);
@@ -573,7 +574,7 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int q = j * BT + r * 32 + (int)lane;
-        dst[r * 32 + lane] = q < p.seq_q ? __ldg(src + q) : fill;
+        dst[r * 32 + lane] = q < p.seq_q ? sgn * __ldg(src + q) : fill;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&stats_full[stage]));
@@ -673,23 +674,27 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       } else {   // stage LSE / D of the 64 query rows of this sub-tile (rows beyond seq_q: +inf -> P = 0)
         const int q = t * 64 + (wg_tid & 63);
         named_bar_sync(1 + wg, 128);                   // previous sub-tile's readers are done
-        if (wg_tid < 64) lse_s[wg_tid] = (q < p.seq_q) ? p.lse[(int64_t)bh * p.seq_q + q] : INFINITY;
+        if (wg_tid < 64) lse_s[wg_tid] = (q < p.seq_q) ? -p.lse[(int64_t)bh * p.seq_q + q] : -INFINITY;
         else dl_s[wg_tid - 64] = (q < p.seq_q) ? p.delta[(int64_t)bh * p.seq_q + q] : 0.f;
         named_bar_sync(1 + wg, 128);
       }
       mbar_wait(smem_u32(&sd_full[buf]), rph);
       tc_fence_after();
-      float pv[64];
+      f32x2 pv[32];                                   // P of this thread's key row, two query columns per entry
+      const f32x2 c2 = f2_pack(c, c);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t r[32], pk[16];
         tmem_ld_x32(T_ST + lane_base + buf * 64 + hh * 32, r);
         tmem_ld_wait();
+        const f32x2* nl = reinterpret_cast<const f32x2*>(lse_s + hh * 32);   // -LSE of two adjacent query columns
 #pragma unroll
         for (int x = 0; x < 32; x += 2) {
-          pv[hh * 32 + x] = fast_exp2(fmaf(__uint_as_float(r[x]), c, -lse_s[hh * 32 + x]));
-          pv[hh * 32 + x + 1] = fast_exp2(fmaf(__uint_as_float(r[x + 1]), c, -lse_s[hh * 32 + x + 1]));
-          pk[x >> 1] = pack_bf16(pv[hh * 32 + x], pv[hh * 32 + x + 1]);
+          const f32x2 e = f2_exp2_mufu(f2_fma(f2_pack_bits(r[x], r[x + 1]), c2, nl[x >> 1]));
+          pv[hh * 16 + (x >> 1)] = e;
+          float p0, p1;
+          f2_unpack(e, p0, p1);
+          pk[x >> 1] = pack_bf16(p0, p1);
         }
         tmem_st_x16(T_ST + lane_base + buf * 64 + hh * 16, pk);   // packed P over columns this thread has already read
       }
@@ -702,10 +707,14 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         uint32_t r[32], pk[16];
         tmem_ld_x32(T_DPT + lane_base + buf * 64 + hh * 32, r);
         tmem_ld_wait();
+        const f32x2* dl2 = reinterpret_cast<const f32x2*>(dl_s + hh * 32);
 #pragma unroll
-        for (int x = 0; x < 32; x += 2)
-          pk[x >> 1] = pack_bf16(pv[hh * 32 + x] * (__uint_as_float(r[x]) - dl_s[hh * 32 + x]),
-                                 pv[hh * 32 + x + 1] * (__uint_as_float(r[x + 1]) - dl_s[hh * 32 + x + 1]));
+        for (int x = 0; x < 32; x += 2) {
+          const f32x2 d = f2_mul(pv[hh * 16 + (x >> 1)], f2_sub(f2_pack_bits(r[x], r[x + 1]), dl2[x >> 1]));
+          float d0, d1;
+          f2_unpack(d, d0, d1);
+          pk[x >> 1] = pack_bf16(d0, d1);
+        }
         tmem_st_x16(T_DPT + lane_base + buf * 64 + hh * 16, pk);
       }
       tmem_st_wait();
@@ -932,6 +941,26 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
 }
 
 
+// dS = P * (dP - D) for 32 score columns of one query row: P = exp2(S * c - LSE); packed fp32 pairs throughout
+// (FFMA2 / FADD2 / FMUL2: the FMA pipe, not MUFU and not the tensor core, bounded the round-1 kernels)
+template <bool MASK>
+__device__ __forceinline__ void dq_softmax_chunk(const uint32_t (&r)[32], const uint32_t (&rd)[32], uint32_t (&pk)[16],
+                                                 f32x2 c2, f32x2 nlse2, f32x2 dl2, int valid) {
+#pragma unroll
+  for (int x = 0; x < 32; x += 2) {
+    f32x2 e = f2_exp2_mufu(f2_fma(f2_pack_bits(r[x], r[x + 1]), c2, nlse2));
+    if (MASK && x + 1 >= valid) {       // keys beyond seq_k (last, partial sub-tile only)
+      float p0, p1;
+      f2_unpack(e, p0, p1);
+      e = f2_pack(x >= valid ? 0.f : p0, 0.f);
+    }
+    const f32x2 d = f2_mul(e, f2_sub(f2_pack_bits(rd[x], rd[x + 1]), dl2));
+    float d0, d1;
+    f2_unpack(d, d0, d1);
+    pk[x >> 1] = pack_bf16(d0, d1);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // v3 dQ: three S / dP accumulator buffers in TMEM instead of two, and K / V streamed as 64-row half tiles.
 //   TMEM: S[3] 3x64 | dP[3] 3x64 | dQ 128  = 512 columns.
@@ -1068,9 +1097,11 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     const float lse = ok ? p.lse[(int64_t)bh * p.seq_q + q] : INFINITY;
     const float dl = ok ? p.delta[(int64_t)bh * p.seq_q + q] : 0.f;
     const float c = p.scale_log2;
+    const f32x2 c2 = f2_pack(c, c), nlse2 = f2_pack(-lse, -lse), dl2 = f2_pack(dl, dl);
     for (int t = wg; t < nsub; t += 2) {
       const uint32_t buf = t % NB, rph = (t / NB) & 1;
       const int valid = p.seq_k - t * 64;    // keys of this sub-tile that exist (>= 64 except in the last one)
+      const bool partial = valid < 64;
       mbar_wait(smem_u32(&sd_full[buf]), rph);
       tc_fence_after();
 #pragma unroll
@@ -1079,14 +1110,8 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
         tmem_ld_x32(T_S + lane_base + buf * 64 + hh * 32, r);
         tmem_ld_x32(T_DP + lane_base + buf * 64 + hh * 32, rd);
         tmem_ld_wait();
-#pragma unroll
-        for (int x = 0; x < 32; x += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(r[x]), c, -lse));
-          float p1 = fast_exp2(fmaf(__uint_as_float(r[x + 1]), c, -lse));
-          if (hh * 32 + x >= valid) p0 = 0.f;
-          if (hh * 32 + x + 1 >= valid) p1 = 0.f;
-          pk[x >> 1] = pack_bf16(p0 * (__uint_as_float(rd[x]) - dl), p1 * (__uint_as_float(rd[x + 1]) - dl));
-        }
+        if (!partial) dq_softmax_chunk<false>(r, rd, pk, c2, nlse2, dl2, 0);
+        else dq_softmax_chunk<true>(r, rd, pk, c2, nlse2, dl2, valid - hh * 32);
         tmem_st_x16(T_DP + lane_base + buf * 64 + hh * 16, pk);
       }
       tmem_st_wait();

@@ -16,6 +16,8 @@
 //
 // Replaces torch SDPA / flash_attn as dispatched by the reference's Flux blocks
 // (reference: diffusers attention inside models/flux.py:502,525; Wan: models/wan/attention.py:108-122).
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "sm100_common.cuh"
 
@@ -38,6 +40,9 @@ struct AttnFwdParams {
   float scale_log2;  // softmax scale * log2(e)
 };
 
+// POLY: of every 8 column pairs of a score row, this many take their exponential from the FMA-pipe polynomial instead of
+// MUFU (0 = all MUFU).  The row maximum, the scaled subtraction and the row sum run on packed fp32 pairs / 3-input max.
+template <int POLY>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                 const __grid_constant__ CUtensorMap tma_v, const AttnFwdParams p) {
@@ -206,11 +211,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int x = 0; x < 128; x += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(r[x]));
-        mx1 = fmaxf(mx1, __uint_as_float(r[x + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(r[x + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(r[x + 3]));
+      for (int x = 0; x < 128; x += 8) {   // FMNMX3: two new columns per instruction
+        mx0 = fmax3(mx0, __uint_as_float(r[x]), __uint_as_float(r[x + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(r[x + 2]), __uint_as_float(r[x + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(r[x + 4]), __uint_as_float(r[x + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(r[x + 6]), __uint_as_float(r[x + 7]));
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       const float m_new = fmaxf(m, mx * c);
@@ -236,17 +241,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         }
       }
       // ---- P = exp2(S*c - m) in place (bf16 pairs packed into the low half of r), fp32 row sum ----
-      float s0 = 0.f, s1 = 0.f;
-      const float neg_m = -m;
+      f32x2 sum_a = f2_pack(0.f, 0.f), sum_b = sum_a;
+      const f32x2 c2 = f2_pack(c, c), neg_m2 = f2_pack(-m, -m);
 #pragma unroll
-      for (int x = 0; x < 128; x += 2) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(r[x]), c, neg_m));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(r[x + 1]), c, neg_m));
-        s0 += p0;
-        s1 += p1;
+      for (int x = 0; x < 128; x += 4) {
+        const f32x2 a0 = f2_fma(f2_pack_bits(r[x], r[x + 1]), c2, neg_m2);
+        const f32x2 a1 = f2_fma(f2_pack_bits(r[x + 2], r[x + 3]), c2, neg_m2);
+        // pairs are numbered x / 2 = 0..63; within every group of 8 the first POLY go to the polynomial
+        const f32x2 e0 = (((x >> 1) & 7) < POLY) ? f2_exp2_poly(a0) : f2_exp2_mufu(a0);
+        const f32x2 e1 = ((((x >> 1) + 1) & 7) < POLY) ? f2_exp2_poly(a1) : f2_exp2_mufu(a1);
+        sum_a = f2_add(sum_a, e0);
+        sum_b = f2_add(sum_b, e1);
+        float p0, p1, p2, p3;
+        f2_unpack(e0, p0, p1);
+        f2_unpack(e1, p2, p3);
         r[x >> 1] = pack_bf16(p0, p1);
+        r[(x >> 1) + 1] = pack_bf16(p2, p3);
       }
-      l += s0 + s1;
+      {
+        float s0, s1, s2, s3;
+        f2_unpack(sum_a, s0, s1);
+        f2_unpack(sum_b, s2, s3);
+        l += (s0 + s1) + (s2 + s3);
+      }
       tmem_st_x32(t_p, r);
       tmem_st_x32(t_p + 32, r + 32);
       tmem_st_wait();
@@ -302,8 +319,13 @@ extern "C" int dpipe_attn_fwd(const dpipe_attn_args* a, void* stream) {
   if ((rc = make_tmap_3d_bf16(&tk, a->k, HD, a->seq_k, bh, HD, (uint64_t)a->seq_k * HD, 64, TK, 1))) return rc;
   if ((rc = make_tmap_3d_bf16(&tv, a->v, HD, a->seq_k, bh, HD, (uint64_t)a->seq_k * HD, 64, TK, 1))) return rc;
   static bool configured = false;
+  static int poly = 2;   // DPIPE_ATTN_FWD_POLY = 0 | 2 | 4: column pairs out of 8 exponentiated on the FMA pipe (A/B knob)
   if (!configured) {
-    DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    const char* e = getenv("DPIPE_ATTN_FWD_POLY");
+    if (e && (e[0] == '0' || e[0] == '2' || e[0] == '4') && e[1] == 0) poly = e[0] - '0';
     configured = true;
   }
   AttnFwdParams p;
@@ -313,7 +335,10 @@ extern "C" int dpipe_attn_fwd(const dpipe_attn_args* a, void* stream) {
   p.batch = a->batch; p.heads = a->heads; p.seq_q = a->seq_q; p.seq_k = a->seq_k;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   dim3 grid((a->seq_q + 2 * TQ - 1) / (2 * TQ), a->heads, a->batch);
-  attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (poly == 0) attn_fwd_kernel<0><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tq, tk, tv, p);
+  else if (poly == 4) attn_fwd_kernel<4><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tq, tk, tv, p);
+  else attn_fwd_kernel<2><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tq, tk, tv, p);
   DPIPE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

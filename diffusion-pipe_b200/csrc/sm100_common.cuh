@@ -336,6 +336,76 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ---- packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2: one issue slot for two lanes) and 3-input max (FMNMX3) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_pack_bits(uint32_t lo, uint32_t hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void f2_unpack_bits(f32x2 v, uint32_t& lo, uint32_t& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// 2^x for a PAIR of arguments on the FMA / ALU pipes only (no MUFU): round-to-nearest split x = n + f with the
+// 1.5 * 2^23 trick, 2^f on [-0.5, 0.5] by a degree-3 minimax polynomial (max relative error 1.0e-4: 40x below one bf16
+// ulp, which is all a softmax probability keeps), 2^n added into the exponent field.  Arguments are clamped to >= -125
+// (the result is then ~2^-125 instead of 0: invisible next to a row maximum of 2^0).  Used for a share of the softmax
+// exponentials so that MUFU (16 results / clk / SM) stops bounding the attention kernels (FlashAttention-4's idea).
+__device__ __forceinline__ f32x2 f2_exp2_poly(f32x2 x) {
+  float x0, x1;
+  f2_unpack(x, x0, x1);
+  x = f2_pack(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+  const f32x2 magic = f2_pack(12582912.0f, 12582912.0f);
+  const f32x2 t = f2_add(x, magic);            // low mantissa bits = round(x) (two's complement)
+  const f32x2 n = f2_sub(t, magic);
+  const f32x2 f = f2_sub(x, n);
+  f32x2 p = f2_fma(f, f2_pack(0.05500889f, 0.05500889f), f2_pack(0.24221097f, 0.24221097f));
+  p = f2_fma(p, f, f2_pack(0.69328293f, 0.69328293f));
+  p = f2_fma(p, f, f2_pack(1.0f, 1.0f));
+  uint32_t p0, p1, t0, t1;
+  f2_unpack_bits(p, p0, p1);
+  f2_unpack_bits(t, t0, t1);
+  return f2_pack_bits(p0 + (t0 << 23), p1 + (t1 << 23));
+}
+__device__ __forceinline__ f32x2 f2_exp2_mufu(f32x2 x) {
+  float x0, x1;
+  f2_unpack(x, x0, x1);
+  return f2_pack(fast_exp2(x0), fast_exp2(x1));
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -304,11 +304,46 @@ class PipelineEngine:
                 self.pipe_buffers[k].extend([None] * (n - len(self.pipe_buffers[k])))
 
     def _exec_schedule(self, sched, train):
+        if getattr(self.link, 'native', False):
+            return self._exec_schedule_native(sched, train)
         handlers = self._INSTRUCTION_MAP
         for tick in sched.steps():
             for cmd in tick:
                 handlers[type(cmd)](self, cmd, train)
         self.link.flush()
+
+    def _exec_schedule_native(self, sched, train):
+        """The C++ executor (csrc/stage_exec.cu) walks the instruction stream: it runs every Send / Recv itself (copy stream,
+        events, peer copies, device-side flags) and hands back only the instructions that need autograd or the optimizer,
+        plus — once per step and channel — the host handshake of a receiving channel."""
+        import ctypes
+        from .. import _lib
+        from .ipc_link import CH_ACT_IN, CH_GRAD_IN, OP_NEED_HANDSHAKE
+        from .schedule import _Instr, make_instruction
+        lib = _lib.lib()
+        plan = sched.raw()
+        ex = self.link.exec
+        _lib.check(lib.dpipe_exec_load_plan(ex, plan, len(plan), int(train), int(self.is_first_stage()), int(self.is_last_stage()),
+                                            max(1, len(self.pipe_buffers['inputs']))), 'dpipe_exec_load_plan')
+        handlers = self._INSTRUCTION_MAP
+        ins = _Instr()
+        while True:
+            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            rc = lib.dpipe_exec_next(ex, stream, ctypes.byref(ins))
+            if rc == 0:
+                break
+            _lib.check(0 if rc > 0 else rc, 'dpipe_exec_next')
+            if ins.op >= OP_NEED_HANDSHAKE:
+                cid = ins.op - OP_NEED_HANDSHAKE
+                if cid not in (CH_ACT_IN, CH_GRAD_IN):
+                    raise RuntimeError('stage executor: a Send was reached before its tuple was staged (internal error)')
+                like = None
+                if cid == CH_GRAD_IN:
+                    like = [t for t in self.pipe_buffers['outputs'][ins.buffer] if t.is_floating_point()]
+                self.link.handshake_recv(cid, like)
+                continue
+            cmd = make_instruction(ins.op, ins.buffer, ins.micro_batch)
+            handlers[type(cmd)](self, cmd, train)
 
     def _exec_load_micro_batch(self, cmd, train):
         b = cmd.buffer_id
@@ -359,13 +394,18 @@ class PipelineEngine:
             if torch.is_tensor(outputs):
                 outputs = (outputs,)
             self.pipe_buffers['outputs'][b] = tuple(outputs)
+            if getattr(self.link, 'native', False):
+                from .ipc_link import CH_ACT_OUT
+                self.link.stage(CH_ACT_OUT, b, self.pipe_buffers['outputs'][b])
+                if not train:
+                    self.pipe_buffers['outputs'][b] = None       # (the link keeps the tuple alive until it has been copied)
         if not train:
             self.pipe_buffers['inputs'][b] = None
             if self.is_last_stage():
                 # forward-only: the loss is already in total_loss, nothing will come back for this buffer
                 self.pipe_buffers['outputs'][b] = None
                 self.pipe_buffers['labels'][b] = None
-                if not self.is_first_stage():
+                if not self.is_first_stage() and not getattr(self.link, 'native', False):
                     self.link.release_activations(b, cmd.micro_batch_id)
 
     def _exec_backward_input(self, cmd, train):
@@ -398,10 +438,15 @@ class PipelineEngine:
             assert len(outs) == len(grads)
             pairs = [(t, g) for t, g in zip(outs, grads) if t.requires_grad]
             torch.autograd.backward(tensors=[p[0] for p in pairs], grad_tensors=[p[1] for p in pairs])
-            self.link.release_grads(b, cmd.micro_batch_id)
+            if not getattr(self.link, 'native', False):
+                self.link.release_grads(b, cmd.micro_batch_id)     # (the C++ executor hands the slot back itself)
         self.pipe_buffers['outputs'][b] = None
         self.pipe_buffers['grads'][b] = None
         self.pipe_buffers['labels'][b] = None
+        if getattr(self.link, 'native', False) and not self.is_first_stage():
+            from .ipc_link import CH_GRAD_OUT
+            self.link.stage(CH_GRAD_OUT, b, self._input_grads(b))   # for the SendGrad the executor runs next
+            self.pipe_buffers['inputs'][b] = None
 
     def _exec_send_activations(self, cmd, train):
         b = cmd.buffer_id
@@ -411,7 +456,11 @@ class PipelineEngine:
 
     def _exec_recv_activations(self, cmd, train):
         b = cmd.buffer_id
-        tensors = self.link.recv_activations(b, cmd.micro_batch_id)
+        if getattr(self.link, 'native', False):
+            from .ipc_link import CH_ACT_IN
+            tensors = self.link.wrap(CH_ACT_IN, cmd.micro_batch_id)   # the executor has already made the stream wait for it
+        else:
+            tensors = self.link.recv_activations(b, cmd.micro_batch_id)
         out = []
         for t in tensors:
             t = t.detach()
@@ -419,21 +468,29 @@ class PipelineEngine:
             out.append(t)
         self.pipe_buffers['inputs'][b] = tuple(out)
 
-    def _exec_send_grads(self, cmd, train):
-        b = cmd.buffer_id
-        inputs = self.pipe_buffers['inputs'][b]
+    def _input_grads(self, b):
+        """gradients of every floating-point tensor of the stage's input tuple (zeros where autograd produced none: the
+        previous stage expects one gradient per float output)"""
         grads = []
-        for t in inputs:
+        for t in self.pipe_buffers['inputs'][b]:
             if t.is_floating_point():
                 grads.append(t.grad if t.grad is not None else torch.zeros_like(t))
-        self.link.send_grads(tuple(grads), b, cmd.micro_batch_id)
+        return tuple(grads)
+
+    def _exec_send_grads(self, cmd, train):
+        b = cmd.buffer_id
+        self.link.send_grads(self._input_grads(b), b, cmd.micro_batch_id)
         self.pipe_buffers['inputs'][b] = None
 
     def _exec_recv_grads(self, cmd, train):
         b = cmd.buffer_id
         outputs = self.pipe_buffers['outputs'][b]
         like = [t for t in outputs if t.is_floating_point()]
-        self.pipe_buffers['grads'][b] = self.link.recv_grads(like, b, cmd.micro_batch_id)
+        if getattr(self.link, 'native', False):
+            from .ipc_link import CH_GRAD_IN
+            self.pipe_buffers['grads'][b] = self.link.wrap(CH_GRAD_IN, cmd.micro_batch_id)
+        else:
+            self.pipe_buffers['grads'][b] = self.link.recv_grads(like, b, cmd.micro_batch_id)
 
     def _exec_reduce_tied_grads(self, cmd, train):
         pass   # no tied layers in any reference model definition

@@ -1,5 +1,8 @@
 """IpcLink — the B200 stage-boundary transport: CUDA-IPC mailboxes + cudaMemcpyPeerAsync over NVLink + device-side
-sequence flags (C ABI: dpipe_ipc_* / dpipe_peer_copy / dpipe_flag_*; csrc/p2p_ipc.cu).  No NCCL on the boundary.
+sequence flags.  No NCCL on the boundary.  The data path lives in C++ (csrc/stage_exec.cu: dpipe_exec_*): the executor
+walks the stage's instruction stream and runs every Send / Recv itself on its own copy stream and events; this module is
+the HOST control plane only — mailbox allocation, the once-per-step shape / IPC-handle handshake over a gloo side group,
+and wrapping a received slot into tensors.
 
 Per direction (activations stage s -> s+1, gradients s+1 -> s) there is one channel:
   * the RECEIVER owns a mailbox  [ready flags | NSLOTS x slot]  in its own HBM and exports it once (re-exported only
@@ -72,8 +75,10 @@ def _layout(specs):
 
 
 class _Channel:
-    def __init__(self, link, peer_rank, peer_device, sending, tag):
+    def __init__(self, link, peer_rank, peer_device, sending, tag, cid):
         self.link = link
+        self.cid = cid             # DPIPE_CH_* of include/dpipe.h
+        self.remade = True         # the mailbox behind this channel is new: the executor restarts its slot counters
         self.peer_rank, self.peer_device = peer_rank, peer_device
         self.sending = sending
         self.tag = tag
@@ -82,7 +87,6 @@ class _Channel:
         self.slot_bytes = 0
         self.specs = None          # [(dtype, shape)] valid until the next reset
         self.offs = None
-        self.count = [0] * self.nslots   # writes (sender) / reads (receiver) per slot
         self.handshaken = False
         if sending:
             self.free_ptr, self.free_handle = _ipc_alloc(self.flag_bytes)    # flow-control flags live with the sender
@@ -107,7 +111,7 @@ class _Channel:
         if self.mail_ptr is not None:
             torch.cuda.synchronize()
             _lib_call('dpipe_ipc_free', ctypes.c_void_p(self.mail_ptr))
-            self.count = [0] * self.nslots
+            self.remade = True
         self.slot_bytes = _align(int(slot_bytes * 1.0))
         total = self.flag_bytes + self.nslots * self.slot_bytes
         self.mail_ptr, self.mail_handle = _ipc_alloc(total)
@@ -118,7 +122,7 @@ class _Channel:
         if self.remote_ptr is not None:
             torch.cuda.synchronize()
             _lib_call('dpipe_ipc_close', ctypes.c_void_p(self.remote_ptr))
-            self.count = [0] * self.nslots
+            self.remade = True
             # the receiver starts the new mailbox with zeroed flags: restart our own flow-control flags as well
             self.link._zero(self.free_ptr, self.flag_bytes)
         self.remote_ptr = _ipc_open(handle)
@@ -144,6 +148,8 @@ class _Channel:
         self.handshaken = True
         self.specs = [(t.dtype, tuple(t.shape)) for t in tensors]
         self.offs, _ = _layout(self.specs)
+        self.bind(self.remade)
+        self.remade = False
 
     def handshake_recv_described(self):
         meta = torch.zeros(_META_LEN, dtype=torch.int64)
@@ -166,6 +172,8 @@ class _Channel:
         if changed:
             self._send_cpu(torch.frombuffer(bytearray(self.mail_handle), dtype=torch.uint8), 3)
         self.handshaken = True
+        self.bind(self.remade)
+        self.remade = False
 
     # ---- gradients: the receiver already knows the shapes (its own outputs) ----
     def handshake_recv_known(self, like):
@@ -181,6 +189,8 @@ class _Channel:
             self._recv_cpu(h, 2)
             self.remote_free = _ipc_open(bytes(h.numpy().tobytes()))
         self.handshaken = True
+        self.bind(self.remade)
+        self.remade = False
 
     def handshake_send_known(self, tensors):
         info = torch.zeros(4, dtype=torch.int64)
@@ -194,51 +204,46 @@ class _Channel:
         self.handshaken = True
         self.specs = [(t.dtype, tuple(t.shape)) for t in tensors]
         self.offs, _ = _layout(self.specs)
+        self.bind(self.remade)
+        self.remade = False
 
-    # ---- data path ----
-    def push(self, tensors, mb):
-        link = self.link
-        k = mb % self.nslots
-        w = self.count[k] + 1
-        s = link.copy_stream
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
-        s.wait_event(ev)
-        sp = ctypes.c_void_p(s.cuda_stream)
-        _lib_call('dpipe_flag_wait_geq', ctypes.c_void_p(self.free_ptr + 8 * k), w - 1, _WAIT_TIMEOUT_S, sp)
-        base = self.remote_ptr + self.flag_bytes + k * self.slot_bytes
-        for t, off in zip(tensors, self.offs):
-            nbytes = t.numel() * t.element_size()
-            if nbytes:
-                _lib_call('dpipe_peer_copy', ctypes.c_void_p(base + off), self.peer_device, ctypes.c_void_p(t.data_ptr()),
-                          link.device.index, nbytes, sp)
-                t.record_stream(s)
-        _lib_call('dpipe_flag_write', ctypes.c_void_p(self.remote_ptr + 8 * k), w, sp)
-        self.count[k] = w
-
-    def pull(self, mb):
-        k = mb % self.nslots
-        w = self.count[k] + 1
-        sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib_call('dpipe_flag_wait_geq', ctypes.c_void_p(self.mail_ptr + 8 * k), w, _WAIT_TIMEOUT_S, sp)
-        self.count[k] = w
-        base = self.flag_bytes + k * self.slot_bytes
-        out = []
-        for (dt, shape), off in zip(self.specs, self.offs):
-            n = 1
+    # ---- after a handshake: hand the channel to the C++ executor ----
+    def bind(self, reset_counts):
+        ex = self.link.exec
+        if self.sending:
+            _lib_call('dpipe_exec_bind', ex, self.cid, ctypes.c_void_p(self.free_ptr), ctypes.c_void_p(self.remote_ptr),
+                      self.peer_device, self.flag_bytes, self.slot_bytes, int(reset_counts))
+        else:
+            _lib_call('dpipe_exec_bind', ex, self.cid, ctypes.c_void_p(self.mail_ptr), ctypes.c_void_p(self.remote_free),
+                      self.peer_device, self.flag_bytes, self.slot_bytes, int(reset_counts))
+        n = len(self.specs)
+        sizes = []
+        for dt, shape in self.specs:
+            k = 1
             for x in shape:
-                n *= x
-            nbytes = n * torch.empty((), dtype=dt).element_size()
-            out.append(self.mail_u8[base + off: base + off + nbytes].view(dt).view(shape))
+                k *= x
+            sizes.append(k * torch.empty((), dtype=dt).element_size())
+        self.nbytes = sizes
+        _lib_call('dpipe_exec_set_layout', ex, self.cid, n, (ctypes.c_int64 * n)(*self.offs), (ctypes.c_int64 * n)(*sizes))
+
+    def wrap(self, mb):
+        """the tensors of the tuple received for micro-batch mb: views of the mailbox slot (no second copy)"""
+        base = ctypes.c_void_p()
+        _lib_call('dpipe_exec_recv_base', self.link.exec, self.cid, mb, ctypes.byref(base))
+        off0 = base.value - self.mail_ptr
+        out = []
+        for (dt, shape), off, nbytes in zip(self.specs, self.offs, self.nbytes):
+            out.append(self.mail_u8[off0 + off: off0 + off + nbytes].view(dt).view(shape))
         return out
 
-    def release(self, mb):
-        k = mb % self.nslots
-        sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib_call('dpipe_flag_write', ctypes.c_void_p(self.remote_free + 8 * k), self.count[k], sp)
+
+CH_ACT_OUT, CH_ACT_IN, CH_GRAD_OUT, CH_GRAD_IN = 0, 1, 2, 3        # include/dpipe.h DPIPE_CH_*
+OP_NEED_HANDSHAKE = 100
 
 
 class IpcLink:
+    native = True      # the engine runs its schedule through dpipe_exec_next (pipe/engine.py:_exec_schedule_native)
+
     def __init__(self, engine, rank_devices=None):
         """rank_devices[r] = CUDA ordinal of global rank r (engine._make_link gathers them); None = ordinal follows the rank"""
         self.engine = engine
@@ -251,7 +256,10 @@ class IpcLink:
         self.nslots = max(2, engine.num_stages)
         if engine.pipeline_schedule == 'zb':
             self.nslots = max(2 * self.nslots, int(engine.zb_max_inflight or 2 * engine.num_stages))
-        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.exec = ctypes.c_void_p()
+        _lib_call('dpipe_exec_create', self.device.index, self.nslots, _WAIT_TIMEOUT_S, ctypes.byref(self.exec))
+        # the executor's copy stream, known to torch's allocator (record_stream on the tensors a pending copy still reads)
+        self.copy_stream = torch.cuda.ExternalStream(_lib.lib().dpipe_exec_copy_stream(self.exec), device=self.device)
         # host control plane: one gloo group per pipeline (every rank creates all of them, in the same order)
         self.ctrl_group = None
         for d in range(grid.data_parallel_size):
@@ -262,73 +270,72 @@ class IpcLink:
         # peers: same node, all GPUs visible in every process under the same ordinals (two stages may share one device:
         # the peer copy degenerates to a device-local copy — tests/test_stage_link_one_gpu.py)
         local_rank = self.device.index
+
         def peer(stage):
             r = grid.stage_to_global(stage)
             return r, (rank_devices[r] if rank_devices is not None else local_rank + (r - engine.global_rank))
         s = engine.stage_id
-        self.act_out = _Channel(self, *peer(s + 1), sending=True, tag=100) if s + 1 < engine.num_stages else None
-        self.act_in = _Channel(self, *peer(s - 1), sending=False, tag=100) if s > 0 else None
-        self.grad_out = _Channel(self, *peer(s - 1), sending=True, tag=200) if s > 0 else None
-        self.grad_in = _Channel(self, *peer(s + 1), sending=False, tag=200) if s + 1 < engine.num_stages else None
+        last = engine.num_stages - 1
+        self.channels = {
+            CH_ACT_OUT: _Channel(self, *peer(s + 1), sending=True, tag=100, cid=CH_ACT_OUT) if s < last else None,
+            CH_ACT_IN: _Channel(self, *peer(s - 1), sending=False, tag=100, cid=CH_ACT_IN) if s > 0 else None,
+            CH_GRAD_OUT: _Channel(self, *peer(s - 1), sending=True, tag=200, cid=CH_GRAD_OUT) if s > 0 else None,
+            CH_GRAD_IN: _Channel(self, *peer(s + 1), sending=False, tag=200, cid=CH_GRAD_IN) if s < last else None,
+        }
         self._fresh = {}
+        self._keep = {}            # (channel, pipe buffer) -> the tensors a pending send still reads
         self.reset()
+
+    def close(self):
+        """explicit teardown (after a device synchronisation).  Not done from __del__: at interpreter exit torch's caching
+        allocator may still hold events recorded on the executor's copy stream, and destroying the stream under it turns a
+        clean exit into a CUDA error."""
+        if self.exec:
+            torch.cuda.synchronize()
+            _lib.lib().dpipe_exec_destroy(self.exec)
+            self.exec = ctypes.c_void_p()
 
     def _zero(self, ptr, nbytes):
         torch.as_tensor(_DevMem(ptr, nbytes), device=self.device).zero_()
         torch.cuda.synchronize()
 
     def reset(self):
-        self._fresh = {'act_out': True, 'act_in': True, 'grad_out': True, 'grad_in': True}
+        """engine.reset_activation_shape() (train.py:916): the next step re-announces its boundary tuples"""
+        self._fresh = {c: True for c in self.channels}
+        _lib_call('dpipe_exec_forget_layouts', self.exec)
 
-    def send_activations(self, outputs, buf, mb, keep=True):
-        ts = [t.contiguous() for t in outputs]
-        if self._fresh['act_out']:
-            self.act_out.handshake_send_described(ts)
-            self._fresh['act_out'] = False
-        elif self.act_out.specs != [(t.dtype, tuple(t.shape)) for t in ts]:
+    # ---- what the engine calls around the executor ----
+    def stage(self, cid, buf, tensors):
+        """the tuple a coming SendActivation / SendGrad of pipe buffer `buf` will copy; the first one of a step announces
+        shapes (and, when a mailbox is new, IPC handles) to the neighbour over the gloo side group"""
+        ch = self.channels[cid]
+        ts = [t.contiguous() for t in tensors]
+        if self._fresh[cid]:
+            (ch.handshake_send_described if cid == CH_ACT_OUT else ch.handshake_send_known)(ts)
+            self._fresh[cid] = False
+        elif ch.specs != [(t.dtype, tuple(t.shape)) for t in ts]:
             # the slot layout on both sides comes from the handshake: a different tuple would be copied to wrong offsets
             raise RuntimeError('the boundary tuple changed shape or dtype since it was announced to the next stage: call '
                                'engine.reset_activation_shape() before a step whose micro-batches have new shapes '
                                '(train.py:916, train.py:181)')
-        self.act_out.push(ts, mb)
-        if not keep and self.act_in is not None:
-            # forward-only schedule: outputs may alias pass-through tensors that live in our input slot, so the slot is
-            # released only after the copy engine has read them
-            ev = torch.cuda.Event()
-            ev.record(self.copy_stream)
-            torch.cuda.current_stream().wait_event(ev)
-            self.act_in.release(mb)
+        n = len(ts)
+        _lib_call('dpipe_exec_stage_send', self.exec, cid, buf, n, (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts]))
+        for t in ts:
+            if t.numel():
+                t.record_stream(self.copy_stream)
+        self._keep[(cid, buf)] = ts
 
-    def recv_activations(self, buf, mb):
-        if self._fresh['act_in']:
-            self.act_in.handshake_recv_described()
-            self._fresh['act_in'] = False
-        return tuple(self.act_in.pull(mb))
+    def handshake_recv(self, cid, like=None):
+        """DPIPE_OP_NEED_HANDSHAKE for a receiving channel (first Recv of a step)"""
+        ch = self.channels[cid]
+        if cid == CH_ACT_IN:
+            ch.handshake_recv_described()
+        else:
+            ch.handshake_recv_known(like)
+        self._fresh[cid] = False
 
-    def send_grads(self, grads, buf, mb):
-        ts = [g.contiguous() for g in grads]
-        if self._fresh['grad_out']:
-            self.grad_out.handshake_send_known(ts)
-            self._fresh['grad_out'] = False
-        self.grad_out.push(ts, mb)
-        # the activation slot of this micro-batch has been fully consumed (its backward is enqueued before us)
-        if self.act_in is not None:
-            self.act_in.release(mb)
-
-    def recv_grads(self, like, buf, mb):
-        if self._fresh['grad_in']:
-            self.grad_in.handshake_recv_known(like)
-            self._fresh['grad_in'] = False
-        return self.grad_in.pull(mb)
-
-    def release_grads(self, buf, mb):
-        if self.grad_in is not None:
-            self.grad_in.release(mb)
-
-    def release_activations(self, buf, mb):
-        """forward-only schedules: the input slot is free as soon as the forward has been enqueued"""
-        if self.act_in is not None:
-            self.act_in.release(mb)
+    def wrap(self, cid, mb):
+        return self.channels[cid].wrap(mb)
 
     def flush(self):
         pass

@@ -85,7 +85,8 @@ _OP_CLASSES = {1: LoadMicroBatch, 2: SendActivation, 3: RecvActivation, 4: SendG
                7: BackwardPass, 8: ReduceTiedGrads, 9: ReduceGrads, 10: OptimizerStep, 11: BackwardInput, 12: BackwardWeight}
 
 
-def _plan(fn_name, micro_batches, stages, stage_id, extra=()):
+def _raw_plan(fn_name, micro_batches, stages, stage_id, extra=()):
+    """the planner's instruction array as it comes out of the C ABI (ctypes array of dpipe_instr)"""
     lib = _lib.lib()
     fn = getattr(lib, fn_name)
     n = fn(micro_batches, stages, stage_id, *extra, None, 0)
@@ -93,6 +94,18 @@ def _plan(fn_name, micro_batches, stages, stage_id, extra=()):
     buf = (_Instr * n)()
     n2 = fn(micro_batches, stages, stage_id, *extra, buf, n)
     _lib.check(0 if n2 == n else -1, fn_name)
+    return buf
+
+
+def make_instruction(op, buffer, micro_batch):
+    """the instruction object for one dpipe_instr (names as deepspeed.runtime.pipe.schedule, utils/patches.py:14-17)"""
+    if 8 <= op <= 10:
+        return _OP_CLASSES[op]()
+    return _OP_CLASSES[op](buffer, micro_batch_id=micro_batch)
+
+
+def _plan(fn_name, micro_batches, stages, stage_id, extra=()):
+    buf = _raw_plan(fn_name, micro_batches, stages, stage_id, extra)
     ticks, cur = [], []
     for ins in buf:
         if ins.op == 0:
@@ -131,6 +144,9 @@ class TrainSchedule(PipeSchedule):
     def steps(self):
         return _plan('dpipe_sched_train', self.micro_batches, self.stages, self.stage_id)
 
+    def raw(self):
+        return _raw_plan('dpipe_sched_train', self.micro_batches, self.stages, self.stage_id)
+
     def num_pipe_buffers(self):
         n = _lib.lib().dpipe_sched_num_pipe_buffers(self.micro_batches, self.stages, self.stage_id)
         _lib.check(0 if n > 0 else n, 'dpipe_sched_num_pipe_buffers')
@@ -140,6 +156,9 @@ class TrainSchedule(PipeSchedule):
 class InferenceSchedule(PipeSchedule):
     def steps(self):
         return _plan('dpipe_sched_infer', self.micro_batches, self.stages, self.stage_id)
+
+    def raw(self):
+        return _raw_plan('dpipe_sched_infer', self.micro_batches, self.stages, self.stage_id)
 
     def num_pipe_buffers(self):
         return 2
@@ -171,6 +190,10 @@ class ZeroBubbleSchedule(PipeSchedule):
     def steps(self):
         return _plan('dpipe_sched_zb_ex', self.micro_batches, self.stages, self.stage_id,
                      (*self.costs, self.max_inflight, self._weights_arg()))
+
+    def raw(self):
+        return _raw_plan('dpipe_sched_zb_ex', self.micro_batches, self.stages, self.stage_id,
+                         (*self.costs, self.max_inflight, self._weights_arg()))
 
     def num_pipe_buffers(self):
         return self.micro_batches     # buffers are indexed by micro-batch id

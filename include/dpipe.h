@@ -333,6 +333,37 @@ int dpipe_flag_write(void* flag, uint64_t value, void* stream);
 /* blocks `stream` (not the host) until *flag >= value; traps after timeout_s seconds (0 = never) */
 int dpipe_flag_wait_geq(const void* flag, uint64_t value, double timeout_s, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Pipeline-schedule executor: walks one stage's instruction stream; C++ owns the order, the copy stream, the events */
+/* and the stage-boundary copies, the host runs only the instructions that need autograd.                           */
+/* replaces: deepspeed PipelineEngine._exec_schedule / _exec_send_* / _exec_recv_* over the instruction stream of   */
+/*           utils/patches.py:113-160, called from train.py:918 (train_batch) and train.py:181 (eval_batch).        */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct dpipe_exec dpipe_exec;
+enum { DPIPE_CH_ACT_OUT = 0, DPIPE_CH_ACT_IN = 1, DPIPE_CH_GRAD_OUT = 2, DPIPE_CH_GRAD_IN = 3 };
+#define DPIPE_OP_NEED_HANDSHAKE 100 /* dpipe_exec_next pseudo-instruction: op = 100 + DPIPE_CH_* of the channel to handshake */
+/* copy stream + event pool on the current device; nslots mailbox slots per channel; timeout of the device-side flag waits */
+int dpipe_exec_create(int device, int nslots, double timeout_s, dpipe_exec** out);
+int dpipe_exec_destroy(dpipe_exec* x);
+void* dpipe_exec_copy_stream(dpipe_exec* x); /* cudaStream_t the boundary copies run on */
+/* after the host handshake of a channel: sender: flags_local = own `free` flags, remote = the peer's mailbox (mapped);
+ * receiver: flags_local = own mailbox, remote = the peer's `free` flags (mapped).  reset_counts when a mailbox was re-made. */
+int dpipe_exec_bind(dpipe_exec* x, int channel, void* flags_local, void* remote, int peer_device, int64_t flag_bytes,
+                    int64_t slot_bytes, int reset_counts);
+/* byte offset and size of every tensor of the boundary tuple inside a slot */
+int dpipe_exec_set_layout(dpipe_exec* x, int channel, int n, const int64_t* offsets, const int64_t* nbytes);
+int dpipe_exec_forget_layouts(dpipe_exec* x); /* reset_activation_shape(): train.py:916 */
+/* the instruction array of dpipe_sched_train / _infer / _zb_ex for this stage */
+int dpipe_exec_load_plan(dpipe_exec* x, const dpipe_instr* instrs, int n, int train, int is_first_stage, int is_last_stage,
+                         int num_buffers);
+/* device pointers of the tuple a coming SendActivation / SendGrad of pipe buffer `buffer` copies (same order as the layout) */
+int dpipe_exec_stage_send(dpipe_exec* x, int channel, int buffer, int n, const void* const* ptrs);
+/* slot that holds (or will hold) the tuple received for micro_batch on DPIPE_CH_ACT_IN / DPIPE_CH_GRAD_IN */
+int dpipe_exec_recv_base(dpipe_exec* x, int channel, int micro_batch, void** base);
+/* runs Send* / Recv* instructions itself; returns 1 with *out = the next instruction the host must execute (or a
+ * DPIPE_OP_NEED_HANDSHAKE pseudo-instruction), 0 when the plan is finished, < 0 on error */
+int dpipe_exec_next(dpipe_exec* x, void* compute_stream, dpipe_instr* out);
+
 #ifdef __cplusplus
 }
 #endif

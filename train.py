@@ -299,6 +299,35 @@ def evaluate(model_engine, eval_dataloaders, step, egas, log):
     np.random.set_state(np_state)
 
 
+class DeferredScalars:
+    """Scalars that live on the device (loss, gradient norm) on their way to the training log without a host sync in the step
+    that produced them: push() starts an asynchronous copy into pinned memory, flush() writes out what has arrived."""
+
+    def __init__(self, log):
+        self.log = log
+        self.pending = []
+
+    def push(self, tag, value, x):
+        import torch
+        if torch.is_tensor(value) and value.is_cuda:
+            host = torch.empty((), dtype=torch.float32, pin_memory=True)
+            host.copy_(value.detach().float().reshape(()), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self.pending.append((tag, host, x, ev))
+        else:
+            self.pending.append((tag, float(value), x, None))
+
+    def flush(self, keep=0):
+        """write everything but the newest `keep` entries (waits for their copies: they were enqueued a step ago)"""
+        n = len(self.pending) - keep
+        for tag, host, x, ev in self.pending[:max(0, n)]:
+            if ev is not None:
+                ev.synchronize()
+            self.log(tag, float(host), x)
+        self.pending = self.pending[max(0, n):]
+
+
 def main(argv=None):
     args = build_parser().parse_args(argv)
     for flag in ('cache_only', 'regenerate_cache', 'dump_dataset', 'test_sample'):
@@ -458,29 +487,38 @@ def main(argv=None):
         evaluate(model_engine, eval_dataloaders, 0, config['eval_gradient_accumulation_steps'], log)
 
     epoch = train_dataloader.epoch
-    epoch_loss, num_steps = 0.0, 0
+    epoch_loss, num_steps = None, 0
     checkpointed = saved = False
     final_model_name = None
+    # the reference reads the loss back with `.item()` after every step (train.py:918), a host<->device sync that
+    # keeps the next step's first kernels from being enqueued until the last optimizer kernel has finished.  Here the scalars
+    # of step s travel to pinned host memory asynchronously and are written to the log once step s+1 has been enqueued — the
+    # same numbers against the same x axis, one step later; everything pending is flushed before an evaluation, at the end of
+    # an epoch and on exit.  The epoch mean accumulates on the device.
+    scalars = DeferredScalars(log)
     while True:                                                          # train.py:915-965
         model_engine.reset_activation_shape()
         iterator = data_feed.get_data_iterator_for_step(train_dataloader, model_engine)
-        loss = model_engine.train_batch(iterator).item()
-        epoch_loss += loss
+        loss = model_engine.train_batch(iterator)
+        epoch_loss = loss.detach().float().clone() if epoch_loss is None else epoch_loss + loss.detach().float()
         num_steps += 1
         train_dataloader.sync_epoch()
         new_epoch, checkpointed, saved = saver.process_epoch(epoch, step, examples)
         finished_epoch = new_epoch != epoch
         x_axis = examples if config['x_axis_examples'] else step
+        scalars.flush(keep=0)                                            # step s-1: its copies finished long ago
         if step % config['logging_steps'] == 0:
-            log('train/loss', loss, x_axis)
+            scalars.push('train/loss', loss, x_axis)
             if model_engine._grad_norm is not None:
-                log('train/grad_norm', float(model_engine._grad_norm), x_axis)
+                scalars.push('train/grad_norm', model_engine._grad_norm, x_axis)
         if (config['eval_every_n_steps'] and step % config['eval_every_n_steps'] == 0) or \
                 (finished_epoch and config['eval_every_n_epochs'] and epoch % config['eval_every_n_epochs'] == 0):
+            scalars.flush(keep=0)
             evaluate(model_engine, eval_dataloaders, x_axis, config['eval_gradient_accumulation_steps'], log)
         if finished_epoch:
-            log('train/epoch_loss', epoch_loss / num_steps, epoch)
-            epoch_loss, num_steps = 0.0, 0
+            scalars.flush(keep=0)
+            log('train/epoch_loss', float(epoch_loss) / num_steps, epoch)
+            epoch_loss, num_steps = None, 0
             if new_epoch is None:
                 final_model_name = f'epoch{epoch}'
                 break
@@ -491,6 +529,7 @@ def main(argv=None):
             break
         step += 1
         examples += global_batch_size
+    scalars.flush(keep=0)
     # final training state and model, unless they were just written
     if not checkpointed:
         saver.save_checkpoint(step, examples)
