@@ -599,6 +599,26 @@ def main():
         prof, ops.PROFILE = ops.PROFILE, None
     clk = clocks.stop() if rank == 0 else None
 
+    # data parallel: what the same gradient all-reduce costs when nothing else runs (the serial cost the overlap is hiding)
+    standalone_reduce_ms = None
+    if dp > 1:
+        nbytes = int(2 * n_params / stages)
+        chunk = torch.empty(min(nbytes // 2, 256 << 20), dtype=torch.bfloat16, device=device).zero_()
+        group = engine.grid.get_data_parallel_group()
+        reps = max(1, nbytes // (2 * chunk.numel()))
+        tdist.all_reduce(chunk, group=group)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            tdist.all_reduce(chunk, op=tdist.ReduceOp.AVG, group=group)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=device)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        standalone_reduce_ms = float(t.item())
+        del chunk
+
     samples_per_step = mbs * M * dp
     value = samples_per_step * a.steps / (ms_dev / 1000.0)
     e2e_value = samples_per_step * a.steps / (ms_e2e / 1000.0)
@@ -715,6 +735,8 @@ def main():
         }
         if dp > 1:
             out['dp_allreduce'] = {'exposed_ms_per_step_max_rank': round(float(red_t.item()), 3),
+                                   'standalone_ms_same_bytes': round(standalone_reduce_ms, 3) if standalone_reduce_ms else None,
+                                   'standalone_busbw_gbs': round(2 * (dp - 1) / dp * int(2 * n_params / stages) / (standalone_reduce_ms / 1e3) / 1e9, 1) if standalone_reduce_ms else None,
                                    'overlapped_with_backward': bool(engine.dp_overlap and schedule_name != 'zb'),
                                    'layers_started_in_backward_rank0': engine.dp_early_layers,
                                    'bytes_per_rank': int(2 * n_params / stages)}

@@ -41,6 +41,10 @@ struct AttnBwdParams {
   __nv_bfloat16* dv;   // [B,H,Lk,128]
   int batch, heads, seq_q, seq_k;
   float scale_log2, scale;
+  const __nv_bfloat16* k;     // [B,H,Lk,128]  (v3 dK/dV kernel: K rows go straight from global memory into TMEM)
+  const __nv_bfloat16* q;     // [B,H,Lq,128]  (v4 dQ kernel: likewise)
+  const __nv_bfloat16* d_o;   // [B*Lq, lddo] token-major
+  int64_t lddo;
 };
 
 // K-major operand tile [128 rows][128 d] as two 64-wide halves: byte offset of k-step `k` (16 d per step)
@@ -1146,6 +1150,476 @@ attn_bwd_dq3_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
   if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// v4 dQ: Q and dO live in TENSOR MEMORY as the A operands of the score MMAs (TS form), not in shared memory.
+//   TMEM: S[2] 2x64 | dP[2] 2x64 | dQ 128 | Q 64 | dO 64   = 512 columns (a [128 x 128] bf16 tile is 64 32-bit columns)
+// The r02 capture of the v3 kernel showed what bounds these kernels: not MUFU, not the FMA pipe, but the shared-memory
+// data pipe feeding the tensor core (l1tex__data_pipe_tc_wavefronts_mem_shared at 60 % of peak with the MMA queue full and the
+// tensor pipe 54 % active).  An SS-form MMA of N = 64 reads 4 KB of A and 2 KB of B from shared memory for 32 cycles of
+// math; the A operand of both score MMAs (the Q and dO tile of the CTA) never changes, so reading it from TMEM removes
+// two thirds of the operand traffic: 112 KB -> 48 KB per 64-key sub-tile.  Each query row is written to TMEM once by the
+// thread that owns it (global -> registers -> tcgen05.st, no shared-memory staging), and the 64 KB of shared memory this
+// frees hold a third K / V tile (6 half-tile slots each).
+// ---------------------------------------------------------------------------------------------
+constexpr int DQ4_SLOTS = 6;
+constexpr int DQ4_SMEM_BYTES = 2 * (DQ4_SLOTS / 2) * BTILE + 1024 + 256;
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dq4_kernel(const __grid_constant__ CUtensorMap tma_k64, const __grid_constant__ CUtensorMap tma_v64,
+                    const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* k_smem = smem;                                  // 3 tiles of [128 kv][128 d] = 6 half-tile slots
+  uint8_t* v_smem = smem + (DQ4_SLOTS / 2) * BTILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * (DQ4_SLOTS / 2) * BTILE);
+  uint64_t* k_full = bars;                    // [6]
+  uint64_t* k_empty = bars + DQ4_SLOTS;       // [6]
+  uint64_t* v_full = bars + 2 * DQ4_SLOTS;    // [6]
+  uint64_t* v_empty = bars + 3 * DQ4_SLOTS;   // [6]
+  uint64_t* sd_full = bars + 4 * DQ4_SLOTS;   // [2]
+  uint64_t* ds_ready = sd_full + 2;           // [2] (4 warps)
+  uint64_t* qa_ready = ds_ready + 2;          // [1] (8 warps): Q and dO rows are in TMEM
+  uint64_t* acc_done = qa_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+  const uint32_t warp = warp_id_uniform();
+  const uint32_t lane = lane_id();
+  const int q0 = blockIdx.x * BT;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int bh = b * p.heads + head;
+  const int nsub = (p.seq_k + 63) / 64;   // 64-key sub-tiles
+
+  if (warp == 0 && elect_one()) { tma_prefetch_desc(&tma_k64); tma_prefetch_desc(&tma_v64); }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < DQ4_SLOTS; ++s) {
+      mbar_init(smem_u32(&k_full[s]), 1); mbar_init(smem_u32(&k_empty[s]), 1);
+      mbar_init(smem_u32(&v_full[s]), 1); mbar_init(smem_u32(&v_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&sd_full[s]), 1); mbar_init(smem_u32(&ds_ready[s]), 4); }
+    mbar_init(smem_u32(qa_ready), 8);
+    mbar_init(smem_u32(acc_done), 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<1>(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t T_S = tmem_base, T_DP = tmem_base + 128, T_DQ = tmem_base + 256, T_QA = tmem_base + 384, T_DOA = tmem_base + 448;
+  auto slot_off = [](int s) { return (uint32_t)((s >> 1) * BTILE + (s & 1) * 8192); };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int slot = 0;
+      uint32_t ph = 1;
+      for (int t = 0; t < nsub; ++t) {
+        mbar_wait(smem_u32(&k_empty[slot]), ph);
+        const uint32_t kb = smem_u32(&k_full[slot]);
+        mbar_expect_tx(kb, BTILE / 2);
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(&tma_k64, kb, smem_u32(k_smem + slot_off(slot) + h * BHALF), h * 64, t * 64, bh, kEvictLast);
+        mbar_wait(smem_u32(&v_empty[slot]), ph);
+        const uint32_t vb = smem_u32(&v_full[slot]);
+        mbar_expect_tx(vb, BTILE / 2);
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(&tma_v64, vb, smem_u32(v_smem + slot_off(slot) + h * BHALF), h * 64, t * 64, bh, kEvictLast);
+        if (++slot == DQ4_SLOTS) { slot = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(BT, 64, false, false);   // [128 q] x [64 kv], A from TMEM
+      constexpr uint32_t idesc_g = make_idesc_bf16(BT, 128, false, true);   // [128 q] x [128 d], K = 64 keys
+      mbar_wait(smem_u32(qa_ready), 0);
+      tc_fence_after();
+      int is_slot = 0;            // slot / phase of the next issue_scores
+      uint32_t is_ph = 0;
+      auto issue_scores = [&](int t) {
+        mbar_wait(smem_u32(&k_full[is_slot]), is_ph);
+        mbar_wait(smem_u32(&v_full[is_slot]), is_ph);
+        tc_fence_after();
+        const uint32_t kb = smem_u32(k_smem + slot_off(is_slot));
+        const uint32_t vb = smem_u32(v_smem + slot_off(is_slot));
+        const uint32_t buf = t & 1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // S[q, 64 kv] = Q K^T
+          umma_ts(T_S + buf * 64, T_QA + k * 8, make_smem_desc(kb + kmajor_off(k), 16, 1024), idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dP[q, 64 kv] = dO V^T
+          umma_ts(T_DP + buf * 64, T_DOA + k * 8, make_smem_desc(vb + kmajor_off(k), 16, 1024), idesc_s, k != 0);
+        umma_commit<1>(smem_u32(&sd_full[buf]));
+        umma_commit<1>(smem_u32(&v_empty[is_slot]));      // this V half tile is consumed by its dP
+        if (++is_slot == DQ4_SLOTS) { is_slot = 0; is_ph ^= 1; }
+      };
+      issue_scores(0);
+      int slot = 0;
+      for (int t = 0; t < nsub; ++t) {
+        if (t + 1 < nsub) issue_scores(t + 1);
+        const uint32_t buf = t & 1, rph = (t >> 1) & 1;
+        const uint32_t kb = smem_u32(k_smem + slot_off(slot));
+        mbar_wait(smem_u32(&ds_ready[buf]), rph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // dQ[q, d] += dS[q, 64 kv] K[64 kv, d]
+          umma_ts(T_DQ, T_DP + buf * 64 + k * 8, make_smem_desc(kb + k * 2048, BHALF, 1024), idesc_g, (t | k) != 0);
+        umma_commit<1>(smem_u32(&k_empty[slot]));
+        if (++slot == DQ4_SLOTS) slot = 0;
+      }
+      umma_commit<1>(smem_u32(acc_done));
+    }
+  } else if (warp >= 4) {
+    const uint32_t quad = warp & 3;
+    const int wg = (warp - 4) >> 2;          // warpgroup wg owns TMEM score buffer wg = the key sub-tiles t with t % 2 == wg
+    const int half = wg;                     // (epilogue: which 64 output columns this warp stores)
+    const uint32_t lane_base = (quad * 32u) << 16;
+    const int q = q0 + quad * 32 + lane;
+    const bool ok = q < p.seq_q;
+    {   // this thread's row of Q (warpgroup 0) or dO (warpgroup 1): 256 contiguous bytes -> 64 TMEM columns of its lane
+      const __nv_bfloat16* row = wg == 0 ? p.q + ((int64_t)bh * p.seq_q + q) * 128
+                                         : p.d_o + ((int64_t)b * p.seq_q + q) * p.lddo + head * 128;
+      const uint32_t dst = (wg == 0 ? T_QA : T_DOA) + lane_base;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t r[32];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+          uint4 v4 = make_uint4(0u, 0u, 0u, 0u);
+          if (ok) v4 = __ldg(reinterpret_cast<const uint4*>(row) + cc * 8 + x);
+          r[x * 4 + 0] = v4.x; r[x * 4 + 1] = v4.y; r[x * 4 + 2] = v4.z; r[x * 4 + 3] = v4.w;
+        }
+        tmem_st_x32(dst + cc * 32, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(qa_ready));
+    }
+    const float lse = ok ? p.lse[(int64_t)bh * p.seq_q + q] : INFINITY;
+    const float dl = ok ? p.delta[(int64_t)bh * p.seq_q + q] : 0.f;
+    const float c = p.scale_log2;
+    const f32x2 c2 = f2_pack(c, c), nlse2 = f2_pack(-lse, -lse), dl2 = f2_pack(dl, dl);
+    const uint32_t buf = wg;
+    for (int t = wg, it = 0; t < nsub; t += 2, ++it) {
+      const uint32_t rph = it & 1;
+      const int valid = p.seq_k - t * 64;    // keys of this sub-tile that exist (>= 64 except in the last one)
+      const bool partial = valid < 64;
+      mbar_wait(smem_u32(&sd_full[buf]), rph);
+      tc_fence_after();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32], rd[32], pk[16];
+        tmem_ld_x32(T_S + lane_base + buf * 64 + hh * 32, r);
+        tmem_ld_x32(T_DP + lane_base + buf * 64 + hh * 32, rd);
+        tmem_ld_wait();
+        if (!partial) dq_softmax_chunk<false>(r, rd, pk, c2, nlse2, dl2, 0);
+        else dq_softmax_chunk<true>(r, rd, pk, c2, nlse2, dl2, valid - hh * 32);
+        tmem_st_x16(T_DP + lane_base + buf * 64 + hh * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ds_ready[buf]));
+    }
+    mbar_wait(smem_u32(acc_done), 0);
+    tc_fence_after();
+    __nv_bfloat16* dst = p.dq + ((int64_t)bh * p.seq_q + q) * 128 + half * 64;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      uint32_t rr[32];
+      tmem_ld_x32(T_DQ + lane_base + half * 64 + cc * 32, rr);
+      tmem_ld_wait();
+      if (ok) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + cc * 32);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          uint4 qv;
+          qv.x = pack_bf16(__uint_as_float(rr[x * 8 + 0]) * p.scale, __uint_as_float(rr[x * 8 + 1]) * p.scale);
+          qv.y = pack_bf16(__uint_as_float(rr[x * 8 + 2]) * p.scale, __uint_as_float(rr[x * 8 + 3]) * p.scale);
+          qv.z = pack_bf16(__uint_as_float(rr[x * 8 + 4]) * p.scale, __uint_as_float(rr[x * 8 + 5]) * p.scale);
+          qv.w = pack_bf16(__uint_as_float(rr[x * 8 + 6]) * p.scale, __uint_as_float(rr[x * 8 + 7]) * p.scale);
+          d4[x] = qv;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// v3 dK / dV: the K tile of the CTA is the A operand of St = K Q^T from TENSOR MEMORY (TS form) — same reasoning as the v4 dQ
+// kernel: the shared-memory data pipe (tensor-core operand reads 53 % + LSE / D broadcasts 32 % of its peak in the r02
+// capture of v2) bounds this kernel, and the stationary A operand is two thirds of the score MMAs' operand bytes.
+//   TMEM: St[2] 2x64 | dPt 64 (single buffer) | K 64 | dV 128 | dK 128 = 512 columns
+// There is no room for V as well, so dPt = V dO^T stays an SS MMA and gets ONE buffer: dPt(t+1) is issued right after the
+// dK MMA that consumes dSt(t) (in-order tensor pipe: no extra barrier), while St keeps two buffers so that the exponentials of
+// sub-tile t+1 run under the dV / dK MMAs of sub-tile t.  Warpgroup t & 1 owns sub-tile t.
+// ---------------------------------------------------------------------------------------------
+constexpr int DKV3_SMEM_BYTES = 5 * BTILE + AB_STATS_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dkv3_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_v,
+                     const __grid_constant__ CUtensorMap tma_do, const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* v_smem = smem;
+  uint8_t* q_smem = smem + BTILE;       // 2 stages of [128 q][128 d]
+  uint8_t* do_smem = smem + 3 * BTILE;  // 2 stages
+  float* stats = reinterpret_cast<float*>(smem + 5 * BTILE);   // ring [4][-LSE 128 | D 128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * BTILE + AB_STATS_BYTES);
+  uint64_t* v_full = bars;          // [1]
+  uint64_t* q_full = bars + 1;      // [2]
+  uint64_t* q_empty = bars + 3;     // [2]
+  uint64_t* do_full = bars + 5;     // [2]
+  uint64_t* do_empty = bars + 7;    // [2]
+  uint64_t* s_full = bars + 9;      // [2] MMA -> softmax: St of buffer b complete
+  uint64_t* dp_full = bars + 11;    // [1] MMA -> softmax: dPt complete
+  uint64_t* p_ready = bars + 12;    // [2] softmax -> MMA (4 warps)
+  uint64_t* ds_ready = bars + 14;   // [2] softmax -> MMA (4 warps)
+  uint64_t* ka_ready = bars + 16;   // [1] (8 warps): the K tile is in TMEM
+  uint64_t* acc_done = bars + 17;
+  uint64_t* stats_full = bars + 18;   // [4]
+  uint64_t* stats_empty = bars + 22;  // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+
+  const uint32_t warp = warp_id_uniform();
+  const uint32_t lane = lane_id();
+  const int kv0 = blockIdx.x * BT;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int bh = b * p.heads + head;
+  const int nq = (p.seq_q + BT - 1) / BT;
+  const int nsub = 2 * nq;
+
+  if (warp == 0 && elect_one()) { tma_prefetch_desc(&tma_q); tma_prefetch_desc(&tma_v); tma_prefetch_desc(&tma_do); }
+  if (warp == 1 && elect_one()) {
+    mbar_init(smem_u32(v_full), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&q_full[s]), 1); mbar_init(smem_u32(&q_empty[s]), 1);
+      mbar_init(smem_u32(&do_full[s]), 1); mbar_init(smem_u32(&do_empty[s]), 1);
+      mbar_init(smem_u32(&s_full[s]), 1);
+      mbar_init(smem_u32(&p_ready[s]), 4); mbar_init(smem_u32(&ds_ready[s]), 4);
+    }
+    mbar_init(smem_u32(dp_full), 1);
+    mbar_init(smem_u32(ka_ready), 8);
+    mbar_init(smem_u32(acc_done), 1);
+    for (int s = 0; s < 4; ++s) { mbar_init(smem_u32(&stats_full[s]), 2); mbar_init(smem_u32(&stats_empty[s]), 8); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<1>(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t T_ST = tmem_base, T_DPT = tmem_base + 128, T_KA = tmem_base + 192, T_DV = tmem_base + 256, T_DK = tmem_base + 384;
+
+  if (warp == 2 || warp == 3) {
+    // warp 2: -LSE, warp 3: D = rowsum(O * dO); rows beyond seq_q get -LSE = -inf (P = 0) and D = 0
+    const float* src = (warp == 2 ? p.lse : p.delta) + (int64_t)bh * p.seq_q;
+    const float fill = warp == 2 ? -INFINITY : 0.f;
+    const float sgn = warp == 2 ? -1.f : 1.f;
+    for (int j = 0; j < nq; ++j) {
+      const int stage = j & 3;
+      mbar_wait(smem_u32(&stats_empty[stage]), ((j >> 2) & 1) ^ 1);
+      float* dst = stats + stage * 256 + (warp == 2 ? 0 : 128);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int q = j * BT + r * 32 + (int)lane;
+        dst[r * 32 + lane] = q < p.seq_q ? sgn * __ldg(src + q) : fill;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&stats_full[stage]));
+    }
+  }
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t vb = smem_u32(v_full);
+      mbar_expect_tx(vb, BTILE);
+      for (int h = 0; h < 2; ++h) tma_load_3d(&tma_v, vb, smem_u32(v_smem + h * BHALF), h * 64, kv0, bh, kEvictFirst);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nq; ++j) {
+        const int q0 = j * BT;
+        mbar_wait(smem_u32(&q_empty[stage]), phase ^ 1);
+        const uint32_t qb = smem_u32(&q_full[stage]);
+        mbar_expect_tx(qb, BTILE);
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(&tma_q, qb, smem_u32(q_smem + stage * BTILE + h * BHALF), h * 64, q0, bh, kEvictLast);
+        mbar_wait(smem_u32(&do_empty[stage]), phase ^ 1);
+        const uint32_t db = smem_u32(&do_full[stage]);
+        mbar_expect_tx(db, BTILE);
+        for (int h = 0; h < 2; ++h)
+          tma_load_4d(&tma_do, db, smem_u32(do_smem + stage * BTILE + h * BHALF), h * 64, q0, head, b, kEvictLast);
+        if (++stage == 2) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(BT, 64, false, false);   // [128 kv] x [64 q]
+      constexpr uint32_t idesc_g = make_idesc_bf16(BT, 128, false, true);   // [128 kv] x [128 d], K = 64 queries
+      const uint32_t vb = smem_u32(v_smem);
+      mbar_wait(smem_u32(ka_ready), 0);
+      mbar_wait(smem_u32(v_full), 0);
+      tc_fence_after();
+      auto issue_s = [&](int t) {    // St[kv, 64 q] = K Q^T, A = K from TMEM
+        const int j = t >> 1, stage = j & 1;
+        if ((t & 1) == 0) { mbar_wait(smem_u32(&q_full[stage]), (j >> 1) & 1); tc_fence_after(); }
+        const uint32_t qb = smem_u32(q_smem + stage * BTILE) + (t & 1) * 8192;
+        const uint32_t buf = t & 1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ts(T_ST + buf * 64, T_KA + k * 8, make_smem_desc(qb + kmajor_off(k), 16, 1024), idesc_s, k != 0);
+        umma_commit<1>(smem_u32(&s_full[buf]));
+      };
+      auto issue_dp = [&](int t) {   // dPt[kv, 64 q] = V dO^T (SS)
+        const int j = t >> 1, stage = j & 1;
+        if ((t & 1) == 0) { mbar_wait(smem_u32(&do_full[stage]), (j >> 1) & 1); tc_fence_after(); }
+        const uint32_t dob = smem_u32(do_smem + stage * BTILE) + (t & 1) * 8192;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss<1>(T_DPT, make_smem_desc(vb + kmajor_off(k), 16, 1024), make_smem_desc(dob + kmajor_off(k), 16, 1024),
+                     idesc_s, k != 0);
+        umma_commit<1>(smem_u32(dp_full));
+      };
+      issue_s(0);
+      issue_dp(0);
+      for (int t = 0; t < nsub; ++t) {
+        if (t + 1 < nsub) issue_s(t + 1);
+        const int j = t >> 1, stage = j & 1;
+        const uint32_t buf = t & 1, rph = (t >> 1) & 1;
+        const uint32_t qb = smem_u32(q_smem + stage * BTILE) + (t & 1) * 8192;
+        const uint32_t dob = smem_u32(do_smem + stage * BTILE) + (t & 1) * 8192;
+        mbar_wait(smem_u32(&p_ready[buf]), rph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // dV[kv, d] += Pt[kv, 64 q] dO[64 q, d]
+          umma_ts(T_DV, T_ST + buf * 64 + k * 8, make_smem_desc(dob + k * 2048, BHALF, 1024), idesc_g, (t | k) != 0);
+        if (t & 1) umma_commit<1>(smem_u32(&do_empty[stage]));
+        mbar_wait(smem_u32(&ds_ready[buf]), rph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // dK[kv, d] += dSt[kv, 64 q] Q[64 q, d]
+          umma_ts(T_DK, T_DPT + k * 8, make_smem_desc(qb + k * 2048, BHALF, 1024), idesc_g, (t | k) != 0);
+        if (t & 1) umma_commit<1>(smem_u32(&q_empty[stage]));
+        if (t + 1 < nsub) issue_dp(t + 1);   // the single dPt buffer is free once the dK MMA above has read dSt (in-order pipe)
+      }
+      umma_commit<1>(smem_u32(acc_done));
+    }
+  } else if (warp >= 4) {
+    const uint32_t quad = warp & 3;
+    const int wg = (warp - 4) >> 2;
+    const uint32_t lane_base = (quad * 32u) << 16;
+    const float c = p.scale_log2;
+    const f32x2 c2 = f2_pack(c, c);
+    const int kv = kv0 + quad * 32 + lane;
+    const bool ok = kv < p.seq_k;
+    {   // this thread's K row, d half `wg`: 128 contiguous bytes -> 32 TMEM columns of its lane
+      const __nv_bfloat16* row = p.k + ((int64_t)bh * p.seq_k + kv) * 128 + wg * 64;
+      uint32_t r[32];
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        uint4 v4 = make_uint4(0u, 0u, 0u, 0u);
+        if (ok) v4 = __ldg(reinterpret_cast<const uint4*>(row) + x);
+        r[x * 4 + 0] = v4.x; r[x * 4 + 1] = v4.y; r[x * 4 + 2] = v4.z; r[x * 4 + 3] = v4.w;
+      }
+      tmem_st_x32(T_KA + lane_base + wg * 32, r);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(ka_ready));
+    }
+    const uint32_t buf = wg;
+    for (int t = wg, it = 0; t < nsub; t += 2, ++it) {
+      const uint32_t rph = it & 1;
+      const int j = t >> 1, stage = j & 3;
+      mbar_wait(smem_u32(&stats_full[stage]), (j >> 2) & 1);
+      const float* lse_s = stats + stage * 256 + (t & 1) * 64;
+      const float* dl_s = lse_s + 128;
+      mbar_wait(smem_u32(&s_full[buf]), rph);
+      tc_fence_after();
+      f32x2 pv[32];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32], pk[16];
+        tmem_ld_x32(T_ST + lane_base + buf * 64 + hh * 32, r);
+        tmem_ld_wait();
+        const f32x2* nl = reinterpret_cast<const f32x2*>(lse_s + hh * 32);
+#pragma unroll
+        for (int x = 0; x < 32; x += 2) {
+          const f32x2 e = f2_exp2_mufu(f2_fma(f2_pack_bits(r[x], r[x + 1]), c2, nl[x >> 1]));
+          pv[hh * 16 + (x >> 1)] = e;
+          float p0, p1;
+          f2_unpack(e, p0, p1);
+          pk[x >> 1] = pack_bf16(p0, p1);
+        }
+        tmem_st_x16(T_ST + lane_base + buf * 64 + hh * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&p_ready[buf]));
+      mbar_wait(smem_u32(dp_full), t & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32], pk[16];
+        tmem_ld_x32(T_DPT + lane_base + hh * 32, r);
+        tmem_ld_wait();
+        const f32x2* dl2 = reinterpret_cast<const f32x2*>(dl_s + hh * 32);
+#pragma unroll
+        for (int x = 0; x < 32; x += 2) {
+          const f32x2 d = f2_mul(pv[hh * 16 + (x >> 1)], f2_sub(f2_pack_bits(r[x], r[x + 1]), dl2[x >> 1]));
+          float d0, d1;
+          f2_unpack(d, d0, d1);
+          pk[x >> 1] = pack_bf16(d0, d1);
+        }
+        tmem_st_x16(T_DPT + lane_base + hh * 16, pk);   // packed dSt over columns this thread has already read
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&ds_ready[buf]));
+        mbar_arrive(smem_u32(&stats_empty[stage]));
+      }
+    }
+    mbar_wait(smem_u32(acc_done), 0);
+    tc_fence_after();
+    const int chalf = wg;
+    const int64_t o = ((int64_t)bh * p.seq_k + kv) * 128 + chalf * 64;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t tt = (which == 0 ? T_DV : T_DK) + lane_base + chalf * 64;
+      __nv_bfloat16* dst = (which == 0 ? p.dv : p.dk) + o;
+      const float mul = which == 0 ? 1.0f : p.scale;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t rr[32];
+        tmem_ld_x32(tt + cc * 32, rr);
+        tmem_ld_wait();
+        if (ok) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + cc * 32);
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            uint4 qv;
+            qv.x = pack_bf16(__uint_as_float(rr[x * 8 + 0]) * mul, __uint_as_float(rr[x * 8 + 1]) * mul);
+            qv.y = pack_bf16(__uint_as_float(rr[x * 8 + 2]) * mul, __uint_as_float(rr[x * 8 + 3]) * mul);
+            qv.z = pack_bf16(__uint_as_float(rr[x * 8 + 4]) * mul, __uint_as_float(rr[x * 8 + 5]) * mul);
+            qv.w = pack_bf16(__uint_as_float(rr[x * 8 + 6]) * mul, __uint_as_float(rr[x * 8 + 7]) * mul);
+            d4[x] = qv;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
 }  // namespace dpipe
 
 extern "C" int dpipe_attn_bwd(const dpipe_attn_bwd_args* a, void* stream) {
@@ -1183,6 +1657,8 @@ extern "C" int dpipe_attn_bwd(const dpipe_attn_bwd_args* a, void* stream) {
     DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
     DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
     DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
+    DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ4_SMEM_BYTES));
+    DPIPE_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV3_SMEM_BYTES));
     configured = true;
   }
   AttnBwdParams p;
@@ -1192,11 +1668,32 @@ extern "C" int dpipe_attn_bwd(const dpipe_attn_bwd_args* a, void* stream) {
   p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv);
   p.batch = B; p.heads = H; p.seq_q = Lq; p.seq_k = Lk;
   p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
-  // DPIPE_ATTN_BWD selects older variants for A/B measurements: 1 = un-pipelined v1, 2 = v2 (round 1), default 3 =
-  // v2 dK/dV with the LSE / D loader warps + v3 dQ (three TMEM score buffers, half-tile K / V slots)
+  p.k = reinterpret_cast<const __nv_bfloat16*>(a->k);
+  p.q = reinterpret_cast<const __nv_bfloat16*>(a->q);
+  p.d_o = reinterpret_cast<const __nv_bfloat16*>(a->d_o);
+  p.lddo = a->lddo;
+  // DPIPE_ATTN_BWD selects older variants for A/B measurements: 1 = un-pipelined v1, 2 = v2 (round 1), 3 = v2 dK/dV with
+  // the LSE / D loader warps + v3 dQ (three TMEM score buffers, half-tile K / V slots), default 4 = the same dK/dV kernel +
+  // v4 dQ (Q and dO resident in TMEM as the A operands), 5 = v3 dK/dV (K resident in TMEM) + v4 dQ
   static int variant = -1;
-  if (variant < 0) { const char* e = getenv("DPIPE_ATTN_BWD"); variant = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3; }
-  if (variant == 3) {
+  if (variant < 0) { const char* e = getenv("DPIPE_ATTN_BWD"); variant = (e && e[0] >= '1' && e[0] <= '5') ? e[0] - '0' : 4; }
+  if (variant == 5) {
+    CUtensorMap tk64, tv64;
+    if ((rc = make_tmap_3d_bf16(&tk64, a->k, 128, Lk, bh, 128, (uint64_t)Lk * 128, 64, 64, 1))) return rc;
+    if ((rc = make_tmap_3d_bf16(&tv64, a->v, 128, Lk, bh, 128, (uint64_t)Lk * 128, 64, 64, 1))) return rc;
+    attn_bwd_dkv3_kernel<<<dim3((Lk + BT - 1) / BT, H, B), AB_THREADS, DKV3_SMEM_BYTES, s>>>(tq, tv, tdo, p);
+    DPIPE_CUDA_CHECK(cudaGetLastError());
+    attn_bwd_dq4_kernel<<<dim3((Lq + BT - 1) / BT, H, B), AB_THREADS, DQ4_SMEM_BYTES, s>>>(tk64, tv64, p);
+    DPIPE_CUDA_CHECK(cudaGetLastError());
+  } else if (variant == 4) {
+    CUtensorMap tk64, tv64;
+    if ((rc = make_tmap_3d_bf16(&tk64, a->k, 128, Lk, bh, 128, (uint64_t)Lk * 128, 64, 64, 1))) return rc;
+    if ((rc = make_tmap_3d_bf16(&tv64, a->v, 128, Lk, bh, 128, (uint64_t)Lk * 128, 64, 64, 1))) return rc;
+    attn_bwd_dkv2_kernel<true><<<dim3((Lk + BT - 1) / BT, H, B), AB_THREADS, AB_SMEM_BYTES, s>>>(tq, tk, tv, tdo, p);
+    DPIPE_CUDA_CHECK(cudaGetLastError());
+    attn_bwd_dq4_kernel<<<dim3((Lq + BT - 1) / BT, H, B), AB_THREADS, DQ4_SMEM_BYTES, s>>>(tk64, tv64, p);
+    DPIPE_CUDA_CHECK(cudaGetLastError());
+  } else if (variant == 3) {
     CUtensorMap tk64, tv64;
     if ((rc = make_tmap_3d_bf16(&tk64, a->k, 128, Lk, bh, 128, (uint64_t)Lk * 128, 64, 64, 1))) return rc;
     if ((rc = make_tmap_3d_bf16(&tv64, a->v, 128, Lk, bh, 128, (uint64_t)Lk * 128, 64, 64, 1))) return rc;

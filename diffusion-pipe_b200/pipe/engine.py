@@ -179,7 +179,7 @@ class PipelineEngine:
         self._dp_reduced_layers, self._dp_reduced_ptrs = set(), set()
         self.dp_reduce_events = None
         self.dp_early_layers = 0                      # layers whose all-reduce started under the backward pass (last step)
-        self.dp_overlap = bool(self.config.get('dp_overlap', True))
+        self.dp_overlap = bool(self.config.get('dp_overlap', os.environ.get('DPIPE_DP_OVERLAP', '1') != '0'))
         self._broadcast_model()
         self.link = self._make_link()
         self.total_loss = None
@@ -261,6 +261,14 @@ class PipelineEngine:
         if kind == 'ipc' and self.is_pipe_parallel:
             from .ipc_link import IpcLink
             return IpcLink(self, devices)
+        if self.pipeline_schedule == 'zb' and self.is_pipe_parallel and self.device.type == 'cuda':
+            # the split-backward order lets a stage run ahead of its neighbour, which needs one-sided sends.  NCCL
+            # point-to-point operations between two ranks run in issue order on both sides: "send activation k+1" on one
+            # stage and "send gradient k" on the other wait for each other's receive forever (seen on 2 B200s in round 2).
+            if self.global_rank == 0:
+                print("pipeline_schedule 'zb' needs the one-sided CUDA-IPC stage link; with torch.distributed p2p on the "
+                      "stage boundaries the reference's 1F1B order is used instead", flush=True)
+            self.pipeline_schedule = '1f1b'
         return DistLink(self)
 
     # ------------------------------------------------------------------ public API

@@ -75,6 +75,8 @@ def _worker(rank, world, port, kind, stages, schedule, outdir, gpu=False, link='
     from diffusion_pipe_b200 import ops
     from diffusion_pipe_b200.pipe import ManualPipelineModule, dist, initialize
     if gpu:
+        import faulthandler
+        faulthandler.dump_traceback_later(420, exit=True)     # a stuck worker must not outlive the test holding a GPU
         torch.cuda.set_device(rank)
         device = torch.device('cuda', rank)
         if world > 1:

@@ -43,6 +43,8 @@ def _worker(rank, world, port, link, outdir, schedule='1f1b'):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1',
                       MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
+    import faulthandler
+    faulthandler.dump_traceback_later(420, exit=True)     # a stuck worker must not outlive the test holding a GPU
     torch.cuda.set_device(rank)
     from diffusion_pipe_b200.flux import FluxPipeline
     from diffusion_pipe_b200.pipe import ManualPipelineModule, dist, initialize

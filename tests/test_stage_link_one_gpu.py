@@ -65,6 +65,8 @@ def _worker(rank, world, port, schedule, split, outdir):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK='0', MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port),
                       DPIPE_LINK_TIMEOUT_S='120')
     sys.path.insert(0, ROOT)
+    import faulthandler
+    faulthandler.dump_traceback_later(420, exit=True)     # a stuck worker must not outlive the test holding a GPU
     torch.cuda.set_device(0)
     dev = torch.device('cuda', 0)
     from diffusion_pipe_b200.pipe import ManualPipelineModule, dist, initialize

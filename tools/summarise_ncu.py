@@ -89,6 +89,61 @@ def full_captures():
             f.write('\n')
 
 
+def hbm_table():
+    """HBM-bound kernels of the elementwise capture: measured DRAM bytes per launch, achieved GB/s against the measured copy
+    peak (MEASURED_PEAKS.json hbm_gbs), and the algorithmic bytes of the shape (1 double + 1 single block, L = 4608 = 4096
+    image + 512 text tokens, D = 3072, 24 heads) where the kernel name and grid identify it."""
+    import json
+    fn = os.path.join(SRC, f'prof_elementwise_{R}.ncu-rep')
+    if not os.path.exists(fn):
+        return
+    try:
+        peak = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']
+    except Exception:
+        peak = 6650.0
+    p = subprocess.run(['ncu', '-i', fn, '--page', 'raw', '--csv'], capture_output=True, text=True)
+    rd = list(csv.reader(p.stdout.splitlines()))
+    if len(rd) < 3:
+        return
+    hdr, units = rd[0], rd[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+
+    def val(row, name):
+        try:
+            v = float(row[ix[name]].replace(',', ''))
+        except (KeyError, ValueError):
+            return None
+        u = units[ix[name]]
+        scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-9, 'us': 1e-6, 'usecond': 1e-6, 'ms': 1e-3,
+                 'msecond': 1e-3, 'nsecond': 1e-9, 'second': 1.0}.get(u, 1.0)
+        return v * scale
+    agg = collections.OrderedDict()
+    for row in rd[2:]:
+        name = re.sub(r'\(.*', '', re.sub(r'<.*', '', row[ix['Kernel Name']])).replace('void ', '').replace('dpipe::', '').strip()
+        grid = row[ix['launch__grid_size']] if 'launch__grid_size' in ix else '?'
+        t, rb, wb = val(row, 'gpu__time_duration.sum'), val(row, 'dram__bytes_read.sum'), val(row, 'dram__bytes_write.sum')
+        if not t or rb is None:
+            continue
+        d = agg.setdefault((name, grid), [0, 0.0, 0.0, 0.0, 0.0])
+        d[0] += 1
+        d[1] += t
+        d[2] += rb
+        d[3] += wb
+        pct = val(row, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')
+        d[4] += pct or 0.0
+    with open(os.path.join(OUT, f'{R}_hbm_kernels.md'), 'w') as f:
+        f.write(f'# {R}: the HBM-bound kernels under `ncu --set full --clock-control none` (1 double + 1 single Flux block at 1024^2)\n\n')
+        f.write(f'Achieved = (dram__bytes_read.sum + dram__bytes_write.sum) / gpu__time_duration.sum per launch, against the measured copy\n'
+                f'peak of this pool ({peak:.1f} GB/s, MEASURED_PEAKS.json).  Launches of one kernel with the same grid are averaged.  Under ncu\n'
+                f'every launch starts with a cold L2 and runs alone; inputs a neighbouring kernel left in the 126 MB L2 show up here as DRAM reads.\n\n')
+        f.write('| kernel | grid | launches | avg us | DRAM read MB | DRAM write MB | GB/s | of HBM peak | ncu dram % |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|\n')
+        for (name, grid), d in agg.items():
+            n, t, rb, wb, pct = d
+            gbs = (rb + wb) / t / 1e9
+            f.write(f'| `{name}` | {grid} | {n} | {t / n * 1e6:.1f} | {rb / n / 1e6:.1f} | {wb / n / 1e6:.1f} | {gbs:.0f} | {gbs / peak:.2f} | {pct / n:.0f} |\n')
+
+
 launch_list()
 full_captures()
+hbm_table()
 print(os.listdir(OUT))
