@@ -581,8 +581,11 @@ def main():
         reduce_ms[:] = [x.elapsed_time(y) for x, y in waits]
         return ms.item(), float(last)
 
-    for _ in range(a.warmup):
-        step(dev_batches, False)
+    first_loss = None
+    for i in range(a.warmup):
+        l0 = step(dev_batches, False)
+        if i == 0:
+            first_loss = l0            # loss of the untouched initial model: must be the same number for every --gpus N
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -729,6 +732,7 @@ def main():
                     'ms_per_step': ms_e2e / a.steps, 'loss': loss_e2e},
             'gpu_launches': int(lt.item()),
             'loss': loss_dev,
+            'first_step_loss': float(first_loss) if first_loss is not None else None,
             'peak_mem_gib_max_rank': round(float(mem_t.item()), 1),
             'stage_kernel_busy_frac': stage_busy,
             'clocks': clk,

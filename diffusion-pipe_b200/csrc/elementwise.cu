@@ -122,8 +122,8 @@ __global__ void ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, int6
 // grid (nchunk, batch), block D/8 threads.  RGT rows are processed together; MAXT bounds the block size so that the
 // register file holds it: <4, 512> (128 registers, D <= 4096: Flux / Qwen 3072) and <2, 1024> (64 registers, D <= 8192:
 // Wan 5120 = 640 threads, which 128 registers per thread do not fit).
-template <int RGT, int MAXT>
-__global__ void __launch_bounds__(MAXT) ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, int64_t lddxn,
+template <int RGT, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dxn, int64_t lddxn,
                                        const __nv_bfloat16* __restrict__ x, int64_t ldx,
                                        const __nv_bfloat16* __restrict__ scale, int64_t mod_stride,
                                        const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(MAXT) ln_modulate_bwd_kernel(const __nv_bfloat
   for (int r0 = rbeg; r0 < rbeg + ROW_CHUNK; r0 += RGT) {
     float g[RGT][8], xh[RGT][8], rs[RGT];
     float sums[2 * RGT];
+    uint4 rraw[RGT];
 #pragma unroll
     for (int i = 0; i < RGT; ++i) {
       const int r = r0 + i;
@@ -153,8 +154,13 @@ __global__ void __launch_bounds__(MAXT) ln_modulate_bwd_kernel(const __nv_bfloat
       if (r < rows_per_batch) {
         const int64_t row = (int64_t)b * rows_per_batch + r;
         float xv[8], dv[8];
-        unpack8(*reinterpret_cast<const uint4*>(x + row * ldx + col), xv);
-        unpack8(*reinterpret_cast<const uint4*>(dxn + row * lddxn + col), dv);
+        // all three inputs of the row are requested before the block reduction (r2: the residual gradient used to be loaded
+        // after it, a third serialised DRAM latency per row group in a kernel that runs at 1-2 CTAs per SM)
+        const uint4 xraw = *reinterpret_cast<const uint4*>(x + row * ldx + col);
+        const uint4 draw = *reinterpret_cast<const uint4*>(dxn + row * lddxn + col);
+        if (dres) rraw[i] = *reinterpret_cast<const uint4*>(dres + row * lddres + col);
+        unpack8(xraw, xv);
+        unpack8(draw, dv);
         const float m = mean_in[row];
         rs[i] = rstd_in[row];
 #pragma unroll
@@ -184,7 +190,7 @@ __global__ void __launch_bounds__(MAXT) ln_modulate_bwd_kernel(const __nv_bfloat
       for (int j = 0; j < 8; ++j) o[j] = rs[i] * (g[i][j] - m1 - xh[i][j] * m2);
       if (dres) {
         float rv[8];
-        unpack8(*reinterpret_cast<const uint4*>(dres + row * lddres + col), rv);
+        unpack8(rraw[i], rv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] += rv[j];
       }
@@ -292,7 +298,7 @@ __global__ void colreduce_finish_kernel(const float* __restrict__ partials, int 
 // One warp walks the tokens of one (sample, head, which in {q,k,v}) slice; each lane owns 4 of the 128 channels.
 // grid (ceil(rows_per_batch / TOK_PER_WARP / warps), heads*3, batch)
 // ---------------------------------------------------------------------------------------------
-constexpr int QK_TOK_PER_WARP = 128;
+constexpr int QK_TOK_PER_WARP = 32;    // (r2: 128 left 17 warps per SM in flight: 0.35 of the HBM peak under ncu)
 struct QkBwdParams {
   const __nv_bfloat16 *dq, *dk, *dv;      // [B,H,seq_total,128]
   const __nv_bfloat16 *qhat, *khat;       // [B,H,seq_total,128]
@@ -481,14 +487,17 @@ extern "C" int dpipe_ln_modulate_bwd_ex(const void* dxn, int64_t lddxn, const vo
   if (rc) return rc;
   if (!dxn || !x || !scale || !mean || !rstd || !dx || !partials) return fail(DPIPE_EINVAL, "dpipe_ln_modulate_bwd: null pointer");
   dim3 grid((rows_per_batch + ROW_CHUNK - 1) / ROW_CHUNK, batch);
-  if (D <= 4096)
-    ln_modulate_bwd_kernel<4, 512><<<grid, D / 8, 0, (cudaStream_t)stream>>>(
-        (const bf16*)dxn, lddxn, (const bf16*)x, ldx, (const bf16*)scale, mod_stride, mean, rstd, (const bf16*)dres, lddres,
-        (bf16*)dx, lddx, partials, rows_per_batch, D, flags);
-  else
-    ln_modulate_bwd_kernel<2, 1024><<<grid, D / 8, 0, (cudaStream_t)stream>>>(
-        (const bf16*)dxn, lddxn, (const bf16*)x, ldx, (const bf16*)scale, mod_stride, mean, rstd, (const bf16*)dres, lddres,
-        (bf16*)dx, lddx, partials, rows_per_batch, D, flags);
+#define DPIPE_LN_BWD_LAUNCH(RGT, MAXT, MINB)                                                                                     \
+  ln_modulate_bwd_kernel<RGT, MAXT, MINB><<<grid, D / 8, 0, (cudaStream_t)stream>>>(                                             \
+      (const bf16*)dxn, lddxn, (const bf16*)x, ldx, (const bf16*)scale, mod_stride, mean, rstd, (const bf16*)dres, lddres,       \
+      (bf16*)dx, lddx, partials, rows_per_batch, D, flags)
+  // block = D / 8 threads; the register cap follows the block size so that D = 3072 (Flux / Qwen) runs TWO 384-thread CTAs per
+  // SM at <= 85 registers and D = 5120 (Wan) one 640-thread CTA at <= 102 (r2: 1 CTA / SM and 0.2 of the HBM peak under ncu)
+  if (D <= 3072) DPIPE_LN_BWD_LAUNCH(2, 384, 2);
+  else if (D <= 4096) DPIPE_LN_BWD_LAUNCH(2, 512, 1);
+  else if (D <= 5120) DPIPE_LN_BWD_LAUNCH(2, 640, 1);
+  else DPIPE_LN_BWD_LAUNCH(2, 1024, 1);
+#undef DPIPE_LN_BWD_LAUNCH
   DPIPE_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -54,6 +54,9 @@ def launch_list():
 
 
 WANT = ['gpu__time_duration.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+        'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'launch__registers_per_thread', 'launch__grid_size',
         'launch__cluster_dim_x', 'sm__warps_active.avg.pct_of_peak_sustained_active',
@@ -63,10 +66,10 @@ WANT = ['gpu__time_duration.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak
 def full_captures():
     rows_out = []
     for fn in sorted(os.listdir(SRC)):
-        if not (fn.endswith('.ncu-rep') and R in fn):
+        if not (fn.startswith('prof_') and fn.endswith(f'_{R}.csv')) or 'elementwise' in fn:
             continue
-        p = subprocess.run(['ncu', '-i', os.path.join(SRC, fn), '--page', 'raw', '--csv'], capture_output=True, text=True)
-        rd = list(csv.reader(p.stdout.splitlines()))
+        with open(os.path.join(SRC, fn)) as fh:
+            rd = list(csv.reader(fh.read().splitlines()))
         if len(rd) < 3:
             continue
         hdr, units = rd[0], rd[1]
@@ -94,15 +97,15 @@ def hbm_table():
     peak (MEASURED_PEAKS.json hbm_gbs), and the algorithmic bytes of the shape (1 double + 1 single block, L = 4608 = 4096
     image + 512 text tokens, D = 3072, 24 heads) where the kernel name and grid identify it."""
     import json
-    fn = os.path.join(SRC, f'prof_elementwise_{R}.ncu-rep')
+    fn = os.path.join(SRC, f'prof_elementwise_{R}.csv')
     if not os.path.exists(fn):
         return
     try:
         peak = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']
     except Exception:
         peak = 6650.0
-    p = subprocess.run(['ncu', '-i', fn, '--page', 'raw', '--csv'], capture_output=True, text=True)
-    rd = list(csv.reader(p.stdout.splitlines()))
+    with open(fn) as fh:
+        rd = list(csv.reader(fh.read().splitlines()))
     if len(rd) < 3:
         return
     hdr, units = rd[0], rd[1]
