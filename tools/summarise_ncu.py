@@ -139,11 +139,31 @@ def hbm_table():
         f.write(f'Achieved = (dram__bytes_read.sum + dram__bytes_write.sum) / gpu__time_duration.sum per launch, against the measured copy\n'
                 f'peak of this pool ({peak:.1f} GB/s, MEASURED_PEAKS.json).  Launches of one kernel with the same grid are averaged.  Under ncu\n'
                 f'every launch starts with a cold L2 and runs alone; inputs a neighbouring kernel left in the 126 MB L2 show up here as DRAM reads.\n\n')
-        f.write('| kernel | grid | launches | avg us | DRAM read MB | DRAM write MB | GB/s | of HBM peak | ncu dram % |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|\n')
+        # algorithmic bytes (read + written, MB) of the launches that the kernel name and grid identify in the 1 + 1 block Flux
+        # model: L = 4608 joint / 4096 image / 512 text rows, D = 3072 (28.3 / 25.2 / 3.1 MB per bf16 [rows, D] matrix)
+        algo = {('ln_modulate_bwd_kernel', '288'): (4 * 28.3 + 7.1, 'dxn, x, dres in; dx + column partials out (single block)'),
+                ('ln_modulate_bwd_kernel', '256'): (4 * 25.2 + 6.3, 'image stream of the double block'),
+                ('ln_modulate_bwd_kernel', '32'): (4 * 3.1 + 0.8, 'text stream'),
+                ('qknorm_rope_bwd_kernel', '648'): (5 * 28.3 + 3 * 28.3, 'dq, dk, dv, q-hat, k-hat in; token-major dqkv out (24 heads x 4608)'),
+                ('qknorm_rope_bwd_kernel', '576'): (8 * 25.2, 'image stream'),
+                ('qknorm_rope_bwd_kernel', '72'): (8 * 3.1, 'text stream'),
+                ('gate_bwd_kernel', '256'): (3 * 25.2 + 6.3, 'dx, y in; dy + partials out'),
+                ('gate_bwd_kernel', '32'): (3 * 3.1 + 0.8, 'text stream'),
+                ('colsum_kernel', '864'): (113.2, 'MLP half of d linear1: [4608, 12288] bf16 in'),
+                ('colsum_kernel', '768'): (100.7, '[4096, 12288] bf16 in'),
+                ('colsum_kernel', '96'): (12.6, '[512, 12288] bf16 in'),
+                ('mod_bwd_kernel', '144'): (56.6 + 56.6, 'W [9216, 3072] in, dW out (first micro-batch: no dW read)'),
+                ('mod_bwd_kernel', '288'): (113.2 + 113.2, 'W [18432, 3072] in, dW out'),
+                ('attn_bwd_delta_kernel', '13824'): (2 * 28.3, 'O and dO rows in, D out')}
+        f.write('| kernel | grid | launches | avg us | DRAM read MB | DRAM write MB | algorithmic MB | GB/s | of HBM peak | ncu dram % |\n|---|---:|---:|---:|---:|---:|---|---:|---:|---:|\n')
         for (name, grid), d in agg.items():
             n, t, rb, wb, pct = d
             gbs = (rb + wb) / t / 1e9
-            f.write(f'| `{name}` | {grid} | {n} | {t / n * 1e6:.1f} | {rb / n / 1e6:.1f} | {wb / n / 1e6:.1f} | {gbs:.0f} | {gbs / peak:.2f} | {pct / n:.0f} |\n')
+            a = algo.get((name, str(grid)))
+            atxt = f'{a[0]:.0f} ({a[1]})' if a else ''
+            f.write(f'| `{name}` | {grid} | {n} | {t / n * 1e6:.1f} | {rb / n / 1e6:.1f} | {wb / n / 1e6:.1f} | {atxt} | {gbs:.0f} | {gbs / peak:.2f} | {pct / n:.0f} |\n')
+        f.write('\nDRAM writes below the algorithmic output size mean the capture ended with the output still in the 126 MB L2 (write-back '
+                'happens under the next kernel); reads match the algorithmic input bytes — none of these kernels re-reads its inputs.\n')
 
 
 launch_list()
