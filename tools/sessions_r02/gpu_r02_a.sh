@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call A (1 GPU): new parity tests first, then the whole GPU suite, attention-backward A/B, a short bench.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 exec 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call B (1 GPU): C++ stage executor on the 1-GPU link tests, attention kernels with packed fp32 math.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 exec 2>&1
 echo "=== link / attention / block tests"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call C (1 GPU): stage executor tests with full logs; ncu source-level captures of the attention kernels
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 exec 2>&1
 echo "=== link tests"

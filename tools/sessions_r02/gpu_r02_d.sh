@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call D (1 GPU): dq4 kernel (Q / dO in TMEM) correctness + A/B, family smoke runs of bench.py
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 exec 2>&1
 echo "=== attention tests"

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, GPU call E (2 GPUs): multi-GPU parity tests over NVLink (C++ executor + IpcLink, DistLink), Flux pp2,
 # Qwen data-parallel x2 (NCCL gradient all-reduce overlapped with the backward pass) and Qwen pp2
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 exec 2>&1
 nvidia-smi --query-gpu=index,name --format=csv,noheader

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call G (8 GPUs): BASELINE.json configs[2] (Flux pp8), configs[3] (Wan2.1-14B pp8), configs[4] (Qwen pp2 x dp4)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 exec 2>&1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, GPU call H (1 GPU): dK/dV v3 kernel check + A/B, ncu evidence (launch list, full captures, HBM kernels), the whole
 # GPU suite, and a clean 1-GPU bench line
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 exec 2>&1
 echo "=== dkv3 (DPIPE_ATTN_BWD=5): tests + A/B"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call I (1 GPU): ncu evidence (sized to travel back) + dK/dV v2 vs v3 A/B; the summary is printed LAST
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 exec 2>&1
 bash tools/profile_ncu.sh r02 > gpurun_out/r02i_profile.log 2>&1

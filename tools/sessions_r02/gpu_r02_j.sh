@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call J (1 GPU): LayerNorm-backward / qk-norm-backward occupancy changes + dK/dV v3 as default candidate
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 exec 2>&1
 timeout 400 python -m pytest tests/test_kernels_gpu.py tests/test_flux_blocks_gpu.py tests/test_flux_e2e_gpu.py tests/test_wan_gpu.py tests/test_qwen_gpu.py -m gpu -q -x 2>&1 | tail -3 > gpurun_out/r02j_t4.log
