@@ -45,3 +45,36 @@ def test_in_place_broadcast_moves_the_parameter_version():
         assert p._version > v0
     finally:
         torch.distributed.destroy_process_group()
+
+
+def test_deferred_scalars_log_the_same_values_one_step_later():
+    """train.py: the per-step `.item()` is replaced by an asynchronous copy that is written to the log after the
+    next step has been enqueued — same tags, values and x axis, in order; flush() drains everything."""
+    import train
+    seen = []
+    sc = train.DeferredScalars(lambda tag, value, x: seen.append((tag, round(float(value), 6), x)))
+    sc.push('train/loss', torch.tensor(1.5), 1)
+    sc.push('train/grad_norm', 0.25, 1)
+    assert seen == []                                   # nothing is written in the step that produced it
+    sc.flush(keep=0)
+    sc.push('train/loss', torch.tensor(1.25), 2)
+    assert seen == [('train/loss', 1.5, 1), ('train/grad_norm', 0.25, 1)]
+    sc.flush(keep=1)
+    assert len(seen) == 2
+    sc.flush(keep=0)
+    assert seen[-1] == ('train/loss', 1.25, 2) and sc.pending == []
+
+
+def test_clip_sees_every_gradient_byte_once_through_fused_buffers():
+    """engine._clip_grad_norm sums the fused gradient allocation behind per-projection views once (flux_blocks.FusedParam) and
+    falls back to the per-tensor path when the views do not cover it"""
+    from diffusion_pipe_b200.pipe.engine import PipelineEngine as E
+    base = torch.arange(12, dtype=torch.float32)
+    a, b = torch.nn.Parameter(torch.zeros(2, 3)), torch.nn.Parameter(torch.zeros(2, 3))
+    a.grad, b.grad = base[:6].view(2, 3), base[6:].view(2, 3)
+    c = torch.nn.Parameter(torch.zeros(4))
+    c.grad = torch.ones(4)
+    bufs = E._unique_grad_buffers([a, b, c])
+    assert len(bufs) == 2 and bufs[0].data_ptr() == base.data_ptr() and bufs[0].numel() == 12
+    assert E._fused_views_cover([a, b, c], bufs)
+    assert not E._fused_views_cover([a, c], E._unique_grad_buffers([a, c]))      # half of the fused buffer is not a gradient here
