@@ -36,6 +36,9 @@ def test_config_defaults_and_batch_tables():
     ds, mbs = T.make_ds_config(cfg)
     assert ds == {'train_micro_batch_size_per_gpu': 1, 'gradient_accumulation_steps': 4, 'gradient_clipping': 1.0,
                   'steps_per_print': 1}
+    # the engine keys this repo adds to the TOML surface reach the engine config; absent keys add nothing
+    ds2, _ = T.make_ds_config(dict(cfg, pipeline_schedule='zb', stage_link='dist', zb_max_inflight=6, dp_overlap=False))
+    assert ds2['pipeline_schedule'] == 'zb' and ds2['stage_link'] == 'dist' and ds2['zb_max_inflight'] == 6 and ds2['dp_overlap'] is False
     assert T.batch_size_table([[512, 4], [1024, 1]], {None: 1}) == {512: 4, 1024: 1}
     assert T.batch_size_table(None, {None: 3}) == {None: 3}
     with pytest.raises(AssertionError):

@@ -121,12 +121,17 @@ def batch_size_table(v, default):
 def make_ds_config(config):
     mbs = batch_size_table(config.get('micro_batch_size_per_gpu', 1), {None: 1})
     gradient_release = config['optimizer'].get('gradient_release', False)
-    return {
+    ds_config = {
         'train_micro_batch_size_per_gpu': list(mbs.values())[0],
         'gradient_accumulation_steps': config.get('gradient_accumulation_steps', 1),
         'gradient_clipping': 0. if gradient_release else config.get('gradient_clipping', 1.0),
         'steps_per_print': config.get('steps_per_print', 1),
-    }, mbs
+    }
+    # engine keys of this repo (not in the reference's TOML surface): passed through when present
+    for key in ('pipeline_schedule', 'stage_link', 'zb_max_inflight', 'zb_costs', 'zb_stage_weights', 'dp_overlap'):
+        if key in config:
+            ds_config[key] = config[key]
+    return ds_config, mbs
 
 
 # ---------------------------------------------------------------------------------------------------------------------
