@@ -403,6 +403,33 @@ def time_balanced_split(n_double, n_single, stages, t_double, t_single, micro_ba
     return list(parts[1:-1]), per_time, per_blocks
 
 
+def split_from_probe(t, n_double, n_single, stages, micro_batches, max_inflight):
+    """t = [double total, single total, double F, B, W, single F, B, W] in ms, the element-wise minimum of every rank's probe
+    (inf where no rank measured).  Returns (split, blocks per stage, planner stage weights, planner F:B:W costs, description);
+    a ratio outside the plausible band, or no measurement at all, falls back to the calibrated constants."""
+    import math
+    t = list(t)
+    finite = all(math.isfinite(x) and x > 0 for x in t)
+    ratio = t[0] / t[1] if finite else float('nan')
+    probe_ok = finite and PLAUSIBLE_DOUBLE_OVER_SINGLE[0] <= ratio <= PLAUSIBLE_DOUBLE_OVER_SINGLE[1]
+    if not finite:                 # no rank measured anything: nominal times (only their ratio matters below)
+        f_, b_, w_ = (x / 100.0 for x in CALIBRATED_FBW)
+        t = [0.0, 4.0] + [4.0 * CALIBRATED_DOUBLE_OVER_SINGLE * x for x in (f_, b_, w_)] + [4.0 * x for x in (f_, b_, w_)]
+    if not probe_ok:
+        t[0] = CALIBRATED_DOUBLE_OVER_SINGLE * t[1]
+    tf, tb, tw = (n_double * t[2 + i] + n_single * t[5 + i] for i in range(3))
+    zb_costs = tuple(max(1, int(round(100.0 * x / (tf + tb + tw)))) for x in (tf, tb, tw))     # measured F : B : W shares
+    if not probe_ok or any(abs(c - ref) > 0.35 * ref for c, ref in zip(zb_costs, CALIBRATED_FBW)):
+        zb_costs = CALIBRATED_FBW
+    split, stage_ms, blocks_per_stage = time_balanced_split(n_double, n_single, stages, t[0], t[1], micro_batches, zb_costs, max_inflight)
+    stage_weights = [max(1, int(round(100 * x))) for x in stage_ms]
+    desc = {'method': 'measured block times, contiguous min-max' if probe_ok else
+            f'calibrated block-time ratio {CALIBRATED_DOUBLE_OVER_SINGLE} (the probe measured {ratio:.2f}: implausible or failed)',
+            'double_ms': round(t[0], 3), 'single_ms': round(t[1], 3), 'double_over_single': round(t[0] / t[1], 3),
+            'blocks_per_stage': blocks_per_stage, 'stage_ms_per_micro_batch': [round(x, 2) for x in stage_ms]}
+    return split, blocks_per_stage, stage_weights, zb_costs, desc
+
+
 def build_family(a, device):
     """(model, layers, example-batch maker or None, workload string, n_blocks)"""
     import torch
@@ -484,26 +511,18 @@ def main():
     if a.family == 'flux':
         n_double, n_single = (int(x) for x in a.layers.split(','))
         if stages > 1 and a.partition == 'time' and n_double and n_single:
-            probe = probe_block_times(device, a.res, a.text_len)
-            t = torch.tensor([sum(probe['double']), sum(probe['single'])] + list(probe['double']) + list(probe['single']),
-                             device=device, dtype=torch.float64)
+            try:
+                probe = probe_block_times(device, a.res, a.text_len)
+                vals = [sum(probe['double']), sum(probe['single'])] + list(probe['double']) + list(probe['single'])
+            except Exception as exc:       # a failed probe on one rank must not take the run down: the other ranks' numbers decide
+                print(f'[rank {rank}] block-time probe failed: {exc!r}', file=sys.stderr, flush=True)
+                probe, vals = None, [float('inf')] * 8
+                torch.cuda.empty_cache()
+            t = torch.tensor(vals, device=device, dtype=torch.float64)
             tdist.all_reduce(t, op=tdist.ReduceOp.MIN)   # every rank must derive the same split: the least disturbed measurement
             t = t.tolist()
-            ratio = t[0] / t[1]
-            probe_ok = PLAUSIBLE_DOUBLE_OVER_SINGLE[0] <= ratio <= PLAUSIBLE_DOUBLE_OVER_SINGLE[1]
-            if not probe_ok:
-                t[0] = CALIBRATED_DOUBLE_OVER_SINGLE * t[1]
-            tf, tb, tw = (n_double * t[2 + i] + n_single * t[5 + i] for i in range(3))
-            zb_costs = tuple(max(1, int(round(100.0 * x / (tf + tb + tw)))) for x in (tf, tb, tw))     # measured F : B : W shares
-            if not probe_ok or any(abs(c - ref) > 0.35 * ref for c, ref in zip(zb_costs, CALIBRATED_FBW)):
-                zb_costs = CALIBRATED_FBW
-            split, stage_ms, blocks_per_stage = time_balanced_split(n_double, n_single, stages, t[0], t[1], M, zb_costs, a.max_inflight)
-            stage_weights = [max(1, int(round(100 * x))) for x in stage_ms]
-            partition_desc = {'method': 'measured block times, contiguous min-max' if probe_ok else
-                              f'calibrated block-time ratio {CALIBRATED_DOUBLE_OVER_SINGLE} (the probe measured {ratio:.2f}: implausible)',
-                              'double_ms': round(t[0], 3), 'single_ms': round(t[1], 3),
-                              'double_over_single': round(t[0] / t[1], 3), 'blocks_per_stage': blocks_per_stage,
-                              'stage_ms_per_micro_batch': [round(x, 2) for x in stage_ms]}
+            split, blocks_per_stage, stage_weights, zb_costs, partition_desc = split_from_probe(
+                t, n_double, n_single, stages, M, a.max_inflight)
         else:
             split, blocks_per_stage = flop_balanced_split(n_double, n_single, stages)
             stage_weights = [max(1, b) for b in blocks_per_stage]

@@ -59,3 +59,18 @@ def test_reference_arm_is_rank0_only_and_bounded(monkeypatch):
     assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] == 8 and len(line['cpu_baseline']['min_max']) == 2
     assert line['e2e'] == {'value': line['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert line['metric'].startswith('training samples/sec')
+
+
+def test_split_from_probe_falls_back_when_the_measurement_is_implausible_or_missing():
+    import bench
+    good = [4.9, 3.71, 1.455, 2.529, 0.957, 1.137, 1.774, 0.761]                  # the 8-GPU run of round 2
+    split, blocks, weights, costs, desc = bench.split_from_probe(good, 19, 38, 8, 16, 0)
+    assert blocks == [6, 6, 6, 7, 8, 8, 8, 8] and desc['method'].startswith('measured') and len(weights) == 8
+    assert abs(sum(costs) - 100) <= 2 and all(abs(c - r) <= 0.35 * r for c, r in zip(costs, bench.CALIBRATED_FBW))
+    bad = [9.476, 3.576, 3.121, 4.831, 0.953, 1.109, 1.71, 0.74]                  # the disturbed 2-GPU probe: 2.65x
+    split, blocks, weights, costs, desc = bench.split_from_probe(bad, 19, 38, 2, 16, 0)
+    assert blocks == [26, 31] and costs == bench.CALIBRATED_FBW and 'calibrated' in desc['method']
+    assert desc['double_over_single'] == bench.CALIBRATED_DOUBLE_OVER_SINGLE
+    none = [float('inf')] * 8                                                     # every rank's probe failed
+    split, blocks, weights, costs, desc = bench.split_from_probe(none, 19, 38, 4, 16, 0)
+    assert sum(blocks) == 57 and costs == bench.CALIBRATED_FBW and all(w >= 1 for w in weights)
