@@ -547,10 +547,13 @@ class PipelineEngine:
         run under the backward passes of the layers still to come (utils/patches.py:152-156 reduces after the drain)."""
         params = []
         for i in range(first, last):
-            if i in self._dp_reduced_layers:
-                continue
-            self._dp_reduced_layers.add(i)
-            self.dp_early_layers += int(early)
+            if early:
+                if i in self._dp_reduced_layers:
+                    continue
+                self._dp_reduced_layers.add(i)
+                self.dp_early_layers += 1
+            # (the final pass looks at every layer again: a gradient that did not exist yet when the layer's callback ran is
+            # picked up here; what has been reduced is remembered per buffer, not per layer)
             f = self.module.forward_funcs[i]
             if isinstance(f, torch.nn.Module):
                 params += [p for p in f.parameters() if p.requires_grad and p.grad is not None]

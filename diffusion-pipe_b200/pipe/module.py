@@ -6,6 +6,7 @@ reference: utils/pipeline.py:11-53 on top of deepspeed.pipe.PipelineModule).
 Rank layout follows DeepSpeed's PipeDataParallelTopology(axes=['pipe','data']): global_rank = stage * dp + dp_rank.
 """
 import ctypes
+import functools
 import re
 
 import torch
@@ -137,6 +138,23 @@ def partition_balanced(weights, num_parts):
     return list(b)
 
 
+class _GradsReady(torch.autograd.Function):
+    """Identity on a layer's inputs (aliases, no copy).  Its backward runs when the gradients of ALL its outputs are
+    complete, i.e. after every backward node of the layer(s) consuming them has been launched; it calls back and hands the
+    gradients on untouched.  See PipelineModule._arm_grads_ready."""
+
+    @staticmethod
+    def forward(ctx, cb, first, last, *xs):
+        ctx.cb, ctx.span = cb, (first, last)
+        ctx.set_materialize_grads(False)
+        return tuple(t.view_as(t) for t in xs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        ctx.cb(*ctx.span)
+        return (None, None, None) + grads
+
+
 class PipelineModule(nn.Module):
     def __init__(self, layers, num_stages=None, topology=None, loss_fn=None, seed_layers=False, seed_fn=None,
                  base_seed=1234, partition_method='parameters', activation_checkpoint_interval=0,
@@ -147,7 +165,9 @@ class PipelineModule(nn.Module):
         self.loss_fn = loss_fn
         self.checkpointable_layers = checkpointable_layers
         self.activation_checkpoint_interval = activation_checkpoint_interval
-        self.activation_checkpoint_func = activation_checkpoint_func or torch.utils.checkpoint.checkpoint
+        # default: the re-entrant form, like DeepSpeed's checkpointing.checkpoint (train.py passes its own, train.py:588-603)
+        self.activation_checkpoint_func = activation_checkpoint_func or functools.partial(torch.utils.checkpoint.checkpoint,
+                                                                                          use_reentrant=True)
         self.dynamic_shape = dynamic_shape
         self.global_rank = dist.get_rank()
         self.world_size = dist.get_world_size()
@@ -266,20 +286,24 @@ class PipelineModule(nn.Module):
 
     @staticmethod
     def _arm_grads_ready(x, first, last, cb):
-        """calls cb(first, last) once the gradient of EVERY input of layers [first, last) that takes part in autograd has
-        been computed: from then on no kernel of these layers' backward is still to be launched, so their parameter
-        gradients are final for this micro-batch (the engine starts their data-parallel all-reduce, pipe/engine.py)"""
-        ts = [t for t in (x if isinstance(x, (tuple, list)) else (x,)) if torch.is_tensor(t) and t.requires_grad]
-        if not ts:
-            return
-        left = [len(ts)]
+        """Returns x with every tensor that takes part in autograd passed through `_GradsReady`: cb(first, last) runs in the
+        backward pass as soon as the gradient of every input of layers [first, last) is complete — from then on no kernel
+        of these layers' backward is still to be launched, so their parameter gradients are final for this micro-batch
+        (the engine starts their data-parallel all-reduce, pipe/engine.py).
 
-        def hook(_grad):
-            left[0] -= 1
-            if left[0] == 0:
-                cb(first, last)
-        for t in ts:
-            t.register_hook(hook)
+        Why not tensor hooks on x itself: a tensor the layers hand through unchanged (the time embedding, the text stream
+        of the single blocks) is ONE autograd tensor consumed by every layer after it; its gradient — and with it a hook
+        on it — completes only when the FIRST of these layers has run its backward, i.e. when nothing is left to overlap
+        with.  The marker gives each layer its own aliases, whose only consumers are that layer and the next marker."""
+        single = not isinstance(x, (tuple, list))
+        xs = [x] if single else list(x)
+        idx = [k for k, t in enumerate(xs) if torch.is_tensor(t) and t.requires_grad]
+        if not idx:
+            return x
+        marked = _GradsReady.apply(cb, first, last, *[xs[k] for k in idx])
+        for k, m in zip(idx, marked):
+            xs[k] = m
+        return xs[0] if single else tuple(xs)
 
     def forward(self, forward_input):
         x = forward_input
@@ -288,14 +312,14 @@ class PipelineModule(nn.Module):
         if interval == 0 or not torch.is_grad_enabled():
             for i, f in enumerate(self.forward_funcs):
                 if ready_cb is not None:
-                    self._arm_grads_ready(x, i, i + 1, ready_cb)
+                    x = self._arm_grads_ready(x, i, i + 1, ready_cb)
                 x = f(x)
             return x
         n = len(self.forward_funcs)
         for start in range(0, n, interval):
             funcs = self.forward_funcs[start:min(start + interval, n)]
             if ready_cb is not None:
-                self._arm_grads_ready(x, start, min(start + interval, n), ready_cb)
+                x = self._arm_grads_ready(x, start, min(start + interval, n), ready_cb)
 
             def run(*inputs, _funcs=funcs):
                 y = inputs if len(inputs) > 1 else inputs[0]

@@ -198,3 +198,82 @@ def test_changed_boundary_shapes_without_reset_are_refused():
     with tempfile.TemporaryDirectory() as d:
         with pytest.raises(Exception, match='reset_activation_shape'):
             mp.spawn(_worker_shape_change, args=(2, _free_port(), d), nprocs=2, join=True)
+
+
+def _passthrough_stack(n=4):
+    """layers of the shape every model definition of the reference has: a stream that each layer rewrites and a tensor that
+    every layer reads and hands on UNCHANGED (the time embedding: models/flux.py:497-533, qwen_image.py:519-605)"""
+    events = []
+
+    class Layer(torch.nn.Module):
+        def __init__(self, i):
+            super().__init__()
+            self.i, self.lin, self.mod = i, torch.nn.Linear(4, 4), torch.nn.Linear(4, 4)
+
+        def forward(self, x):
+            h, temb = x
+            layer = self
+
+            class Tap(torch.autograd.Function):
+                @staticmethod
+                def forward(ctx, a):
+                    return a.clone()
+
+                @staticmethod
+                def backward(ctx, g):
+                    events.append(('backward', layer.i))
+                    return g
+            return Tap.apply(self.lin(h) * self.mod(temb)), temb
+    torch.manual_seed(0)
+    return [Layer(i) for i in range(n)], events
+
+
+def test_grads_ready_callback_runs_right_after_each_layers_backward_despite_a_handed_through_tensor():
+    """A hook on the handed-through tensor itself would complete only after the FIRST layer's backward (its gradient sums
+    over every layer) and every data-parallel all-reduce would start when nothing is left to overlap with."""
+    from diffusion_pipe_b200.pipe.module import PipelineModule
+    layers, events = _passthrough_stack()
+    x = (torch.randn(2, 4, requires_grad=True), torch.randn(2, 4, requires_grad=True))
+    y = x
+    for i, f in enumerate(layers):
+        y = PipelineModule._arm_grads_ready(y, i, i + 1, lambda a, b: events.append(('ready', a)))
+        y = f(y)
+    y[0].sum().backward()
+    assert events == [(k, i) for i in (3, 2, 1, 0) for k in ('backward', 'ready')], events
+    # parameter gradients of a layer exist when its callback runs (AccumulateGrad nodes run before any other ready node)
+    layers, events = _passthrough_stack()
+    seen = {}
+    y = (x[0].detach().requires_grad_(True), x[1].detach().requires_grad_(True))
+    for i, f in enumerate(layers):
+        y = PipelineModule._arm_grads_ready(y, i, i + 1, lambda a, b: seen.setdefault(a, [p.grad is not None for p in layers[a].parameters()]))
+        y = f(y)
+    y[0].sum().backward()
+    assert sorted(seen) == [0, 1, 2, 3] and all(all(v) for v in seen.values()), seen
+
+
+@pytest.mark.parametrize('interval', [0, 2])
+def test_arming_the_callbacks_changes_no_gradient(interval):
+    """the markers are aliases: outputs, input gradients and parameter gradients are bit-identical with and without them,
+    also with activation checkpointing (one marker per checkpointed segment); ints / non-grad tensors pass untouched"""
+    from diffusion_pipe_b200.pipe.module import PipelineModule
+    import toy_model
+    res = []
+    for armed in (False, True):
+        layers = toy_model.make_layers()
+        pm = PipelineModule(layers=layers, num_stages=1, loss_fn=toy_model.loss_fn, activation_checkpoint_interval=interval,
+                            device=torch.device('cpu'))
+        fired = []
+        pm._grads_ready_cb = (lambda a, b: fired.append((a, b))) if armed else None
+        (feats, label), = toy_model.make_micro_batches(1, MBS, seed=7)
+        feats = tuple(t.clone().requires_grad_(t.is_floating_point()) for t in feats)
+        loss = toy_model.loss_fn(pm(feats if len(feats) > 1 else feats[0]), label)
+        loss.backward()
+        res.append((loss.detach(), [t.grad for t in feats if t.is_floating_point()],
+                    {n: p.grad.clone() for n, p in pm.named_parameters() if p.grad is not None}, fired))
+    (l0, g0, p0, f0), (l1, g1, p1, f1) = res
+    assert torch.equal(l0, l1) and not f0 and f1
+    assert len(g0) == len(g1) and all((a is None and b is None) or torch.equal(a, b) for a, b in zip(g0, g1))
+    assert p0.keys() == p1.keys() and all(torch.equal(p0[k], p1[k]) for k in p0)
+    spans = sorted(f1)
+    n = len(pm.forward_funcs)
+    assert spans[0][0] <= 1 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans, spans[1:])), spans
