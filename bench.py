@@ -742,10 +742,16 @@ def main():
     if rank == 0 and world == 1 and not a.no_cpu_baseline and a.family == 'flux':
         del dev_batches, host_batches
         n_double, n_single = (int(x) for x in a.layers.split(','))
-        vals = [cpu_reference_sample(a.res, a.text_len, n_double, n_single) for _ in range(3)]
-        vs = sorted(v for v, _, _ in vals)
-        cpu = {'value': vs[1], 'unit': 'samples/s', 'cores': vals[0][2], 'kind': 'port',
-               'sample': vals[-1][1] + '; median of 3 samples', 'min_max': [vs[0], vs[-1]]}
+        vals = []
+        try:
+            for _ in range(3):
+                vals.append(cpu_reference_sample(a.res, a.text_len, n_double, n_single))
+        except Exception as exc:          # a baseline sample that fails must not take the measured line down with it
+            print(f'cpu baseline sample failed: {exc!r}', file=sys.stderr, flush=True)
+        if vals:
+            vs = sorted(v for v, _, _ in vals)
+            cpu = {'value': vs[len(vs) // 2], 'unit': 'samples/s', 'cores': vals[0][2], 'kind': 'port',
+                   'sample': vals[-1][1] + f'; median of {len(vs)} sample(s)', 'min_max': [vs[0], vs[-1]]}
 
     link_name, schedule_name = type(engine.link).__name__, engine.pipeline_schedule
 
