@@ -145,3 +145,9 @@ def test_attention_on_more_shapes(shape):
     import test_kernels_gpu as KT
     from diffusion_pipe_b200 import ops
     KT.test_attention_forward_backward(ops, shape)
+
+
+# ---- 5. the driver's own smoke entry point (same call the round-end check makes, so a break shows up in the test log too) ----
+def test_graft_entry_smoke_runs():
+    import __graft_entry__ as entry
+    entry.smoke()
