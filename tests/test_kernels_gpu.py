@@ -117,7 +117,7 @@ def test_attention_rescale_path(ops):
     _check(lse * math.log(2.0), lseref, 1e-3)
 
 
-@pytest.mark.parametrize('D', [512, 5120])      # 5120 = Wan-14B width: 640-thread CTAs take the <2, 1024> backward variant
+@pytest.mark.parametrize('D', [512, 5120])      # 5120 = Wan-14B width: 640-thread CTAs, the <2, 640, 1> backward variant (512 -> <2, 384, 2>)
 def test_ln_modulate_and_gate_backward(ops, D):
     torch.manual_seed(5)
     B, L = 2, 50
