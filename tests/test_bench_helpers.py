@@ -74,3 +74,28 @@ def test_split_from_probe_falls_back_when_the_measurement_is_implausible_or_miss
     none = [float('inf')] * 8                                                     # every rank's probe failed
     split, blocks, weights, costs, desc = bench.split_from_probe(none, 19, 38, 4, 16, 0)
     assert sum(blocks) == 57 and costs == bench.CALIBRATED_FBW and all(w >= 1 for w in weights)
+
+
+def test_the_orders_the_scaling_run_will_execute_are_complete_and_deadlock_free():
+    """exactly what `bench.py --gpus N` hands to the engine for N = 3, 4, 8 (zero-bubble order, per-stage weights and F:B:W
+    costs from the block-time probe or from the calibrated fallback; N = 2 runs the reference's 1F1B order)"""
+    import bench
+    from diffusion_pipe_b200.pipe.schedule import ZeroBubbleSchedule
+    good = [4.9, 3.71, 1.455, 2.529, 0.957, 1.137, 1.774, 0.761]
+    for probe in (good, [float('inf')] * 8):
+        for stages in (3, 4, 8):
+            _split, blocks, weights, costs, _ = bench.split_from_probe(probe, 19, 38, stages, 16, 0)
+            assert sum(blocks) == 57 and len(weights) == stages
+            for st in range(stages):
+                seq = [(c.name, getattr(c, 'micro_batch_id', None))
+                       for t in ZeroBubbleSchedule(16, stages, st, costs, None, weights).steps() for c in t]
+                for kind in ('ForwardPass', 'BackwardInput', 'BackwardWeight'):
+                    assert [mb for n, mb in seq if n == kind] == list(range(16)), (stages, st, kind)
+                held = peak = 0
+                for n, _ in seq:
+                    held += (n == 'ForwardPass') - (n == 'BackwardWeight')
+                    peak = max(peak, held)
+                assert peak <= 2 * stages, (stages, st, peak)          # IpcLink sizes its mailboxes for 2 x stages slots
+            ms = ZeroBubbleSchedule(16, stages, 0, costs, None, weights).simulated_makespan()
+            work = 16 * sum(costs) * max(weights)
+            assert ms > 0 and work / ms > 0.80, (stages, work / ms)     # the joint replay completes; bubble below 20 %
