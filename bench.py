@@ -57,7 +57,7 @@ def parse():
     ap.add_argument('--no-library-baseline', action='store_true',
                     help='skip the cuBLAS + SDPA timing of the restated reference blocks on the GPU (context only, N=1)')
     ap.add_argument('--schedule', default='auto', choices=['auto', '1f1b', 'zb'],
-                    help="pipeline order: the reference's 1F1B or the split-backward zero-bubble order (auto: zb from 3 stages up; at 2 stages the 1F1B bubble is 1/17 of the step and measured no worse)")
+                    help="pipeline order: the reference's 1F1B or the split-backward zero-bubble order (auto: zb whenever there is more than one stage and the stage link is one-sided; the engine itself falls back to 1F1B on torch.distributed p2p links)")
     ap.add_argument('--profile-kernels', action='store_true', default=True)
     ap.add_argument('--family', default='flux', choices=['flux', 'wan', 'qwen'],
                     help='flux = the BASELINE.json metric (configs[1]/[2]); wan = configs[3] (Wan2.1-14B t2v, 33 frames 512^2); '
@@ -503,7 +503,12 @@ def main():
     dp = world // stages
     M, mbs = a.micro_batches, a.micro_batch_size
     fam = FAMILIES[a.family]
-    schedule = ('zb' if stages > 2 else '1f1b') if a.schedule == 'auto' else a.schedule
+    # auto: the split-backward order from 2 stages up.  The planner's replay of the measured-time split (the same C++ code that
+    # predicted the 8-stage gain over 1F1B to within 1.5 %: 1.226x simulated, 1.212x measured) gives 1.97x / 3.72x / 6.83x for
+    # 2 / 4 / 8 stages against the 1F1B bounds 1.88x / 3.37x / 5.57x at 16 micro-batches.
+    # (2 stages x data parallel keeps the reference's 1F1B order, as measured in profiles/r02_qwen_pp2dp4.json: only that
+    # order lets the gradient all-reduce of a layer start under the last backward pass)
+    schedule = ('zb' if stages > 2 or (stages == 2 and dp == 1) else '1f1b') if a.schedule == 'auto' else a.schedule
 
     # ---- stage partition: measured block times (Flux: double vs single), block count otherwise ----
     probe = None

@@ -77,13 +77,13 @@ def test_split_from_probe_falls_back_when_the_measurement_is_implausible_or_miss
 
 
 def test_the_orders_the_scaling_run_will_execute_are_complete_and_deadlock_free():
-    """exactly what `bench.py --gpus N` hands to the engine for N = 3, 4, 8 (zero-bubble order, per-stage weights and F:B:W
-    costs from the block-time probe or from the calibrated fallback; N = 2 runs the reference's 1F1B order)"""
+    """exactly what `bench.py --gpus N` hands to the engine for N = 2, 3, 4, 8 (zero-bubble order, per-stage weights and F:B:W
+    costs from the block-time probe or from the calibrated fallback)"""
     import bench
     from diffusion_pipe_b200.pipe.schedule import ZeroBubbleSchedule
     good = [4.9, 3.71, 1.455, 2.529, 0.957, 1.137, 1.774, 0.761]
     for probe in (good, [float('inf')] * 8):
-        for stages in (3, 4, 8):
+        for stages in (2, 3, 4, 8):
             _split, blocks, weights, costs, _ = bench.split_from_probe(probe, 19, 38, stages, 16, 0)
             assert sum(blocks) == 57 and len(weights) == stages
             for st in range(stages):
