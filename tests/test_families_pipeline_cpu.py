@@ -68,7 +68,7 @@ def _micro_batches(kind, model, n, seed):
     return data_feed.split_batch((feats, label), n)
 
 
-def _worker(rank, world, port, kind, stages, schedule, outdir, gpu=False, link='dist', gas=GAS, save_params=False):
+def _worker(rank, world, port, kind, stages, schedule, outdir, gpu=False, link='dist', gas=GAS, save_params=False, lora=False):
     """gpu=False: CPU + gloo + kernel test doubles;  gpu=True (tests/test_pipeline_multigpu.py): one GPU per rank, NCCL,
     the real kernels and the requested stage link"""
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
@@ -89,6 +89,12 @@ def _worker(rank, world, port, kind, stages, schedule, outdir, gpu=False, link='
         if world > 1:
             dist.init_distributed('gloo')
     model = _make(kind, device)
+    if lora:
+        # adapter factors as a launcher without a common seed leaves them (train.py never seeds): every data-parallel
+        # replica draws its own A at attach time (B starts at zero, models/base.py:272-303); the engine must make all of
+        # them train replica 0's.  Nothing touches the factors between attach and engine construction, as in train.py.
+        torch.manual_seed(1 + (rank % (world // stages)))
+        model.configure_adapter({'type': 'lora', 'rank': 8, 'alpha': 8, 'dropout': 0.0})
     pm = ManualPipelineModule(layers=model.to_layers(), num_stages=stages, partition_method='uniform', manual_partition_split=None,
                               loss_fn=model.get_loss_fn(), dynamic_shape=True, device=device)
     engine, _, _, _ = initialize(model=pm, config={'train_micro_batch_size_per_gpu': 1, 'gradient_accumulation_steps': gas,
@@ -115,20 +121,20 @@ def _worker(rank, world, port, kind, stages, schedule, outdir, gpu=False, link='
         dist.barrier()
 
 
-def _run(kind, stages, schedule, gpu=False, link='dist', dp=1, gas=GAS, save_params=False):
+def _run(kind, stages, schedule, gpu=False, link='dist', dp=1, gas=GAS, save_params=False, lora=False):
     with tempfile.TemporaryDirectory() as d:
         port = _free_port()
         if dp > 1:
             world = stages * dp
-            mp.spawn(_worker, args=(world, port, kind, stages, schedule, d, gpu, link, gas, save_params), nprocs=world, join=True)
+            mp.spawn(_worker, args=(world, port, kind, stages, schedule, d, gpu, link, gas, save_params, lora), nprocs=world, join=True)
             return [torch.load(os.path.join(d, f'rank{r}.pt'), weights_only=False) for r in range(world)]
         if stages == 1 and not gpu:
-            _worker(0, 1, port, kind, 1, schedule, d)
+            _worker(0, 1, port, kind, 1, schedule, d, False, link, gas, save_params, lora)
             import torch.distributed as tdist
             if tdist.is_initialized():
                 tdist.destroy_process_group()
         else:
-            mp.spawn(_worker, args=(stages, port, kind, stages, schedule, d, gpu, link, gas, save_params), nprocs=stages, join=True)
+            mp.spawn(_worker, args=(stages, port, kind, stages, schedule, d, gpu, link, gas, save_params, lora), nprocs=stages, join=True)
         return [torch.load(os.path.join(d, f'rank{r}.pt'), weights_only=False) for r in range(stages)]
 
 
@@ -159,5 +165,23 @@ def test_qwen_two_stages_times_two_replicas_equals_one_pipeline_on_the_same_glob
         for k, v in r['params'].items():
             assert (v - ref[k]).norm() <= 2e-2 * (ref[k].norm() + 1e-6) + 1e-4, k
     # replicas of a stage hold identical parameters after the step
+    for k, v in two[0]['params'].items():
+        assert torch.equal(v, two[1]['params'][k]), k
+
+
+def test_lora_replicas_train_the_first_replicas_factors():
+    """utils/patches.py:163-172 with an adapter: two data-parallel replicas that drew DIFFERENT LoRA factors equal one
+    pipeline holding replica 0's factors on the same global batch — from the first step on (the broadcast reaches the fused
+    [[W|B],[A|0]] site buffers of lora.py, not only the parameter tensors), only adapter parameters move, and both
+    replicas end with identical ones"""
+    one = _run('qwen_image', 1, '1f1b', gas=8, save_params=True, lora=True)[0]
+    two = _run('qwen_image', 1, '1f1b', dp=2, gas=4, save_params=True, lora=True)
+    trained = [k for k in one['params'] if '.lora_' in k]
+    assert trained
+    for r in two:
+        assert r['losses'] == pytest.approx(one['losses'], rel=2e-3), (r['losses'], one['losses'])
+        assert r['norm'] == pytest.approx(one['norm'], rel=2e-2)
+        for k in trained:
+            assert (r['params'][k] - one['params'][k]).norm() <= 2e-2 * (one['params'][k].norm() + 1e-6) + 1e-4, k
     for k, v in two[0]['params'].items():
         assert torch.equal(v, two[1]['params'][k]), k
